@@ -1,0 +1,157 @@
+// HBM-bound cast / column-sum / transpose kernels (vectorised, coalesced; no data reuse -> no tensor cores).
+#include "common.cuh"
+#include "../../include/multimae_b200.h"
+
+namespace mmae {
+void count_launch();
+namespace {
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x * 8;
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    if (i + 8 <= n) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + i + 4));
+      uint4 o;
+      o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+      o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+      *reinterpret_cast<uint4*>(dst + i) = o;
+    } else {
+      for (int64_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+    }
+  }
+}
+
+// Tile: ROWS_PER_BLOCK rows x 128 columns; block (32, 8).  Each thread owns 4 consecutive columns.
+constexpr int CS_ROWS = 64;
+
+template <bool SRC_BF16>
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const void* __restrict__ src_, int64_t ld_src,
+                                                          bf16* __restrict__ dst, int64_t ld_dst,
+                                                          float* __restrict__ colsum, int M, int N) {
+  __shared__ float4 red[8][32];
+  const int col = blockIdx.x * 128 + threadIdx.x * 4;
+  const int r0 = blockIdx.y * CS_ROWS;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < N) {
+#pragma unroll 4
+    for (int r = r0 + threadIdx.y; r < min(r0 + CS_ROWS, M); r += 8) {
+      float4 v;
+      if constexpr (SRC_BF16) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(src_) + int64_t(r) * ld_src + col));
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        v = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src_) + int64_t(r) * ld_src + col));
+        if (dst) {
+          uint2 o;
+          o.x = pack_bf16x2(v.x, v.y);
+          o.y = pack_bf16x2(v.z, v.w);
+          *reinterpret_cast<uint2*>(dst + int64_t(r) * ld_dst + col) = o;
+        }
+      }
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  if (colsum == nullptr) return;
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) {
+      const float4 o = red[y][threadIdx.x];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    atomicAdd(colsum + col + 0, acc.x);
+    atomicAdd(colsum + col + 1, acc.y);
+    atomicAdd(colsum + col + 2, acc.z);
+    atomicAdd(colsum + col + 3, acc.w);
+  }
+}
+
+// 64x64 bf16 tile transpose through padded shared memory; block 256 threads
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restrict__ src, int64_t ld_src,
+                                                             bf16* __restrict__ dst, int64_t ld_dst, int M, int N) {
+  __shared__ bf16 tile[64][66];
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  // load: each thread reads 2 consecutive columns; 32 threads cover 64 columns, 8 row groups
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = ty + i * 8;
+    const int gm = m0 + r, gn = n0 + tx * 2;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+    if (gm < M && gn < N) v = *reinterpret_cast<const __nv_bfloat162*>(src + int64_t(gm) * ld_src + gn);
+    tile[r][tx * 2] = v.x;
+    tile[r][tx * 2 + 1] = v.y;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = ty + i * 8;  // row of the transposed tile = column n
+    const int gn = n0 + r, gm = m0 + tx * 2;
+    if (gn < N && gm < M) {
+      __nv_bfloat162 v;
+      v.x = tile[tx * 2][r];
+      v.y = tile[tx * 2 + 1][r];
+      *reinterpret_cast<__nv_bfloat162*>(dst + int64_t(gn) * ld_dst + gm) = v;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace mmae
+
+using namespace mmae;
+
+extern "C" int mmae_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
+  MMAE_CHECK(src && dst_bf16 && n >= 0, MMAE_ERR_ARG, "mmae_cast_f32_to_bf16: bad args");
+  if (n == 0) return MMAE_OK;
+  MMAE_CHECK((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0,
+             MMAE_ERR_ARG, "mmae_cast_f32_to_bf16: pointers must be 16-byte aligned");
+  const int threads = 256;
+  int64_t blocks = (n / 8 + threads - 1) / threads;
+  const int64_t cap = int64_t(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  cast_f32_bf16_kernel<<<(unsigned)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<bf16*>(dst_bf16), n);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+extern "C" int mmae_cast_colsum_f32(const float* src, int64_t ld_src, void* dst_bf16, int64_t ld_dst, float* colsum,
+                                    int M, int N, void* stream) {
+  MMAE_CHECK(src && M > 0 && N > 0 && N % 4 == 0 && ld_src % 4 == 0 && (!dst_bf16 || ld_dst % 4 == 0), MMAE_ERR_ARG,
+             "mmae_cast_colsum_f32: bad args (N, ld must be multiples of 4)");
+  dim3 grid(ceil_div(N, 128), ceil_div(M, CS_ROWS)), block(32, 8);
+  cast_colsum_kernel<false><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, ld_src, reinterpret_cast<bf16*>(dst_bf16), ld_dst, colsum, M, N);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+extern "C" int mmae_colsum_bf16(const void* src_bf16, int64_t ld_src, float* colsum, int M, int N, void* stream) {
+  MMAE_CHECK(src_bf16 && colsum && M > 0 && N > 0 && N % 4 == 0 && ld_src % 4 == 0, MMAE_ERR_ARG,
+             "mmae_colsum_bf16: bad args");
+  dim3 grid(ceil_div(N, 128), ceil_div(M, CS_ROWS)), block(32, 8);
+  cast_colsum_kernel<true><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src_bf16, ld_src, nullptr, 0,
+                                                                                      colsum, M, N);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+extern "C" int mmae_transpose_bf16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int M, int N,
+                                   void* stream) {
+  MMAE_CHECK(src && dst && M > 0 && N > 0 && M % 2 == 0 && N % 2 == 0 && ld_src % 2 == 0 && ld_dst % 2 == 0,
+             MMAE_ERR_ARG, "mmae_transpose_bf16: bad args");
+  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+  transpose_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(src), ld_src, reinterpret_cast<bf16*>(dst), ld_dst, M, N);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}

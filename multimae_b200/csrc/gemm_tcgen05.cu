@@ -1,0 +1,308 @@
+// tcgen05 / TMA GEMM for sm_100a:  C[M,N] = epilogue(alpha * A * B^T), bf16 operands, fp32 accumulate in TMEM.
+//
+// One CTA computes one 128 x BN output tile over a K range (split-K along gridDim.z).
+//   warp 0     : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1     : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16), tcgen05.commit
+//   warps 2..5 : epilogue       (tcgen05.ld TMEM -> registers -> fused bias/GELU/dGELU/residual -> global)
+// Two CTAs are resident per SM (3-stage ring, 96 KB each), so one CTA's epilogue overlaps the other's mainloop.
+//
+// Replaces the cuBLAS/cuDNN calls behind nn.Linear / nn.Conv2d(k=s=P) on the reference path
+// (multimae/multimae_utils.py:149-153,172,180,203-212; multimae/input_adapters.py:110,232;
+//  multimae/output_adapters.py:258,274) and their autograd dgrad/wgrad.
+#include "common.cuh"
+#include "../../include/multimae_b200.h"
+
+namespace mmae {
+
+void count_launch();
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  int M, N, K;
+  int num_kb;        // total k-blocks (ceil(K / BK))
+  int kb_per_split;  // k-blocks handled by one split
+  mmae_gemm_epilogue ep;
+};
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
+    gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const GemmParams p) {
+  using L = GemmSmem<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;  // power of two >= 32 (BN in {64,128,256})
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * BM;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  int nkb = p.num_kb - kb_begin;
+  if (nkb > p.kb_per_split) nkb = p.kb_per_split;
+  if (nkb < 0) nkb = 0;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        uint8_t* sA = smem + s * L::STAGE_BYTES;
+        uint8_t* sB = sA + L::A_BYTES;
+        const int k0 = (kb_begin + kb) * BK;
+        if constexpr (!A_MN) {
+          tma_load_2d(sA, &tmA, &full_bar[s], k0, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * (64 * BK * 2), &tmA, &full_bar[s], m0 + c * 64, k0);
+        }
+        if constexpr (!B_MN) {
+          tma_load_2d(sB, &tmB, &full_bar[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + c * (64 * BK * 2), &tmB, &full_bar[s], n0 + c * 64, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+        for (int j = 0; j < BK / UMMA_K; ++j) {
+          // K-major : advance 16 elements (32 B) inside the 128 B swizzle row
+          // MN-major: advance 16 k-rows of 128 B; 64-element M/N chunks are (64*BK*2) bytes apart
+          const uint64_t da = A_MN ? umma_smem_desc_sw128(a_addr + j * (UMMA_K * 128), 64 * BK * 2, 1024)
+                                   : umma_smem_desc_sw128(a_addr + j * (UMMA_K * 2), 16, 1024);
+          const uint64_t db = B_MN ? umma_smem_desc_sw128(b_addr + j * (UMMA_K * 128), 64 * BK * 2, 1024)
+                                   : umma_smem_desc_sw128(b_addr + j * (UMMA_K * 2), 16, 1024);
+          tc_mma_f16_ss(tmem_base, da, db, idesc, (kb | j) != 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above retire
+      }
+      tc_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else if (nkb > 0) {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const mmae_gemm_epilogue& ep = p.ep;
+    const bool first_split = blockIdx.z == 0;
+    const bool atomic_out = ep.accumulate != 0 || gridDim.z > 1;
+    const float* bias = first_split ? ep.bias : nullptr;
+    const float* resid = first_split ? ep.residual : nullptr;
+    const bf16* zptr = reinterpret_cast<const bf16*>(ep.dgelu_z);
+    bf16* preact = reinterpret_cast<bf16*>(ep.preact_bf16);
+    bf16* out_b = reinterpret_cast<bf16*>(ep.out_bf16);
+    float* out_f = ep.out_f32;
+
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nb = n0 + c * 32;
+      if (nb >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
+      tc_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = nb + g * 8;
+        if (!row_ok || n >= p.N) continue;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * ep.alpha;
+        if (bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (preact) {
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(preact + int64_t(row) * ep.ld_preact + n) = o;
+        }
+        if (ep.act == 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (zptr) {
+          const uint4 z = __ldg(reinterpret_cast<const uint4*>(zptr + int64_t(row) * ep.ld_dgelu_z + n));
+          const float2 z0 = unpack_bf16x2(z.x), z1 = unpack_bf16x2(z.y), z2 = unpack_bf16x2(z.z),
+                       z3 = unpack_bf16x2(z.w);
+          v[0] *= dgelu_erf(z0.x); v[1] *= dgelu_erf(z0.y); v[2] *= dgelu_erf(z1.x); v[3] *= dgelu_erf(z1.y);
+          v[4] *= dgelu_erf(z2.x); v[5] *= dgelu_erf(z2.y); v[6] *= dgelu_erf(z3.x); v[7] *= dgelu_erf(z3.y);
+        }
+        if (resid) {
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(resid + int64_t(row) * ep.ld_residual + n));
+          const float4 r1 = __ldg(reinterpret_cast<const float4*>(resid + int64_t(row) * ep.ld_residual + n + 4));
+          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+          v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+        if (out_f) {
+          float* dst = out_f + int64_t(row) * ep.ld_out_f32 + n;
+          if (atomic_out) {
+            red_add_v4(dst, v[0], v[1], v[2], v[3]);
+            red_add_v4(dst + 4, v[4], v[5], v[6], v[7]);
+          } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
+        if (out_b) {
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(out_b + int64_t(row) * ep.ld_out_bf16 + n) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int split_k,
+                cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    MMAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), split_k);
+  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+}  // namespace
+}  // namespace mmae
+
+using namespace mmae;
+
+extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                              int b_mn_major, int M, int N, int K, int split_k, const mmae_gemm_epilogue* ep,
+                              void* stream) {
+  MMAE_CHECK(A && B && ep, MMAE_ERR_ARG, "mmae_gemm_bf16: null operand");
+  MMAE_CHECK(M > 0 && N > 0 && K > 0, MMAE_ERR_ARG, "mmae_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  MMAE_CHECK(N % 8 == 0, MMAE_ERR_ARG, "mmae_gemm_bf16: N=%d must be a multiple of 8", N);
+  MMAE_CHECK(lda % 8 == 0 && ldb % 8 == 0, MMAE_ERR_ARG, "mmae_gemm_bf16: lda/ldb must be multiples of 8");
+  MMAE_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+             MMAE_ERR_ARG, "mmae_gemm_bf16: operands must be 16-byte aligned");
+  MMAE_CHECK(ep->out_f32 || ep->out_bf16, MMAE_ERR_ARG, "mmae_gemm_bf16: no output");
+  if (split_k < 1) split_k = 1;
+  const int num_kb = ceil_div(K, BK);
+  if (split_k > num_kb) split_k = num_kb;
+  const int kb_per_split = ceil_div(num_kb, split_k);
+  split_k = ceil_div(num_kb, kb_per_split);  // no empty splits
+  if (split_k > 1 || ep->accumulate) {
+    MMAE_CHECK(ep->out_f32 && !ep->out_bf16 && !ep->preact_bf16 && !ep->dgelu_z && ep->act == 0, MMAE_ERR_ARG,
+               "mmae_gemm_bf16: split-K / accumulate supports only a linear fp32 epilogue");
+  }
+#define MMAE_LD_OK(ptr, ld) (!(ptr) || ((ld) % 8 == 0 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0))
+  MMAE_CHECK(MMAE_LD_OK(ep->residual, ep->ld_residual) && MMAE_LD_OK(ep->dgelu_z, ep->ld_dgelu_z) &&
+                 MMAE_LD_OK(ep->preact_bf16, ep->ld_preact) && MMAE_LD_OK(ep->out_f32, ep->ld_out_f32) &&
+                 MMAE_LD_OK(ep->out_bf16, ep->ld_out_bf16) &&
+                 (!ep->bias || (reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0),
+             MMAE_ERR_ARG, "mmae_gemm_bf16: epilogue tensors need 16-byte alignment and ld %% 8 == 0");
+#undef MMAE_LD_OK
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn_major) {
+    rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BK, BM);
+  } else {
+    MMAE_CHECK(M % 8 == 0, MMAE_ERR_ARG, "mmae_gemm_bf16: MN-major A needs M %% 8 == 0");
+    rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BK);
+  }
+  if (rc) return rc;
+  constexpr int BN = 128;
+  if (!b_mn_major) {
+    rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BN);
+  } else {
+    rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK);
+  }
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.num_kb = num_kb;
+  p.kb_per_split = kb_per_split;
+  p.ep = *ep;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  constexpr int STAGES = 3;
+  if (!a_mn_major && !b_mn_major) return launch_gemm<BN, STAGES, false, false>(tmA, tmB, p, split_k, st);
+  if (!a_mn_major && b_mn_major) return launch_gemm<BN, STAGES, false, true>(tmA, tmB, p, split_k, st);
+  if (a_mn_major && !b_mn_major) return launch_gemm<BN, STAGES, true, false>(tmA, tmB, p, split_k, st);
+  return launch_gemm<BN, STAGES, true, true>(tmA, tmB, p, split_k, st);
+}

@@ -1,0 +1,142 @@
+"""Generate the golden fixtures under tests/golden/ from the LIVE reference (runs only where /root/reference exists).
+
+    python tests/golden/make_golden.py
+
+The reference (EPFL-VILAB/MultiMAE) has no tests or golden vectors of its own, so these fixtures are what pins the
+oracle (oracle/multimae_oracle.py) and, through it, the CUDA path.  The reference is imported unmodified; the only
+shim is a stub `torch._six` module (utils/native_scaler.py:11 imports a module removed in torch >= 2.0).
+
+Fixtures (all fp32, CPU, torch.save of plain dicts of tensors):
+  sampler_*.pt : Dirichlet shares + uniform noises fed to / index triples returned by generate_random_masks
+  tiny3.pt     : 3-modality MultiMAE (dim 32, depth 2) fwd + 4 losses + all parameter gradients
+  interp.pt    : RGB-only model built with the default 224 pos-emb grid run on 32x32 inputs (bicubic/bilinear resize)
+"""
+import math
+import os
+import sys
+import types
+from functools import partial
+
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def import_reference():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference tree %s not present: fixtures can only be regenerated in the authoring container" % REF)
+    six = types.ModuleType("torch._six")
+    six.inf = math.inf
+    sys.modules.setdefault("torch._six", six)
+    sys.path.insert(0, REF)
+    import multimae.multimae as mm                      # noqa: E402
+    from multimae.criterion import MaskedCrossEntropyLoss, MaskedL1Loss, MaskedMSELoss  # noqa: E402
+    from multimae.input_adapters import PatchedInputAdapter, SemSegInputAdapter        # noqa: E402
+    from multimae.output_adapters import SpatialOutputAdapter                          # noqa: E402
+    return types.SimpleNamespace(mm=mm, MSE=MaskedMSELoss, L1=MaskedL1Loss, CE=MaskedCrossEntropyLoss,
+                                 Patched=PatchedInputAdapter, SemSeg=SemSegInputAdapter, Spatial=SpatialOutputAdapter)
+
+
+def record_sampler(R, name, B, tokens_per_task, num_encoded, alphas, seed):
+    """Replays generate_random_masks' RNG consumption (multimae/multimae.py:187,195,204) to capture its draws."""
+    model = R.mm.MultiMAE(input_adapters={}, output_adapters=None, dim_tokens=8, depth=0, num_heads=1)
+    fake = {"t%d" % i: torch.zeros(B, n, 1) for i, n in enumerate(tokens_per_task)}
+    torch.manual_seed(seed)
+    masks, ids_keep, ids_restore = model.generate_random_masks(fake, num_encoded, alphas=alphas)
+    torch.manual_seed(seed)
+    a = [alphas] * len(tokens_per_task) if isinstance(alphas, float) else alphas
+    shares = torch.distributions.Dirichlet(torch.Tensor(a)).sample((B,))
+    noises = [torch.rand(B, n) for n in tokens_per_task]
+    noise_all = torch.rand(B, sum(tokens_per_task))
+    # sanity: the replayed draws must reproduce the recorded result through the reference formulae
+    per_task = (shares * num_encoded).round().long()
+    chk = []
+    for i, nz in enumerate(noises):
+        order = torch.argsort(nz, dim=1)
+        chk.append(torch.where(order < per_task[:, i:i + 1], 0, 1))
+    ids_shuffle = torch.argsort(torch.cat(chk, 1) + noise_all, dim=1)
+    assert torch.equal(ids_shuffle[:, :num_encoded], ids_keep), "RNG replay diverged from the reference"
+    torch.save({"shares": shares, "noises": noises, "noise_all": noise_all, "num_encoded": num_encoded,
+                "task_masks": [masks[k] for k in fake], "ids_keep": ids_keep, "ids_restore": ids_restore},
+               os.path.join(HERE, name))
+    print("wrote", name)
+
+
+def build_model(R, in_domains, dim, depth, heads, dec_dim, dec_depth, dec_heads, image_size, extra_norm_pix=True):
+    conf = {"rgb": (3, 1), "depth": (1, 1)}
+    inputs, outputs = {}, {}
+    for d in in_domains:
+        if d == "semseg":
+            inputs[d] = R.SemSeg(num_classes=133, dim_class_emb=64, interpolate_class_emb=False, stride_level=4,
+                                 patch_size_full=16, image_size=image_size)
+        else:
+            inputs[d] = R.Patched(num_channels=conf[d][0], stride_level=1, patch_size_full=16, image_size=image_size)
+
+    def out_adapter(task):
+        ch, stride = (133, 4) if task == "semseg" else conf[task]
+        return R.Spatial(num_channels=ch, stride_level=stride, patch_size_full=16, dim_tokens=dec_dim, depth=dec_depth,
+                         num_heads=dec_heads, use_task_queries=True, task=task, context_tasks=list(in_domains),
+                         use_xattn=True, image_size=image_size)
+
+    for d in in_domains:
+        outputs[d] = out_adapter(d)
+    if extra_norm_pix:
+        outputs["norm_rgb"] = out_adapter("rgb")
+    model = R.mm.MultiMAE(input_adapters=inputs, output_adapters=outputs, num_global_tokens=1, dim_tokens=dim,
+                          depth=depth, num_heads=heads, mlp_ratio=4, qkv_bias=True,
+                          norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    # the reference leaves mask_token at zero and biases at zero; perturb so that every term is exercised
+    g = torch.Generator().manual_seed(1234)
+    with torch.no_grad():
+        for n, p_ in model.named_parameters():
+            if p_.requires_grad and (n.endswith(".bias") or n.endswith("mask_token")):
+                p_.add_(torch.randn(p_.shape, generator=g) * 0.05)
+    return model.float().train()
+
+
+def record_model(R, name, in_domains, B, size, num_encoded, seed, **kw):
+    torch.manual_seed(seed)
+    model = build_model(R, in_domains, **kw)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = {}
+    for d in in_domains:
+        if d == "semseg":
+            x[d] = torch.randint(0, 133, (B, size // 4, size // 4), generator=g)
+        else:
+            x[d] = torch.randn(B, 3 if d == "rgb" else 1, size, size, generator=g)
+    torch.manual_seed(seed + 2)
+    tokens_like = {d: torch.zeros(B, (size // 16) ** 2, 1) for d in in_domains}
+    triple = model.generate_random_masks(tokens_like, num_encoded, alphas=1.0)
+    model.generate_random_masks = lambda *a, **k: triple
+    preds, masks = model(x, num_encoded_tokens=num_encoded, alphas=1.0)
+    loss_fns = {"rgb": R.MSE(16, 1), "depth": R.L1(16, 1), "semseg": R.CE(16, 4), "norm_rgb": R.MSE(16, 1, norm_pix=True)}
+    losses = {}
+    for task in preds:
+        src = "rgb" if task == "norm_rgb" else task
+        losses[task] = loss_fns[task](preds[task].float(), x[src], mask=masks.get(src))
+    sum(losses.values()).backward()
+    grads = {n: p_.grad.clone() for n, p_ in model.named_parameters() if p_.grad is not None}
+    gnorm = torch.norm(torch.stack([g_.norm(2) for g_ in grads.values()]), 2)
+    torch.save({
+        "config": dict(in_domains=list(in_domains), B=B, size=size, num_encoded=num_encoded, **kw),
+        "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+        "inputs": x,
+        "task_masks": {k: v.clone() for k, v in masks.items()},
+        "ids_keep": triple[1].clone(), "ids_restore": triple[2].clone(),
+        "preds": {k: v.detach().clone() for k, v in preds.items()},
+        "losses": {k: v.detach().clone() for k, v in losses.items()},
+        "grads": grads, "grad_norm": gnorm,
+    }, os.path.join(HERE, name))
+    print("wrote", name, {k: round(float(v), 6) for k, v in losses.items()}, "grad_norm", float(gnorm))
+
+
+if __name__ == "__main__":
+    R = import_reference()
+    record_sampler(R, "sampler_small.pt", B=16, tokens_per_task=[16, 16, 16], num_encoded=12, alphas=1.0, seed=3)
+    record_sampler(R, "sampler_cfg2.pt", B=8, tokens_per_task=[196, 196, 196], num_encoded=98, alphas=1.0, seed=4)
+    record_sampler(R, "sampler_alpha.pt", B=8, tokens_per_task=[196, 196], num_encoded=98, alphas=[0.5, 2.0], seed=5)
+    record_model(R, "tiny3.pt", ("rgb", "depth", "semseg"), B=3, size=64, num_encoded=12, seed=7,
+                 dim=32, depth=2, heads=2, dec_dim=16, dec_depth=1, dec_heads=2, image_size=64)
+    record_model(R, "interp.pt", ("rgb",), B=2, size=32, num_encoded=2, seed=11,
+                 dim=32, depth=1, heads=2, dec_dim=16, dec_depth=1, dec_heads=2, image_size=224)
