@@ -80,6 +80,35 @@ int mmae_colsum_bf16(const void* src_bf16, int64_t ld_src, float* colsum, int M,
 /* dst[N,M] = src[M,N]^T (bf16) */
 int mmae_transpose_bf16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int M, int N, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (fp32 statistics; eps given).  nn.LayerNorm(eps=1e-6): multimae/multimae_utils.py:222,225 and
+ * multimae/output_adapters.py:120-122.  D must be a multiple of 128, <= 1024.
+ *   forward : y = (x-mean)*rstd*gamma+beta, written as bf16 (GEMM operand) and/or fp32; saves mean/rstd.
+ *   backward: dx = dx_resid(optional) + LN'(dy); dgamma/dbeta are ACCUMULATED (+=) with fp32 atomics.
+ * ---------------------------------------------------------------------------------------------- */
+int mmae_layernorm_forward(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
+                           int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd, int M, int D,
+                           float eps, void* stream);
+int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
+                            const float* mean, const float* rstd, const float* gamma, const float* dx_resid,
+                            int64_t ldr, float* dx, int64_t lddx, float* dgamma, float* dbeta, int M, int D,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-head attention (scores stay on chip).  Attention / CrossAttention:
+ * multimae/multimae_utils.py:172-179, 203-211.  q/k/v/o are bf16 views into row-major [B*N, ld] projection
+ * buffers: head h = columns [h*head_dim, (h+1)*head_dim) from the given base pointer, batch b = rows
+ * [b*N, (b+1)*N).  head_dim in {32, 64}.  lse[B,H,Nq] = log-sum-exp of the scaled scores (saved for backward).
+ * backward: delta_ws is a [B,H,Nq] fp32 scratch; dq/dk/dv are written (not accumulated).
+ * ---------------------------------------------------------------------------------------------- */
+int mmae_attention_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                           void* o, int64_t ldo, float* lse, int B, int H, int Nq, int Nk, int head_dim,
+                           float scale, void* stream);
+int mmae_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                            const void* o, int64_t ldo, const void* d_o, int64_t lddo, const float* lse,
+                            float* delta_ws, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv,
+                            int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,390 @@
+// Coalesced index kernels around the GEMMs (all HBM-bound integer/byte shuffling, no tensor cores):
+//   * gather-first patch embedding operand builder (+ nn.Embedding lookup for semseg)
+//   * packed-sequence assembly (bias + positional embedding + global token)
+//   * decoder query / context construction and its backward
+//   * patch <-> image (un)patchify
+// They replace the cat/gather/repeat/rearrange chains of multimae/multimae.py:340-347,
+// multimae/input_adapters.py:110-117,229-239 and multimae/output_adapters.py:183-234,277-280.
+#include "common.cuh"
+#include "../../include/multimae_b200.h"
+
+namespace mmae {
+void count_launch();
+namespace {
+
+__device__ __forceinline__ int task_of(const mmae_embed_layout& L, int g) {
+  int t = 0;
+#pragma unroll
+  for (int i = 1; i < MMAE_MAX_TASKS; ++i)
+    if (i < L.num_tasks && g >= L.tok_offset[i]) t = i;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A_cat[r, :] for kept token r = (b, i): zeros except the K-segment of the token's task, which holds the patch pixels
+// in conv-weight order (c, py, px); semseg patches hold class_emb[label, e] in (e, py, px) order.
+// One CTA per kept token.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_gather_kernel(mmae_embed_layout L, mmae_embed_inputs in,
+                                                           const int64_t* __restrict__ ids_keep, int T,
+                                                           bf16* __restrict__ A, int* __restrict__ row_task,
+                                                           int* __restrict__ row_patch) {
+  const int r = blockIdx.x;
+  const int b = r / T;
+  const int g = (int)ids_keep[r];
+  const int t = task_of(L, g);
+  const int p = g - L.tok_offset[t];
+  if (threadIdx.x == 0) {
+    row_task[r] = t;
+    row_patch[r] = p;
+  }
+  const int P = L.patch[t], C = L.channels[t], Wt = L.grid_w * P, Ht = L.grid_h * P;
+  const int ph = p / L.grid_w, pw = p % L.grid_w;
+  const int k_begin = L.k_offset[t], k_end = L.k_offset[t + 1];
+  bf16* Ar = A + int64_t(r) * L.k_offset[L.num_tasks];
+  const bf16 zero = __float2bfloat16_rn(0.f);
+  for (int k = threadIdx.x; k < L.k_offset[L.num_tasks]; k += blockDim.x) {
+    bf16 v = zero;
+    if (k >= k_begin && k < k_end) {
+      const int kk = k - k_begin;
+      const int c = kk / (P * P), py = (kk / P) % P, px = kk % P;
+      const int y = ph * P + py, x = pw * P + px;
+      if (L.is_semseg[t]) {
+        const int64_t label = reinterpret_cast<const int64_t*>(in.data[t])[(int64_t(b) * Ht + y) * Wt + x];
+        v = __float2bfloat16_rn(__ldg(in.class_emb[t] + label * C + c));
+      } else {
+        v = __float2bfloat16_rn(__ldg(reinterpret_cast<const float*>(in.data[t]) + ((int64_t(b) * C + c) * Ht + y) * Wt + x));
+      }
+    }
+    Ar[k] = v;
+  }
+}
+
+// x[b, i, :] = C[b*T+i, :] + bias_t + pos_t[p]   (i < T);   x[b, T+j, :] = global_tokens[j, :]
+__global__ void __launch_bounds__(256) embed_assemble_kernel(const float* __restrict__ Cmat, mmae_embed_params prm,
+                                                             const int* __restrict__ row_task,
+                                                             const int* __restrict__ row_patch, int T, int G, int D,
+                                                             float* __restrict__ x) {
+  const int row = blockIdx.x;  // b*(T+G) + i
+  const int b = row / (T + G), i = row % (T + G);
+  float4* dst = reinterpret_cast<float4*>(x + int64_t(row) * D);
+  if (i >= T) {
+    const float4* src = reinterpret_cast<const float4*>(prm.global_tokens + int64_t(i - T) * D);
+    for (int c = threadIdx.x; c < D / 4; c += blockDim.x) dst[c] = __ldg(src + c);
+    return;
+  }
+  const int r = b * T + i;
+  const int t = row_task[r], p = row_patch[r];
+  const float4* cs = reinterpret_cast<const float4*>(Cmat + int64_t(r) * D);
+  const float4* bs = reinterpret_cast<const float4*>(prm.bias[t]);
+  const float4* ps = reinterpret_cast<const float4*>(prm.pos[t] + int64_t(p) * D);
+  for (int c = threadIdx.x; c < D / 4; c += blockDim.x) {
+    const float4 a = __ldg(cs + c), bb = __ldg(bs + c), pp = __ldg(ps + c);
+    dst[c] = make_float4(a.x + bb.x + pp.x, a.y + bb.y + pp.y, a.z + bb.z + pp.z, a.w + bb.w + pp.w);
+  }
+}
+
+// backward of the assembly: dC (bf16 rows of kept tokens), per-task bias grads, global-token grad
+constexpr int EB_ROWS = 32;
+__global__ void __launch_bounds__(256) embed_assemble_bwd_kernel(const float* __restrict__ dx, int T, int G, int D, int B,
+                                                                 const int* __restrict__ row_task,
+                                                                 bf16* __restrict__ dC, mmae_embed_grads grads,
+                                                                 int num_tasks) {
+  // block handles EB_ROWS consecutive sequence rows; thread c handles columns c, c+256, ...
+  const int row0 = blockIdx.x * EB_ROWS;
+  const int rows_total = B * (T + G);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float accb[MMAE_MAX_TASKS];
+#pragma unroll
+    for (int t = 0; t < MMAE_MAX_TASKS; ++t) accb[t] = 0.f;
+    float accg = 0.f;
+    int gidx = -1;
+    for (int row = row0; row < min(row0 + EB_ROWS, rows_total); ++row) {
+      const int b = row / (T + G), i = row % (T + G);
+      const float v = dx[int64_t(row) * D + c];
+      if (i >= T) {
+        // global tokens: at most one global-token index per flush (G is tiny); flush when it changes
+        if (gidx != i - T && gidx >= 0) {
+          atomicAdd(grads.global_tokens + int64_t(gidx) * D + c, accg);
+          accg = 0.f;
+        }
+        gidx = i - T;
+        accg += v;
+      } else {
+        const int r = b * T + i;
+        dC[int64_t(r) * D + c] = __float2bfloat16_rn(v);
+        const int t = row_task[r];
+#pragma unroll
+        for (int tt = 0; tt < MMAE_MAX_TASKS; ++tt)
+          if (tt == t) accb[tt] += v;
+      }
+    }
+    if (gidx >= 0) atomicAdd(grads.global_tokens + int64_t(gidx) * D + c, accg);
+#pragma unroll
+    for (int t = 0; t < MMAE_MAX_TASKS; ++t)
+      if (t < num_tasks && accb[t] != 0.f) atomicAdd(grads.bias[t] + c, accb[t]);
+  }
+}
+
+// dclass_emb[label, e] += dA[r, k_off + e*P*P + py*P + px] over the semseg rows; smem-privatised table per CTA
+__global__ void __launch_bounds__(256) semseg_emb_bwd_kernel(const bf16* __restrict__ dA, int64_t ld_dA,
+                                                             const int64_t* __restrict__ labels,
+                                                             const int64_t* __restrict__ ids_keep,
+                                                             const int* __restrict__ row_task,
+                                                             const int* __restrict__ row_patch, int task, int T,
+                                                             int rows, int rows_per_cta, int grid_w, int grid_h, int P,
+                                                             int E, int num_classes, float* __restrict__ dtable) {
+  extern __shared__ float tab[];  // [num_classes * E]
+  for (int i = threadIdx.x; i < num_classes * E; i += blockDim.x) tab[i] = 0.f;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_cta;
+  const int Wt = grid_w * P, Ht = grid_h * P;
+  for (int r = r0; r < min(r0 + rows_per_cta, rows); ++r) {
+    if (row_task[r] != task) continue;  // uniform per row
+    const int b = r / T, p = row_patch[r];
+    const int ph = p / grid_w, pw = p % grid_w;
+    for (int k = threadIdx.x; k < E * P * P; k += blockDim.x) {
+      const int e = k / (P * P), py = (k / P) % P, px = k % P;
+      const int64_t label = labels[(int64_t(b) * Ht + ph * P + py) * Wt + pw * P + px];
+      atomicAdd(&tab[label * E + e], __bfloat162float(dA[int64_t(r) * ld_dA + k]));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < num_classes * E; i += blockDim.x)
+    if (tab[i] != 0.f) atomicAdd(dtable + i, tab[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// decoder queries / context  (multimae/output_adapters.py:183-234)
+//   queries[b, j]  = (visible ? ctx[b, rank] : mask_token) + task_emb[own] + pos[j]            j in own task's tokens
+//   context[b, i]  = ctx[b, i] + task_emb[task(i)] + pos[patch(i)]   (i < T);   context[b, T+g] = ctx[b, T+g]
+// One CTA row per output row; rows [0, B*P) are queries, rows [B*P, B*P + B*(T+G)) are context.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) dec_build_kernel(const float* __restrict__ ctx, mmae_decoder_index ix,
+                                                       const float* __restrict__ mask_token,
+                                                       const float* __restrict__ task_emb,  // [num_tasks, Dd] (zeros if absent)
+                                                       const float* __restrict__ pos,       // [P, Dd]
+                                                       float* __restrict__ queries, float* __restrict__ context) {
+  const int Dd = ix.dim, T = ix.num_visible, G = ix.num_global, P = ix.num_queries;
+  const int row = blockIdx.x;
+  const int nq_rows = ix.batch * P;
+  const float4 *base, *te, *pe = nullptr;
+  float4* dst;
+  if (row < nq_rows) {
+    const int b = row / P, j = row % P;
+    const int g = ix.tok_offset[ix.own_task] + j;
+    const int rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
+    base = rank < T ? reinterpret_cast<const float4*>(ctx + (int64_t(b) * (T + G) + rank) * Dd)
+                    : reinterpret_cast<const float4*>(mask_token);
+    te = reinterpret_cast<const float4*>(task_emb + int64_t(ix.own_task) * Dd);
+    pe = reinterpret_cast<const float4*>(pos + int64_t(j) * Dd);
+    dst = reinterpret_cast<float4*>(queries + int64_t(row) * Dd);
+  } else {
+    const int cr = row - nq_rows;
+    const int b = cr / (T + G), i = cr % (T + G);
+    base = reinterpret_cast<const float4*>(ctx + int64_t(cr) * Dd);
+    dst = reinterpret_cast<float4*>(context + int64_t(cr) * Dd);
+    te = nullptr;
+    if (i < T) {
+      const int g = (int)ix.ids_keep[int64_t(b) * T + i];
+      int t = 0;
+#pragma unroll
+      for (int q = 1; q < MMAE_MAX_TASKS; ++q)
+        if (q < ix.num_tasks && g >= ix.tok_offset[q]) t = q;
+      te = reinterpret_cast<const float4*>(task_emb + int64_t(t) * Dd);
+      pe = reinterpret_cast<const float4*>(pos + int64_t(g - ix.tok_offset[t]) * Dd);
+    }
+  }
+  for (int c = threadIdx.x; c < Dd / 4; c += blockDim.x) {
+    float4 v = __ldg(base + c);
+    if (te) {
+      const float4 a = __ldg(te + c), p4 = __ldg(pe + c);
+      v.x += a.x + p4.x; v.y += a.y + p4.y; v.z += a.z + p4.z; v.w += a.w + p4.w;
+    }
+    dst[c] = v;
+  }
+}
+
+// backward: dctx[b,i] = dcontext[b,i] (+ dqueries[b, g-start] if token i belongs to the own task);
+// dmask_token += dqueries of masked positions; dtask_emb[t] += dcontext rows of task t (+ all dqueries for own).
+constexpr int DB_ROWS = 16;
+__global__ void __launch_bounds__(256) dec_build_bwd_kernel(const float* __restrict__ dqueries,
+                                                            const float* __restrict__ dcontext, mmae_decoder_index ix,
+                                                            float* __restrict__ dctx, float* __restrict__ dmask_token,
+                                                            float* __restrict__ dtask_emb) {
+  const int Dd = ix.dim, T = ix.num_visible, G = ix.num_global, P = ix.num_queries;
+  const int nq_rows = ix.batch * P, nc_rows = ix.batch * (T + G);
+  const int row0 = blockIdx.x * DB_ROWS;
+  const int c = threadIdx.x;  // one column per thread; Dd <= 256 handled by the loop below
+  for (int col = c; col < Dd; col += blockDim.x) {
+    float acc_mask = 0.f;
+    float acc_te[MMAE_MAX_TASKS];
+#pragma unroll
+    for (int t = 0; t < MMAE_MAX_TASKS; ++t) acc_te[t] = 0.f;
+    for (int row = row0; row < min(row0 + DB_ROWS, nq_rows + nc_rows); ++row) {
+      if (row < nq_rows) {
+        const int b = row / P, j = row % P;
+        const int g = ix.tok_offset[ix.own_task] + j;
+        const int rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
+        const float v = dqueries[int64_t(row) * Dd + col];
+        if (rank >= T) acc_mask += v;
+#pragma unroll
+        for (int t = 0; t < MMAE_MAX_TASKS; ++t)
+          if (t == ix.own_task) acc_te[t] += v;
+      } else {
+        const int cr = row - nq_rows;
+        const int b = cr / (T + G), i = cr % (T + G);
+        float v = dcontext[int64_t(cr) * Dd + col];
+        if (i < T) {
+          const int g = (int)ix.ids_keep[int64_t(b) * T + i];
+          int t = 0;
+#pragma unroll
+          for (int q = 1; q < MMAE_MAX_TASKS; ++q)
+            if (q < ix.num_tasks && g >= ix.tok_offset[q]) t = q;
+#pragma unroll
+          for (int tt = 0; tt < MMAE_MAX_TASKS; ++tt)
+            if (tt == t) acc_te[tt] += v;
+          if (t == ix.own_task) v += dqueries[(int64_t(b) * P + (g - ix.tok_offset[t])) * Dd + col];
+        }
+        dctx[int64_t(cr) * Dd + col] = v;
+      }
+    }
+    if (acc_mask != 0.f) atomicAdd(dmask_token + col, acc_mask);
+#pragma unroll
+    for (int t = 0; t < MMAE_MAX_TASKS; ++t)
+      if (t < ix.num_tasks && acc_te[t] != 0.f) atomicAdd(dtask_emb + int64_t(t) * Dd + col, acc_te[t]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// unpatchify: tokens [B*nh*nw, C*P*P] (c, py, px) -> image [B, C, nh*P, nw*P]   (output_adapters.py:277-280)
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool TO_IMAGE, typename TokT>
+__global__ void __launch_bounds__(256) unpatchify_kernel(TokT* __restrict__ tok, int64_t ld_tok, float* __restrict__ img,
+                                                         int B, int C, int nh, int nw, int P) {
+  // one CTA per (b, c, image row y); threads over x
+  const int W = nw * P, H = nh * P;
+  const int y = blockIdx.x % H, c = (blockIdx.x / H) % C, b = blockIdx.x / (H * C);
+  const int ph = y / P, py = y % P;
+  float* irow = img + ((int64_t(b) * C + c) * H + y) * W;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    const int pw = x / P, px = x % P;
+    const int64_t ti = (int64_t(b) * nh * nw + ph * nw + pw) * ld_tok + (c * P + py) * P + px;
+    if constexpr (TO_IMAGE) {
+      irow[x] = (float)tok[ti];
+    } else {
+      tok[ti] = (TokT)irow[x];
+    }
+  }
+}
+
+__global__ void cast2d_kernel(const float* __restrict__ src, int64_t ld_src, bf16* __restrict__ dst, int64_t ld_dst,
+                              int rows, int cols) {
+  const int r = blockIdx.y;
+  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4; c < cols; c += gridDim.x * blockDim.x * 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + int64_t(r) * ld_src + c));
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + int64_t(r) * ld_dst + c) = o;
+  }
+}
+
+}  // namespace
+
+// ---- internal launchers shared with modules.cu ------------------------------------------------------------------------
+int launch_embed_gather(const mmae_embed_layout& L, const mmae_embed_inputs& in, const int64_t* ids_keep, int B, int T,
+                        bf16* A, int* row_task, int* row_patch, cudaStream_t st) {
+  embed_gather_kernel<<<B * T, 256, 0, st>>>(L, in, ids_keep, T, A, row_task, row_patch);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+int launch_embed_assemble(const float* Cmat, const mmae_embed_params& prm, const int* row_task, const int* row_patch,
+                          int B, int T, int G, int D, float* x, cudaStream_t st) {
+  embed_assemble_kernel<<<B * (T + G), 256, 0, st>>>(Cmat, prm, row_task, row_patch, T, G, D, x);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+int launch_embed_assemble_bwd(const float* dx, int B, int T, int G, int D, const int* row_task, bf16* dC,
+                              const mmae_embed_grads& grads, int num_tasks, cudaStream_t st) {
+  embed_assemble_bwd_kernel<<<ceil_div(B * (T + G), EB_ROWS), 256, 0, st>>>(dx, T, G, D, B, row_task, dC, grads,
+                                                                            num_tasks);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+int launch_semseg_emb_bwd(const bf16* dA, int64_t ld_dA, const int64_t* labels, const int64_t* ids_keep,
+                          const int* row_task, const int* row_patch, int task, int T, int rows, int grid_w, int grid_h,
+                          int P, int E, int num_classes, float* dtable, cudaStream_t st) {
+  const size_t smem = size_t(num_classes) * E * 4;
+  MMAE_CHECK(smem <= 96 * 1024, MMAE_ERR_UNSUPPORTED, "class embedding table too large for the smem-privatised scatter");
+  static bool configured = false;
+  if (!configured) {
+    MMAE_CUDA_OK(cudaFuncSetAttribute(semseg_emb_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  const int ctas = std::min(rows, 2 * sm_count());
+  const int rows_per_cta = ceil_div(rows, ctas);
+  semseg_emb_bwd_kernel<<<ceil_div(rows, rows_per_cta), 256, smem, st>>>(dA, ld_dA, labels, ids_keep, row_task,
+                                                                          row_patch, task, T, rows, rows_per_cta,
+                                                                          grid_w, grid_h, P, E, num_classes, dtable);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float* mask_token, const float* task_emb,
+                     const float* pos, float* queries, float* context, cudaStream_t st) {
+  const int rows = ix.batch * ix.num_queries + ix.batch * (ix.num_visible + ix.num_global);
+  dec_build_kernel<<<rows, 64, 0, st>>>(ctx, ix, mask_token, task_emb, pos, queries, context);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+int launch_dec_build_bwd(const float* dqueries, const float* dcontext, const mmae_decoder_index& ix, float* dctx,
+                         float* dmask_token, float* dtask_emb, cudaStream_t st) {
+  const int rows = ix.batch * ix.num_queries + ix.batch * (ix.num_visible + ix.num_global);
+  dec_build_bwd_kernel<<<ceil_div(rows, DB_ROWS), 256, 0, st>>>(dqueries, dcontext, ix, dctx, dmask_token, dtask_emb);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+int launch_cast2d(const float* src, int64_t ld_src, bf16* dst, int64_t ld_dst, int rows, int cols, cudaStream_t st) {
+  dim3 grid(std::max(1, std::min(8, ceil_div(cols, 1024))), rows);
+  cast2d_kernel<<<grid, 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, cols);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+}  // namespace mmae
+
+using namespace mmae;
+
+extern "C" int mmae_unpatchify(const float* tokens, int64_t ld_tok, float* image, int B, int C, int nh, int nw, int P,
+                               void* stream) {
+  MMAE_CHECK(tokens && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG, "mmae_unpatchify: bad args");
+  unpatchify_kernel<true, const float><<<B * C * nh * P, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      tokens, ld_tok, image, B, C, nh, nw, P);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+extern "C" int mmae_patchify_bf16(const float* image, void* tokens_bf16, int64_t ld_tok, int B, int C, int nh, int nw,
+                                  int P, void* stream) {
+  MMAE_CHECK(tokens_bf16 && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG,
+             "mmae_patchify_bf16: bad args");
+  unpatchify_kernel<false, bf16><<<B * C * nh * P, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<bf16*>(tokens_bf16), ld_tok, const_cast<float*>(image), B, C, nh, nw, P);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}

@@ -1,0 +1,211 @@
+// LayerNorm forward / backward (fp32 statistics, eps as given), one warp per row, rows kept in registers.
+// Replaces nn.LayerNorm(eps=1e-6) at multimae/multimae_utils.py:222,225,230-231 and
+// multimae/output_adapters.py:120-122,265-266 (autocast keeps LayerNorm in fp32: SURVEY.md §A.2).
+// HBM-bound: fwd reads 4 B/elem, writes 2 B/elem (bf16 operand for the next GEMM) + 8 B/row of statistics.
+#include "common.cuh"
+#include "../../include/multimae_b200.h"
+
+namespace mmae {
+void count_launch();
+namespace {
+
+constexpr int LN_WARPS = 8;
+
+// D = NVEC * 128 (each lane owns NVEC float4, strided by 32 lanes)
+template <int NVEC>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __restrict__ x, int64_t ldx,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, bf16* __restrict__ y_bf16,
+                                                               int64_t ldy, float* __restrict__ y_f32, int64_t ldyf,
+                                                               float* __restrict__ mean_out,
+                                                               float* __restrict__ rstd_out, int M, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * LN_WARPS + warp;
+  if (row >= M) return;
+  constexpr int D = NVEC * 128;
+  const float* xr = x + int64_t(row) * ldx;
+  float4 v[NVEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    v[i] = __ldg(reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4));
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    if (y_bf16) {
+      uint2 p;
+      p.x = pack_bf16x2(o.x, o.y);
+      p.y = pack_bf16x2(o.z, o.w);
+      *reinterpret_cast<uint2*>(y_bf16 + int64_t(row) * ldy + c) = p;
+    }
+    if (y_f32) *reinterpret_cast<float4*>(y_f32 + int64_t(row) * ldyf + c) = o;
+  }
+}
+
+// Backward.  dx_out = dx_resid (optional) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * gamma.
+// dgamma/dbeta: per-lane register partials over the block's rows -> smem reduce over warps -> fp32 atomics.
+constexpr int LNB_ROWS = 64;  // rows per block
+
+template <int NVEC, bool DY_BF16>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __restrict__ dy_, int64_t lddy,
+                                                               const float* __restrict__ x, int64_t ldx,
+                                                               const float* __restrict__ mean_in,
+                                                               const float* __restrict__ rstd_in,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ dx_resid, int64_t ldr,
+                                                               float* __restrict__ dx, int64_t lddx,
+                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                               int M) {
+  constexpr int D = NVEC * 128;
+  __shared__ float4 red[LN_WARPS][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 dg[NVEC], db[NVEC], gm[NVEC];
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
+  }
+  const int r_end = min((blockIdx.x + 1) * LNB_ROWS, M);
+  for (int row = blockIdx.x * LNB_ROWS + warp; row < r_end; row += LN_WARPS) {
+    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
+    float4 xh[NVEC], g[NVEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + int64_t(row) * ldx + c));
+      float4 d;
+      if constexpr (DY_BF16) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + int64_t(row) * lddy + c));
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        d = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        d = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + int64_t(row) * lddy + c));
+      }
+      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+      g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
+      s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+      s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+    }
+    const float c1 = warp_sum(s1) * (1.0f / D), c2 = warp_sum(s2) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      float4 o;
+      o.x = rstd * (g[i].x - c1 - xh[i].x * c2);
+      o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
+      o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
+      o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
+      if (dx_resid) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(dx_resid + int64_t(row) * ldr + c));
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      *reinterpret_cast<float4*>(dx + int64_t(row) * lddx + c) = o;
+    }
+  }
+  // column reductions across the block's warps
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? dgamma : dbeta;
+    if (dst == nullptr) continue;
+#pragma unroll
+    for (int i = 0; i < NVEC; ++i) {
+      __syncthreads();
+      red[warp][lane] = pass == 0 ? dg[i] : db[i];
+      __syncthreads();
+      if (warp == 0) {
+        float4 a = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < LN_WARPS; ++w) {
+          const float4 o = red[w][lane];
+          a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+        }
+        const int c = (i * 32 + lane) * 4;
+        atomicAdd(dst + c + 0, a.x);
+        atomicAdd(dst + c + 1, a.y);
+        atomicAdd(dst + c + 2, a.z);
+        atomicAdd(dst + c + 3, a.w);
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace mmae
+
+using namespace mmae;
+
+extern "C" int mmae_layernorm_forward(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
+                                      int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd, int M, int D,
+                                      float eps, void* stream) {
+  MMAE_CHECK(x && gamma && beta && (y_bf16 || y_f32) && M > 0, MMAE_ERR_ARG, "mmae_layernorm_forward: bad args");
+  MMAE_CHECK(D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && ldyf % 4 == 0, MMAE_ERR_UNSUPPORTED,
+             "mmae_layernorm_forward: D=%d must be a multiple of 128 and <= 1024", D);
+  dim3 grid(ceil_div(M, LN_WARPS)), block(LN_WARPS * 32);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  bf16* yb = reinterpret_cast<bf16*>(y_bf16);
+#define LN_CASE(NV)                                                                                            \
+  case NV:                                                                                                     \
+    ln_fwd_kernel<NV><<<grid, block, 0, st>>>(x, ldx, gamma, beta, yb, ldy, y_f32, ldyf, mean, rstd, M, eps); \
+    break;
+  switch (D / 128) {
+    LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+    default: MMAE_CHECK(false, MMAE_ERR_UNSUPPORTED, "mmae_layernorm_forward: unsupported D=%d", D);
+  }
+#undef LN_CASE
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+extern "C" int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
+                                       const float* mean, const float* rstd, const float* gamma, const float* dx_resid,
+                                       int64_t ldr, float* dx, int64_t lddx, float* dgamma, float* dbeta, int M, int D,
+                                       void* stream) {
+  MMAE_CHECK(dy && x && mean && rstd && gamma && dx && M > 0, MMAE_ERR_ARG, "mmae_layernorm_backward: bad args");
+  MMAE_CHECK(D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && ldr % 4 == 0,
+             MMAE_ERR_UNSUPPORTED, "mmae_layernorm_backward: D=%d must be a multiple of 128 and <= 1024", D);
+  dim3 grid(ceil_div(M, LNB_ROWS)), block(LN_WARPS * 32);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define LNB_CASE(NV)                                                                                              \
+  case NV:                                                                                                        \
+    if (dy_is_bf16)                                                                                               \
+      ln_bwd_kernel<NV, true><<<grid, block, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx,     \
+                                                      lddx, dgamma, dbeta, M);                                   \
+    else                                                                                                          \
+      ln_bwd_kernel<NV, false><<<grid, block, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx,    \
+                                                       lddx, dgamma, dbeta, M);                                  \
+    break;
+  switch (D / 128) {
+    LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
+    default: MMAE_CHECK(false, MMAE_ERR_UNSUPPORTED, "mmae_layernorm_backward: unsupported D=%d", D);
+  }
+#undef LNB_CASE
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}

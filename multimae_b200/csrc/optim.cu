@@ -1,0 +1,133 @@
+// Flat-buffer gradient post-processing and optimizer update (HBM-bound, single pass each).
+//
+// mmae_grad_unscale_norm replaces GradScaler.unscale_ + get_grad_norm_ (utils/native_scaler.py:34-35, 49-62): the
+// reference launches ~344 per-tensor norm kernels + a stack + a norm; the L2 norm of per-tensor L2 norms equals the
+// L2 norm of the concatenation, so one pass over the flat gradient buffer suffices.
+// mmae_adamw_step is torch.optim.AdamW's update (utils/optim_factory.py:155-174 builds it) over flat buffers.
+#include "common.cuh"
+#include "../../include/multimae_b200.h"
+
+namespace mmae {
+void count_launch();
+namespace {
+
+// out[0] += sum(g^2) after unscaling, out[1] = 1.0 if any non-finite value was seen (left untouched otherwise)
+__global__ void __launch_bounds__(256) unscale_norm_kernel(float* __restrict__ g, int64_t n, const float* __restrict__ inv_scale_ptr,
+                                                           float inv_scale_imm, float post_scale, float* __restrict__ out) {
+  __shared__ float red[8];
+  const float inv = (inv_scale_ptr ? inv_scale_ptr[0] : inv_scale_imm) * post_scale;
+  float acc = 0.f;
+  bool bad = false;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x * 4;
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      float4 v = *reinterpret_cast<float4*>(g + i);
+      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+      if (inv != 1.0f) *reinterpret_cast<float4*>(g + i) = v;
+      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+    } else {
+      for (int64_t j = i; j < n; ++j) {
+        const float v = g[j] * inv;
+        if (inv != 1.0f) g[j] = v;
+        acc += v * v;
+        bad |= !isfinite(v);
+      }
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t = red[threadIdx.x];
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffu, t, o);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+  if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) out[1] = 1.0f;
+}
+
+__global__ void sqrt_kernel(const float* __restrict__ in, float* __restrict__ norm_out) { norm_out[0] = sqrtf(in[0]); }
+
+// decoupled weight decay AdamW, skipping the whole update when found_inf[0] != 0 (GradScaler.step semantics)
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
+                                                    float eps, float wd, float bc1, float bc2_sqrt,
+                                                    const float* __restrict__ found_inf) {
+  if (found_inf != nullptr && found_inf[0] != 0.f) return;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x * 4;
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      float4 pp = *reinterpret_cast<float4*>(p + i);
+      const float4 gg = *reinterpret_cast<const float4*>(g + i);
+      float4 mm = *reinterpret_cast<float4*>(m + i);
+      float4 vv = *reinterpret_cast<float4*>(v + i);
+#define MMAE_ADAM1(P, G, M, V)                                     \
+  P *= (1.f - lr * wd);                                            \
+  M = beta1 * M + (1.f - beta1) * G;                               \
+  V = beta2 * V + (1.f - beta2) * G * G;                           \
+  P -= (lr / bc1) * M / (sqrtf(V) / bc2_sqrt + eps);
+      MMAE_ADAM1(pp.x, gg.x, mm.x, vv.x)
+      MMAE_ADAM1(pp.y, gg.y, mm.y, vv.y)
+      MMAE_ADAM1(pp.z, gg.z, mm.z, vv.z)
+      MMAE_ADAM1(pp.w, gg.w, mm.w, vv.w)
+      *reinterpret_cast<float4*>(p + i) = pp;
+      *reinterpret_cast<float4*>(m + i) = mm;
+      *reinterpret_cast<float4*>(v + i) = vv;
+    } else {
+      for (int64_t j = i; j < n; ++j) {
+        float P = p[j], M = m[j], V = v[j];
+        const float G = g[j];
+        MMAE_ADAM1(P, G, M, V)
+        p[j] = P; m[j] = M; v[j] = V;
+      }
+    }
+  }
+#undef MMAE_ADAM1
+}
+
+}  // namespace
+}  // namespace mmae
+
+using namespace mmae;
+
+extern "C" int mmae_grad_unscale_norm(float* grads, int64_t n, const float* inv_scale_dev, float inv_scale,
+                                      float post_scale, float* out2, float* norm_out, void* stream) {
+  MMAE_CHECK(grads && out2 && n >= 0 && (reinterpret_cast<uintptr_t>(grads) & 15) == 0, MMAE_ERR_ARG,
+             "mmae_grad_unscale_norm: bad args");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMAE_CUDA_OK(cudaMemsetAsync(out2, 0, 2 * sizeof(float), st));
+  if (n > 0) {
+    int64_t blocks = (n / 4 + 255) / 256;
+    const int64_t cap = int64_t(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    unscale_norm_kernel<<<(unsigned)blocks, 256, 0, st>>>(grads, n, inv_scale_dev, inv_scale, post_scale, out2);
+    count_launch();
+    MMAE_LAUNCH_OK();
+  }
+  if (norm_out) {
+    sqrt_kernel<<<1, 1, 0, st>>>(out2, norm_out);
+    count_launch();
+    MMAE_LAUNCH_OK();
+  }
+  return MMAE_OK;
+}
+
+extern "C" int mmae_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int step,
+                               const float* found_inf_dev, void* stream) {
+  MMAE_CHECK(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, MMAE_ERR_ARG, "mmae_adamw_step: bad args");
+  if (n == 0) return MMAE_OK;
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.0f - powf(beta2, (float)step));
+  int64_t blocks = (n / 4 + 255) / 256;
+  const int64_t cap = int64_t(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  adamw_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, found_inf_dev);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}

@@ -80,3 +80,50 @@ def transpose_bf16(src, dst=None):
     L.check(L.lib().mmae_transpose_bf16(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), M, N,
                                         L.current_stream()), "mmae_transpose_bf16")
     return dst
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-6, out_bf16=True, out_f32=False):
+    """x [M,D] fp32 -> (y_bf16|None, y_f32|None, mean[M], rstd[M])."""
+    _need_cuda(x)
+    M, D = x.shape
+    yb = torch.empty((M, D), dtype=torch.bfloat16, device=x.device) if out_bf16 else None
+    yf = torch.empty((M, D), dtype=torch.float32, device=x.device) if out_f32 else None
+    mean = torch.empty(M, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    L.check(L.lib().mmae_layernorm_forward(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), L.ptr(yb),
+                                           D, L.ptr(yf), D, mean.data_ptr(), rstd.data_ptr(), M, D, eps,
+                                           L.current_stream()), "mmae_layernorm_forward")
+    return yb, yf, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dx_resid=None, dx=None):
+    M, D = x.shape
+    if dx is None:
+        dx = torch.empty((M, D), dtype=torch.float32, device=x.device)
+    L.check(L.lib().mmae_layernorm_backward(dy.data_ptr(), int(dy.dtype == torch.bfloat16), dy.stride(0), x.data_ptr(),
+                                            x.stride(0), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                            L.ptr(dx_resid), dx_resid.stride(0) if dx_resid is not None else 0,
+                                            dx.data_ptr(), dx.stride(0), L.ptr(dgamma), L.ptr(dbeta), M, D,
+                                            L.current_stream()), "mmae_layernorm_backward")
+    return dx
+
+
+def attention_fwd(q, k, v, B, H, Nq, Nk, dh, scale, out=None):
+    """q: [B*Nq, >=H*dh] view, k/v: [B*Nk, ...] views (bf16, unit inner stride). Returns (o [B*Nq, H*dh], lse)."""
+    _need_cuda(q, k, v)
+    if out is None:
+        out = torch.empty((B * Nq, H * dh), dtype=torch.bfloat16, device=q.device)
+    lse = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
+    L.check(L.lib().mmae_attention_forward(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                           v.stride(0), out.data_ptr(), out.stride(0), lse.data_ptr(), B, H, Nq, Nk,
+                                           dh, scale, L.current_stream()), "mmae_attention_forward")
+    return out, lse
+
+
+def attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, Nq, Nk, dh, scale):
+    delta = torch.empty((B, H, Nq), dtype=torch.float32, device=q.device)
+    L.check(L.lib().mmae_attention_backward(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(),
+                                            v.stride(0), o.data_ptr(), o.stride(0), do.data_ptr(), do.stride(0),
+                                            lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dq.stride(0),
+                                            dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), B, H, Nq, Nk, dh,
+                                            scale, L.current_stream()), "mmae_attention_backward")

@@ -8,7 +8,7 @@ import time
 import torch
 
 sys.path.insert(0, ".")
-from multimae_b200 import kernels as K  # noqa: E402
+from multimae_b200 import kernels as KN  # noqa: E402
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -37,7 +37,7 @@ def gemm_case(M, N, K, a_mn, b_mn, split_k=1):
     Ain = A.t().contiguous() if a_mn else A
     Bin = B.t().contiguous() if b_mn else B
     out = torch.zeros(M, N, device=dev, dtype=torch.float32)
-    K.gemm(Ain, Bin, a_mn=a_mn, b_mn=b_mn, out_f32=out, split_k=split_k)
+    KN.gemm(Ain, Bin, a_mn=a_mn, b_mn=b_mn, out_f32=out, split_k=split_k)
     torch.cuda.synchronize()
     report("gemm M=%d N=%d K=%d a_mn=%d b_mn=%d split=%d" % (M, N, K, a_mn, b_mn, split_k), relerr(out, ref), 1e-5)
 
@@ -68,44 +68,117 @@ resid = torch.randn(M, N, device=dev)
 acc = A.float() @ B.float().t()
 
 out = torch.empty(M, N, device=dev)
-K.gemm(A, B, bias=bias, out_f32=out)
+KN.gemm(A, B, bias=bias, out_f32=out)
 report("epilogue bias", relerr(out, acc + bias), 1e-5)
 
 outb = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
 pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-K.gemm(A, B, bias=bias, act=1, preact=pre, out_bf16=outb)
+KN.gemm(A, B, bias=bias, act=1, preact=pre, out_bf16=outb)
 z = acc + bias
 report("epilogue bias+gelu -> bf16", relerr(outb, torch.nn.functional.gelu(z)), 4e-3)
 report("epilogue preact bf16", relerr(pre, z), 4e-3)
 
 out = torch.empty(M, N, device=dev)
-K.gemm(A, B, bias=bias, residual=resid, out_f32=out)
+KN.gemm(A, B, bias=bias, residual=resid, out_f32=out)
 report("epilogue bias+residual", relerr(out, acc + bias + resid), 1e-5)
 
 zz = (torch.randn(M, N, device=dev)).to(torch.bfloat16)
 out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-K.gemm(A, B, dgelu_z=zz, out_bf16=out)
+KN.gemm(A, B, dgelu_z=zz, out_bf16=out)
 zf = zz.float().requires_grad_(True)
 torch.nn.functional.gelu(zf).sum().backward()
 report("epilogue dgelu", relerr(out, acc * zf.grad), 4e-3)
 
 out = torch.ones(M, N, device=dev)
-K.gemm(A, B, out_f32=out, accumulate=True, alpha=0.5)
+KN.gemm(A, B, out_f32=out, accumulate=True, alpha=0.5)
 report("epilogue accumulate alpha", relerr(out, 1 + 0.5 * acc), 1e-5)
 
 # ---- element-wise kernels
 x = torch.randn(1000, 776, device=dev)
-report("cast_bf16", relerr(K.cast_bf16(x), x.to(torch.bfloat16)), 1e-7)
+report("cast_bf16", relerr(KN.cast_bf16(x), x.to(torch.bfloat16)), 1e-7)
 dst = torch.empty(1000, 776, device=dev, dtype=torch.bfloat16)
 cs = torch.zeros(776, device=dev)
-K.cast_colsum(x, dst, cs)
+KN.cast_colsum(x, dst, cs)
 report("cast_colsum cast", relerr(dst, x.to(torch.bfloat16)), 1e-7)
 report("cast_colsum sum", relerr(cs, x.sum(0)), 1e-5)
 cs2 = torch.zeros(776, device=dev)
-K.colsum_bf16(dst, cs2)
+KN.colsum_bf16(dst, cs2)
 report("colsum_bf16", relerr(cs2, dst.float().sum(0)), 1e-5)
-t = K.transpose_bf16(dst)
+t = KN.transpose_bf16(dst)
 report("transpose_bf16", relerr(t, dst.t()), 1e-7)
+
+
+# ---- LayerNorm forward / backward
+for (M, D) in [(1000, 768), (396, 256), (130, 1024)]:
+    x = torch.randn(M, D, device=dev) * 2 + 0.5
+    gam = torch.randn(D, device=dev)
+    bet = torch.randn(D, device=dev)
+    yb, yf, mean, rstd = KN.layernorm_fwd(x, gam, bet, 1e-6, out_bf16=True, out_f32=True)
+    xr = x.clone().requires_grad_(True)
+    gr = gam.clone().requires_grad_(True)
+    br = bet.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-6)
+    report("ln fwd f32 M=%d D=%d" % (M, D), relerr(yf, ref), 1e-5)
+    report("ln fwd bf16 M=%d D=%d" % (M, D), relerr(yb, ref), 4e-3)
+    dy = torch.randn(M, D, device=dev)
+    resid = torch.randn(M, D, device=dev)
+    ref.backward(dy)
+    dgam = torch.zeros(D, device=dev)
+    dbet = torch.zeros(D, device=dev)
+    dx = KN.layernorm_bwd(dy, x, mean, rstd, gam, dgam, dbet, dx_resid=resid)
+    report("ln bwd dx (+resid) M=%d D=%d" % (M, D), relerr(dx, xr.grad + resid), 1e-5)
+    report("ln bwd dgamma M=%d D=%d" % (M, D), relerr(dgam, gr.grad), 1e-4)
+    report("ln bwd dbeta M=%d D=%d" % (M, D), relerr(dbet, br.grad), 1e-4)
+    dyb = dy.to(torch.bfloat16)
+    dx2 = KN.layernorm_bwd(dyb, x, mean, rstd, gam, None, None)
+    xr2 = x.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr2, (D,), gam, bet, 1e-6).backward(dyb.float())
+    report("ln bwd dx (bf16 dy) M=%d D=%d" % (M, D), relerr(dx2, xr2.grad), 1e-5)
+
+
+# ---- attention forward / backward (packed projection layouts as the blocks use them)
+def attn_case(B, H, Nq, Nk, dh, self_attn):
+    D = H * dh
+    scale = dh ** -0.5
+    if self_attn:
+        qkv = rand_bf16(B * Nq, 3 * D)
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    else:
+        q = rand_bf16(B * Nq, D)
+        kv = rand_bf16(B * Nk, 2 * D)
+        k, v = kv[:, :D], kv[:, D:]
+    o, lse = KN.attention_fwd(q, k, v, B, H, Nq, Nk, dh, scale)
+    qf = q.float().reshape(B, Nq, H, dh).transpose(1, 2).detach().requires_grad_(True)
+    kf = k.float().reshape(B, Nk, H, dh).transpose(1, 2).detach().requires_grad_(True)
+    vf = v.float().reshape(B, Nk, H, dh).transpose(1, 2).detach().requires_grad_(True)
+    s = (qf @ kf.transpose(-2, -1)) * scale
+    ref = torch.softmax(s, -1) @ vf
+    ref2 = ref.transpose(1, 2).reshape(B * Nq, D)
+    tag = "B=%d H=%d Nq=%d Nk=%d dh=%d" % (B, H, Nq, Nk, dh)
+    report("attn fwd o " + tag, relerr(o, ref2), 6e-3)
+    report("attn fwd lse " + tag, relerr(lse, torch.logsumexp(s, -1)), 1e-4)
+    do = rand_bf16(B * Nq, D)
+    ref2.backward(do.float())
+    if self_attn:
+        dqkv = torch.empty(B * Nq, 3 * D, device=dev, dtype=torch.bfloat16)
+        dq, dk, dv = dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:]
+    else:
+        dq = torch.empty(B * Nq, D, device=dev, dtype=torch.bfloat16)
+        dkv = torch.empty(B * Nk, 2 * D, device=dev, dtype=torch.bfloat16)
+        dk, dv = dkv[:, :D], dkv[:, D:]
+    KN.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, Nq, Nk, dh, scale)
+    report("attn bwd dq " + tag, relerr(dq, qf.grad.transpose(1, 2).reshape(B * Nq, D)), 1e-2)
+    report("attn bwd dk " + tag, relerr(dk, kf.grad.transpose(1, 2).reshape(B * Nk, D)), 1e-2)
+    report("attn bwd dv " + tag, relerr(dv, vf.grad.transpose(1, 2).reshape(B * Nk, D)), 1e-2)
+
+
+for args in [(3, 12, 99, 99, 64, True), (2, 8, 196, 99, 32, False), (2, 8, 196, 196, 32, True),
+             (1, 2, 393, 393, 64, True), (1, 2, 130, 70, 32, False), (2, 1, 17, 5, 64, False)]:
+    try:
+        attn_case(*args)
+    except Exception as e:  # noqa: BLE001
+        fails += 1
+        print("attn case %s EXC %s" % (str(args), e), flush=True)
 
 # ---- quick timing vs cuBLAS on the encoder shapes (device events, inputs > L2 not enforced here: indicative)
 def time_it(fn, iters=20):
@@ -131,14 +204,35 @@ for (M, N, K_, a_mn, b_mn, split) in [(12672, 2304, 768, 0, 0, 1), (12672, 768, 
     Bin = B.t().contiguous() if b_mn else B
     if split > 1:
         out = torch.zeros(M, N, device=dev)
-        ms = time_it(lambda: K.gemm(Ain, Bin, a_mn=bool(a_mn), b_mn=bool(b_mn), out_f32=out, split_k=split))
+        ms = time_it(lambda: KN.gemm(Ain, Bin, a_mn=bool(a_mn), b_mn=bool(b_mn), out_f32=out, split_k=split))
     else:
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        ms = time_it(lambda: K.gemm(Ain, Bin, a_mn=bool(a_mn), b_mn=bool(b_mn), out_bf16=out))
+        ms = time_it(lambda: KN.gemm(Ain, Bin, a_mn=bool(a_mn), b_mn=bool(b_mn), out_bf16=out))
     ms_ref = time_it(lambda: torch.matmul(A, B.t()))
     fl = 2.0 * M * N * K_
     print("time M=%d N=%d K=%d a_mn=%d b_mn=%d split=%d : ours %.3f ms (%.0f TF/s)  cublas %.3f ms (%.0f TF/s)" %
           (M, N, K_, a_mn, b_mn, split, ms, fl / ms / 1e9, ms_ref, fl / ms_ref / 1e9), flush=True)
+
+
+# attention timing at the encoder shape
+B_, H_, N_, dh_ = 128, 12, 99, 64
+qkv = rand_bf16(B_ * N_, 3 * H_ * dh_)
+D_ = H_ * dh_
+q, k, v = qkv[:, :D_], qkv[:, D_:2 * D_], qkv[:, 2 * D_:]
+o = torch.empty(B_ * N_, D_, device=dev, dtype=torch.bfloat16)
+ms = time_it(lambda: KN.attention_fwd(q, k, v, B_, H_, N_, N_, dh_, 0.125, out=o))
+fl = 4.0 * B_ * H_ * N_ * N_ * dh_
+print("time attn fwd enc: %.3f ms (%.1f TF/s useful)" % (ms, fl / ms / 1e9), flush=True)
+o, lse = KN.attention_fwd(q, k, v, B_, H_, N_, N_, dh_, 0.125)
+do = rand_bf16(B_ * N_, D_)
+dqkv = torch.empty_like(qkv)
+ms = time_it(lambda: KN.attention_bwd(q, k, v, o, do, lse, dqkv[:, :D_], dqkv[:, D_:2 * D_], dqkv[:, 2 * D_:], B_, H_, N_, N_, dh_, 0.125))
+print("time attn bwd enc: %.3f ms (%.1f TF/s useful)" % (ms, 2.5 * fl / ms / 1e9), flush=True)
+x = torch.randn(12672, 768, device=dev)
+gam = torch.ones(768, device=dev)
+bet = torch.zeros(768, device=dev)
+ms = time_it(lambda: KN.layernorm_fwd(x, gam, bet))
+print("time ln fwd 12672x768: %.3f ms (%.0f GB/s)" % (ms, 12672 * 768 * 6 / ms / 1e6), flush=True)
 
 print("FAILS", fails)
 sys.exit(1 if fails else 0)
