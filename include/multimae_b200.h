@@ -109,6 +109,160 @@ int mmae_attention_backward(const void* q, int64_t ldq, const void* k, int64_t l
                             float* delta_ws, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv,
                             int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Dirichlet token-mask sampler.  MultiMAE.generate_random_masks, multimae/multimae.py:189-216, as a pure
+ * function of the random draws: shares[B,T] (Dirichlet sample), noise_task[B,total] (the per-task
+ * torch.rand draws concatenated in task order), noise_all[B,total].  Outputs are int64 like the reference:
+ * task_masks[B,total] (0 = visible; split per task by the caller), ids_keep[B,num_encoded],
+ * ids_restore[B,total].  Ties break towards the lower index.
+ * ---------------------------------------------------------------------------------------------- */
+int mmae_sample_masks(const float* shares, const float* noise_task, const float* noise_all, int B, int num_tasks,
+                      const int* tokens_per_task_host, int num_encoded, int64_t* task_masks, int64_t* ids_keep,
+                      int64_t* ids_restore, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gather-first patch embedding (PatchedInputAdapter.forward multimae/input_adapters.py:97-119,
+ * SemSegInputAdapter.forward :215-241, and the cat/gather/global-token cat of multimae/multimae.py:340-347).
+ * Only the num_encoded visible patches per sample are embedded: one K-concatenated GEMM
+ * [B*T, sum_t K_t] x [D, sum_t K_t]^T whose A rows are zero outside the token's own task segment.
+ * ---------------------------------------------------------------------------------------------- */
+#define MMAE_MAX_TASKS 8
+
+typedef struct mmae_embed_layout {
+  int num_tasks;
+  int grid_h[MMAE_MAX_TASKS], grid_w[MMAE_MAX_TASKS]; /* patch grid of each task at the current image size */
+  int tok_offset[MMAE_MAX_TASKS + 1];                 /* token range of each task in the concatenated sequence */
+  int k_offset[MMAE_MAX_TASKS + 1];                   /* K segment of each task (K_t = channels * patch^2) */
+  int patch[MMAE_MAX_TASKS];                          /* P_H = P_W in input pixels (16, 16, 4) */
+  int channels[MMAE_MAX_TASKS];                       /* image channels, or dim_class_emb for semseg */
+  int is_semseg[MMAE_MAX_TASKS];
+  int num_classes[MMAE_MAX_TASKS];
+} mmae_embed_layout;
+
+typedef struct mmae_embed_inputs {
+  const void* data[MMAE_MAX_TASKS];       /* fp32 [B,C,H,W]  or  int64 [B,H,W] class ids */
+  const float* class_emb[MMAE_MAX_TASKS]; /* [num_classes, dim_class_emb] (semseg) or NULL */
+} mmae_embed_inputs;
+
+typedef struct mmae_embed_params {
+  const float* weight[MMAE_MAX_TASKS]; /* proj.weight viewed as [D, C*P*P] */
+  const float* bias[MMAE_MAX_TASKS];   /* proj.bias [D] */
+  const float* pos[MMAE_MAX_TASKS];    /* [N_t, D] rows of the (resized) positional table */
+  const float* global_tokens;          /* [G, D] */
+} mmae_embed_params;
+
+typedef struct mmae_embed_grads {      /* accumulated (+=) */
+  float* weight[MMAE_MAX_TASKS];
+  float* bias[MMAE_MAX_TASKS];
+  float* class_emb[MMAE_MAX_TASKS];
+  float* global_tokens;
+} mmae_embed_grads;
+
+int64_t mmae_embed_saved_bytes(const mmae_embed_layout* layout, int B, int T, int D);
+int64_t mmae_embed_workspace_bytes(const mmae_embed_layout* layout, int B, int T, int D);
+/* x_out: [B, T+G, D] fp32 packed encoder input (global tokens last) */
+int mmae_embed_forward(const mmae_embed_layout* layout, const mmae_embed_inputs* in, const mmae_embed_params* prm,
+                       const int64_t* ids_keep, int B, int T, int G, int D, float* x_out, void* saved, void* ws,
+                       void* stream);
+int mmae_embed_backward(const mmae_embed_layout* layout, const mmae_embed_inputs* in, const mmae_embed_params* prm,
+                        const mmae_embed_grads* grads, const int64_t* ids_keep, int B, int T, int G, int D,
+                        const float* dx, const void* saved, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pre-LN transformer block (Block / Attention / Mlp, multimae/multimae_utils.py:138-182, 217-232); used by the
+ * encoder (D=768/1024) and the decoder transformer layers (D=256).  x: [B, N, D] fp32 residual stream.
+ * `saved` keeps the bf16 operands needed by backward; sizes from the *_bytes queries.  Gradients of the
+ * parameters are ACCUMULATED (+=) into `grads` (zero them once per step).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mmae_block_params {
+  const float *norm1_w, *norm1_b, *qkv_w, *qkv_b, *proj_w, *proj_b, *norm2_w, *norm2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} mmae_block_params;
+typedef struct mmae_block_grads {
+  float *norm1_w, *norm1_b, *qkv_w, *qkv_b, *proj_w, *proj_b, *norm2_w, *norm2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} mmae_block_grads;
+
+int64_t mmae_block_saved_bytes(int B, int N, int D, int H, int hidden);
+int64_t mmae_block_workspace_bytes(int B, int N, int D, int H, int hidden);
+int mmae_block_forward(const float* x_in, float* x_out, int B, int N, int D, int H, int hidden, float eps,
+                       const mmae_block_params* prm, void* saved, void* ws, void* stream);
+int mmae_block_backward(const float* x_in, const float* dx_out, float* dx_in, int B, int N, int D, int H, int hidden,
+                        const mmae_block_params* prm, const mmae_block_grads* grads, const void* saved, void* ws,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SpatialOutputAdapter, split at its decoder_transformer (multimae/output_adapters.py:236-282):
+ *   head: proj_context -> queries/context construction (get_queries_and_context :183-234) -> LayerNorms ->
+ *         CrossAttention (no residual) -> x + mlp(out_norm(x))                                   (:258-266)
+ *   tail: out_proj + un-patchify to [B, C, H, W]                                                (:274-280)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct mmae_decoder_index {
+  int batch, dim, num_visible, num_global, num_queries, total_tokens, num_tasks, own_task;
+  int tok_offset[MMAE_MAX_TASKS + 1];
+  const int64_t* ids_keep;    /* [B, num_visible] */
+  const int64_t* ids_restore; /* [B, total_tokens] */
+} mmae_decoder_index;
+
+typedef struct mmae_dechead_params {
+  const float *proj_context_w, *proj_context_b, *mask_token, *pos;  /* pos: [num_queries, Dd] resized table rows */
+  const float* task_emb[MMAE_MAX_TASKS];                           /* [Dd] per context task or NULL */
+  const float *context_norm_w, *context_norm_b, *query_norm_w, *query_norm_b, *out_norm_w, *out_norm_b;
+  const float *q_w, *q_b, *kv_w, *kv_b, *proj_w, *proj_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} mmae_dechead_params;
+typedef struct mmae_dechead_grads {
+  float *proj_context_w, *proj_context_b, *mask_token;
+  float* task_emb[MMAE_MAX_TASKS];
+  float *context_norm_w, *context_norm_b, *query_norm_w, *query_norm_b, *out_norm_w, *out_norm_b;
+  float *q_w, *q_b, *kv_w, *kv_b, *proj_w, *proj_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} mmae_dechead_grads;
+
+int64_t mmae_dechead_saved_bytes(const mmae_decoder_index* ix, int D_enc, int H, int hidden);
+int64_t mmae_dechead_workspace_bytes(const mmae_decoder_index* ix, int D_enc, int H, int hidden);
+/* enc: [B, T+G, D_enc] fp32 encoder output; x_out: [B, num_queries, Dd] fp32 */
+int mmae_dechead_forward(const float* enc, int D_enc, const mmae_decoder_index* ix, int H, int hidden, float eps,
+                         const mmae_dechead_params* prm, float* x_out, void* saved, void* ws, void* stream);
+/* denc is ACCUMULATED (+=): the four adapters share one encoder-output gradient */
+int mmae_dechead_backward(const float* enc, int D_enc, const mmae_decoder_index* ix, int H, int hidden,
+                          const mmae_dechead_params* prm, const mmae_dechead_grads* grads, const float* dx_out,
+                          float* denc, const void* saved, void* ws, void* stream);
+
+int64_t mmae_dectail_saved_bytes(int B, int nh, int nw, int Dd, int C, int P);
+int64_t mmae_dectail_workspace_bytes(int B, int nh, int nw, int Dd, int C, int P);
+/* x: [B, nh*nw, Dd] fp32 -> pred [B, C, nh*P, nw*P] fp32 */
+int mmae_dectail_forward(const float* x, int B, int nh, int nw, int Dd, int C, int P, const float* out_w,
+                         const float* out_b, float* pred, void* saved, void* ws, void* stream);
+int mmae_dectail_backward(const float* dpred, int B, int nh, int nw, int Dd, int C, int P, const float* out_w,
+                          float* d_out_w, float* d_out_b, float* dx, const void* saved, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Masked reconstruction losses (multimae/criterion.py:37-57, 84-114, 141-171).
+ * kind: 0 = MSE, 1 = L1, 2 = cross-entropy (pred = logits [B,C,H,W], target = int64 [B,H,W]).
+ * mask: int64 [B, (H/scale)*(W/scale)] (non-zero = contributes) or NULL (plain mean).  ws: 2*B floats kept until
+ * backward.  loss_out / grad_out are device scalars.  No host synchronisation (mask.sum()==0 -> 0 on device).
+ * ---------------------------------------------------------------------------------------------- */
+int mmae_masked_loss_forward(int kind, int norm_pix, float label_smoothing, const float* pred, const void* target,
+                             const int64_t* mask, int B, int C, int H, int W, int scale, float* ws, float* loss_out,
+                             void* stream);
+int mmae_masked_loss_backward(int kind, int norm_pix, float label_smoothing, const float* pred, const void* target,
+                              const int64_t* mask, int B, int C, int H, int W, int scale, const float* ws,
+                              const float* grad_out, float* dpred, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Flat-buffer gradient post-processing and AdamW (utils/native_scaler.py:34-36, 49-62; torch.optim.AdamW as built
+ * by utils/optim_factory.py:155-174).  out2[0] = sum of squares AFTER unscaling, out2[1] = 1 if a non-finite
+ * gradient was seen; grads *= inv_scale * post_scale (inv_scale read from inv_scale_dev when non-NULL).
+ * ---------------------------------------------------------------------------------------------- */
+int mmae_grad_unscale_norm(float* grads, int64_t n, const float* inv_scale_dev, float inv_scale, float post_scale,
+                           float* out2, float* norm_out, void* stream);
+int mmae_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, const float* found_inf_dev,
+                    void* stream);
+
+/* image <-> token layout helpers ('b (nh nw) (c ph pw) <-> b c (nh ph) (nw pw)') */
+int mmae_unpatchify(const float* tokens, int64_t ld_tok, float* image, int B, int C, int nh, int nw, int P,
+                    void* stream);
+int mmae_patchify_bf16(const float* image, void* tokens_bf16, int64_t ld_tok, int B, int C, int nh, int nw, int P,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,67 @@ class GemmEpilogue(ctypes.Structure):
     ]
 
 
+MAX_TASKS = 8
+c_float_p = c_void_p  # device pointers travel as integers
+
+
+class EmbedLayout(ctypes.Structure):
+    _fields_ = [
+        ("num_tasks", c_int),
+        ("grid_h", c_int * MAX_TASKS), ("grid_w", c_int * MAX_TASKS),
+        ("tok_offset", c_int * (MAX_TASKS + 1)),
+        ("k_offset", c_int * (MAX_TASKS + 1)),
+        ("patch", c_int * MAX_TASKS), ("channels", c_int * MAX_TASKS),
+        ("is_semseg", c_int * MAX_TASKS), ("num_classes", c_int * MAX_TASKS),
+    ]
+
+
+class EmbedInputs(ctypes.Structure):
+    _fields_ = [("data", c_void_p * MAX_TASKS), ("class_emb", c_void_p * MAX_TASKS)]
+
+
+class EmbedParams(ctypes.Structure):
+    _fields_ = [("weight", c_void_p * MAX_TASKS), ("bias", c_void_p * MAX_TASKS), ("pos", c_void_p * MAX_TASKS),
+                ("global_tokens", c_void_p)]
+
+
+class EmbedGrads(ctypes.Structure):
+    _fields_ = [("weight", c_void_p * MAX_TASKS), ("bias", c_void_p * MAX_TASKS), ("class_emb", c_void_p * MAX_TASKS),
+                ("global_tokens", c_void_p)]
+
+
+BLOCK_FIELDS = ["norm1_w", "norm1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "norm2_w", "norm2_b", "fc1_w", "fc1_b",
+                "fc2_w", "fc2_b"]
+
+
+class BlockParams(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in BLOCK_FIELDS]
+
+
+class BlockGrads(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in BLOCK_FIELDS]
+
+
+class DecoderIndex(ctypes.Structure):
+    _fields_ = [("batch", c_int), ("dim", c_int), ("num_visible", c_int), ("num_global", c_int),
+                ("num_queries", c_int), ("total_tokens", c_int), ("num_tasks", c_int), ("own_task", c_int),
+                ("tok_offset", c_int * (MAX_TASKS + 1)), ("ids_keep", c_void_p), ("ids_restore", c_void_p)]
+
+
+HEAD_TAIL_FIELDS = ["context_norm_w", "context_norm_b", "query_norm_w", "query_norm_b", "out_norm_w", "out_norm_b",
+                    "q_w", "q_b", "kv_w", "kv_b", "proj_w", "proj_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b"]
+
+
+class DecHeadParams(ctypes.Structure):
+    _fields_ = ([("proj_context_w", c_void_p), ("proj_context_b", c_void_p), ("mask_token", c_void_p),
+                 ("pos", c_void_p), ("task_emb", c_void_p * MAX_TASKS)] + [(n, c_void_p) for n in HEAD_TAIL_FIELDS])
+
+
+class DecHeadGrads(ctypes.Structure):
+    _fields_ = ([("proj_context_w", c_void_p), ("proj_context_b", c_void_p), ("mask_token", c_void_p),
+                 ("task_emb", c_void_p * MAX_TASKS)] + [(n, c_void_p) for n in HEAD_TAIL_FIELDS])
+
+
 class MmaeError(RuntimeError):
     pass
 
@@ -61,6 +122,44 @@ SIGNATURES = {
     "mmae_attention_backward": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p,
                                         c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64,
                                         c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "mmae_sample_masks": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_int), c_int, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "mmae_embed_saved_bytes": (c_i64, [ctypes.POINTER(EmbedLayout), c_int, c_int, c_int]),
+    "mmae_embed_workspace_bytes": (c_i64, [ctypes.POINTER(EmbedLayout), c_int, c_int, c_int]),
+    "mmae_embed_forward": (c_int, [ctypes.POINTER(EmbedLayout), ctypes.POINTER(EmbedInputs), ctypes.POINTER(EmbedParams),
+                                   c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmae_embed_backward": (c_int, [ctypes.POINTER(EmbedLayout), ctypes.POINTER(EmbedInputs),
+                                    ctypes.POINTER(EmbedParams), ctypes.POINTER(EmbedGrads), c_void_p, c_int, c_int,
+                                    c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmae_block_saved_bytes": (c_i64, [c_int] * 5),
+    "mmae_block_workspace_bytes": (c_i64, [c_int] * 5),
+    "mmae_block_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                   ctypes.POINTER(BlockParams), c_void_p, c_void_p, c_void_p]),
+    "mmae_block_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                    ctypes.POINTER(BlockParams), ctypes.POINTER(BlockGrads), c_void_p, c_void_p,
+                                    c_void_p]),
+    "mmae_dechead_saved_bytes": (c_i64, [ctypes.POINTER(DecoderIndex), c_int, c_int, c_int]),
+    "mmae_dechead_workspace_bytes": (c_i64, [ctypes.POINTER(DecoderIndex), c_int, c_int, c_int]),
+    "mmae_dechead_forward": (c_int, [c_void_p, c_int, ctypes.POINTER(DecoderIndex), c_int, c_int, c_float,
+                                     ctypes.POINTER(DecHeadParams), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmae_dechead_backward": (c_int, [c_void_p, c_int, ctypes.POINTER(DecoderIndex), c_int, c_int,
+                                      ctypes.POINTER(DecHeadParams), ctypes.POINTER(DecHeadGrads), c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    "mmae_dectail_saved_bytes": (c_i64, [c_int] * 6),
+    "mmae_dectail_workspace_bytes": (c_i64, [c_int] * 6),
+    "mmae_dectail_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
+    "mmae_dectail_backward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmae_masked_loss_forward": (c_int, [c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_int, c_void_p, c_void_p, c_void_p]),
+    "mmae_masked_loss_backward": (c_int, [c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmae_grad_unscale_norm": (c_int, [c_void_p, c_i64, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "mmae_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float,
+                                c_float, c_int, c_void_p, c_void_p]),
+    "mmae_unpatchify": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mmae_patchify_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 ABI_VERSION = 1

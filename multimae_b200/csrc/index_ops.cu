@@ -8,6 +8,8 @@
 #include "common.cuh"
 #include "../../include/multimae_b200.h"
 
+#include "internal.h"
+
 namespace mmae {
 void count_launch();
 namespace {
@@ -38,8 +40,8 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(mmae_embed_layout L, 
     row_task[r] = t;
     row_patch[r] = p;
   }
-  const int P = L.patch[t], C = L.channels[t], Wt = L.grid_w * P, Ht = L.grid_h * P;
-  const int ph = p / L.grid_w, pw = p % L.grid_w;
+  const int P = L.patch[t], C = L.channels[t], Wt = L.grid_w[t] * P, Ht = L.grid_h[t] * P;
+  const int ph = p / L.grid_w[t], pw = p % L.grid_w[t];
   const int k_begin = L.k_offset[t], k_end = L.k_offset[t + 1];
   bf16* Ar = A + int64_t(r) * L.k_offset[L.num_tasks];
   const bf16 zero = __float2bfloat16_rn(0.f);
@@ -161,14 +163,13 @@ __global__ void __launch_bounds__(256) semseg_emb_bwd_kernel(const bf16* __restr
 // One CTA row per output row; rows [0, B*P) are queries, rows [B*P, B*P + B*(T+G)) are context.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) dec_build_kernel(const float* __restrict__ ctx, mmae_decoder_index ix,
-                                                       const float* __restrict__ mask_token,
-                                                       const float* __restrict__ task_emb,  // [num_tasks, Dd] (zeros if absent)
-                                                       const float* __restrict__ pos,       // [P, Dd]
+                                                       const float* __restrict__ mask_token, TaskEmbPtrs task_emb,
+                                                       const float* __restrict__ pos,  // [P, Dd]
                                                        float* __restrict__ queries, float* __restrict__ context) {
   const int Dd = ix.dim, T = ix.num_visible, G = ix.num_global, P = ix.num_queries;
   const int row = blockIdx.x;
   const int nq_rows = ix.batch * P;
-  const float4 *base, *te, *pe = nullptr;
+  const float4 *base, *te = nullptr, *pe = nullptr;
   float4* dst;
   if (row < nq_rows) {
     const int b = row / P, j = row % P;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(64) dec_build_kernel(const float* __restrict__
     const int rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
     base = rank < T ? reinterpret_cast<const float4*>(ctx + (int64_t(b) * (T + G) + rank) * Dd)
                     : reinterpret_cast<const float4*>(mask_token);
-    te = reinterpret_cast<const float4*>(task_emb + int64_t(ix.own_task) * Dd);
+    te = reinterpret_cast<const float4*>(task_emb.p[ix.own_task]);
     pe = reinterpret_cast<const float4*>(pos + int64_t(j) * Dd);
     dst = reinterpret_cast<float4*>(queries + int64_t(row) * Dd);
   } else {
@@ -185,21 +186,26 @@ __global__ void __launch_bounds__(64) dec_build_kernel(const float* __restrict__
     base = reinterpret_cast<const float4*>(ctx + int64_t(cr) * Dd);
     dst = reinterpret_cast<float4*>(context + int64_t(cr) * Dd);
     te = nullptr;
+    pe = nullptr;
     if (i < T) {
       const int g = (int)ix.ids_keep[int64_t(b) * T + i];
       int t = 0;
 #pragma unroll
       for (int q = 1; q < MMAE_MAX_TASKS; ++q)
         if (q < ix.num_tasks && g >= ix.tok_offset[q]) t = q;
-      te = reinterpret_cast<const float4*>(task_emb + int64_t(t) * Dd);
+      te = reinterpret_cast<const float4*>(task_emb.p[t]);
       pe = reinterpret_cast<const float4*>(pos + int64_t(g - ix.tok_offset[t]) * Dd);
     }
   }
   for (int c = threadIdx.x; c < Dd / 4; c += blockDim.x) {
     float4 v = __ldg(base + c);
+    if (pe) {
+      const float4 p4 = __ldg(pe + c);
+      v.x += p4.x; v.y += p4.y; v.z += p4.z; v.w += p4.w;
+    }
     if (te) {
-      const float4 a = __ldg(te + c), p4 = __ldg(pe + c);
-      v.x += a.x + p4.x; v.y += a.y + p4.y; v.z += a.z + p4.z; v.w += a.w + p4.w;
+      const float4 a = __ldg(te + c);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
     }
     dst[c] = v;
   }
@@ -211,7 +217,7 @@ constexpr int DB_ROWS = 16;
 __global__ void __launch_bounds__(256) dec_build_bwd_kernel(const float* __restrict__ dqueries,
                                                             const float* __restrict__ dcontext, mmae_decoder_index ix,
                                                             float* __restrict__ dctx, float* __restrict__ dmask_token,
-                                                            float* __restrict__ dtask_emb) {
+                                                            TaskEmbGradPtrs dtask_emb) {
   const int Dd = ix.dim, T = ix.num_visible, G = ix.num_global, P = ix.num_queries;
   const int nq_rows = ix.batch * P, nc_rows = ix.batch * (T + G);
   const int row0 = blockIdx.x * DB_ROWS;
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(256) dec_build_bwd_kernel(const float* __restr
     if (acc_mask != 0.f) atomicAdd(dmask_token + col, acc_mask);
 #pragma unroll
     for (int t = 0; t < MMAE_MAX_TASKS; ++t)
-      if (t < ix.num_tasks && acc_te[t] != 0.f) atomicAdd(dtask_emb + int64_t(t) * Dd + col, acc_te[t]);
+      if (t < ix.num_tasks && dtask_emb.p[t] != nullptr && acc_te[t] != 0.f) atomicAdd(dtask_emb.p[t] + col, acc_te[t]);
   }
 }
 
@@ -338,7 +344,7 @@ int launch_semseg_emb_bwd(const bf16* dA, int64_t ld_dA, const int64_t* labels, 
   return MMAE_OK;
 }
 
-int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float* mask_token, const float* task_emb,
+int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float* mask_token, const TaskEmbPtrs& task_emb,
                      const float* pos, float* queries, float* context, cudaStream_t st) {
   const int rows = ix.batch * ix.num_queries + ix.batch * (ix.num_visible + ix.num_global);
   dec_build_kernel<<<rows, 64, 0, st>>>(ctx, ix, mask_token, task_emb, pos, queries, context);
@@ -348,7 +354,7 @@ int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float
 }
 
 int launch_dec_build_bwd(const float* dqueries, const float* dcontext, const mmae_decoder_index& ix, float* dctx,
-                         float* dmask_token, float* dtask_emb, cudaStream_t st) {
+                         float* dmask_token, const TaskEmbGradPtrs& dtask_emb, cudaStream_t st) {
   const int rows = ix.batch * ix.num_queries + ix.batch * (ix.num_visible + ix.num_global);
   dec_build_bwd_kernel<<<ceil_div(rows, DB_ROWS), 256, 0, st>>>(dqueries, dcontext, ix, dctx, dmask_token, dtask_emb);
   count_launch();

@@ -1,0 +1,34 @@
+// Internal (non-ABI) declarations shared between the kernel files and modules.cu.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+#include "../../include/multimae_b200.h"
+
+namespace mmae {
+
+struct TaskEmbPtrs {
+  const float* p[MMAE_MAX_TASKS];
+};
+struct TaskEmbGradPtrs {
+  float* p[MMAE_MAX_TASKS];
+};
+
+void count_launch();
+
+int launch_embed_gather(const mmae_embed_layout& L, const mmae_embed_inputs& in, const int64_t* ids_keep, int B, int T,
+                        bf16* A, int* row_task, int* row_patch, cudaStream_t st);
+int launch_embed_assemble(const float* Cmat, const mmae_embed_params& prm, const int* row_task, const int* row_patch,
+                          int B, int T, int G, int D, float* x, cudaStream_t st);
+int launch_embed_assemble_bwd(const float* dx, int B, int T, int G, int D, const int* row_task, bf16* dC,
+                              const mmae_embed_grads& grads, int num_tasks, cudaStream_t st);
+int launch_semseg_emb_bwd(const bf16* dA, int64_t ld_dA, const int64_t* labels, const int64_t* ids_keep,
+                          const int* row_task, const int* row_patch, int task, int T, int rows, int grid_w, int grid_h,
+                          int P, int E, int num_classes, float* dtable, cudaStream_t st);
+int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float* mask_token, const TaskEmbPtrs& task_emb,
+                     const float* pos, float* queries, float* context, cudaStream_t st);
+int launch_dec_build_bwd(const float* dqueries, const float* dcontext, const mmae_decoder_index& ix, float* dctx,
+                         float* dmask_token, const TaskEmbGradPtrs& dtask_emb, cudaStream_t st);
+int launch_cast2d(const float* src, int64_t ld_src, bf16* dst, int64_t ld_dst, int rows, int cols, cudaStream_t st);
+
+}  // namespace mmae

@@ -1,0 +1,546 @@
+// Module-level entry points of the C ABI: each one is the forward or backward of one reference nn.Module on the hot
+// path, expressed as a fixed sequence of the kernels in this library (tcgen05 GEMMs with fused epilogues, LayerNorm,
+// fused attention, index kernels).  The host passes raw device pointers; all scratch ("ws") and saved-for-backward
+// ("saved") memory is caller-provided, sized by the *_bytes queries, so nothing here allocates.
+#include "internal.h"
+
+namespace mmae {
+namespace {
+
+struct Carver {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(reinterpret_cast<uint8_t*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+int pick_split(int M, int N, int K) {
+  const int tiles = ceil_div(M, 128) * ceil_div(N, 128);
+  int s = (2 * sm_count()) / std::max(tiles, 1);
+  const int kb = ceil_div(K, 64);
+  s = std::min(s, std::max(1, kb / 4));
+  return std::max(s, 1);
+}
+
+mmae_gemm_epilogue ep_zero() {
+  mmae_gemm_epilogue ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.alpha = 1.0f;
+  return ep;
+}
+
+// y = x W^T + b  (bf16 out), W: [N, K]
+int linear_bf16(const bf16* x, const bf16* W, const float* b, bf16* y, int M, int N, int K, void* st) {
+  mmae_gemm_epilogue ep = ep_zero();
+  ep.bias = b;
+  ep.out_bf16 = y;
+  ep.ld_out_bf16 = N;
+  return mmae_gemm_bf16(x, K, 0, W, K, 0, M, N, K, 1, &ep, st);
+}
+// y = x W^T + b (+ residual) (fp32 out)
+int linear_f32(const bf16* x, const bf16* W, const float* b, const float* resid, float* y, int M, int N, int K,
+               void* st) {
+  mmae_gemm_epilogue ep = ep_zero();
+  ep.bias = b;
+  ep.residual = resid;
+  ep.ld_residual = N;
+  ep.out_f32 = y;
+  ep.ld_out_f32 = N;
+  return mmae_gemm_bf16(x, K, 0, W, K, 0, M, N, K, 1, &ep, st);
+}
+// z = x W^T + b (bf16, saved), a = gelu(z) (bf16)
+int linear_gelu(const bf16* x, const bf16* W, const float* b, bf16* z, bf16* a, int M, int N, int K, void* st) {
+  mmae_gemm_epilogue ep = ep_zero();
+  ep.bias = b;
+  ep.act = 1;
+  ep.preact_bf16 = z;
+  ep.ld_preact = N;
+  ep.out_bf16 = a;
+  ep.ld_out_bf16 = N;
+  return mmae_gemm_bf16(x, K, 0, W, K, 0, M, N, K, 1, &ep, st);
+}
+// dx[M, Kin] = dy[M, Nout] W[Nout, Kin]  (bf16 out; optional * gelu'(z))
+int dgrad_bf16(const bf16* dy, int64_t lddy, const bf16* W, const bf16* dgelu_z, bf16* dx, int M, int Nout, int Kin,
+               void* st) {
+  mmae_gemm_epilogue ep = ep_zero();
+  ep.dgelu_z = dgelu_z;
+  ep.ld_dgelu_z = Kin;
+  ep.out_bf16 = dx;
+  ep.ld_out_bf16 = Kin;
+  return mmae_gemm_bf16(dy, lddy, 0, W, Kin, 1, M, Kin, Nout, 1, &ep, st);
+}
+// dW[Nout, Kin] += dy[M, Nout]^T x[M, Kin]
+int wgrad(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, float* dW, int M, int Nout, int Kin, void* st) {
+  mmae_gemm_epilogue ep = ep_zero();
+  ep.accumulate = 1;
+  ep.out_f32 = dW;
+  ep.ld_out_f32 = Kin;
+  return mmae_gemm_bf16(dy, lddy, 1, x, ldx, 1, Nout, Kin, M, pick_split(Nout, Kin, M), &ep, st);
+}
+
+#define RUN(expr)             \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != MMAE_OK) return _rc; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------ block
+struct BlockSaved {
+  bf16 *wqkv, *wproj, *w1, *w2, *h1, *qkv, *o, *h2, *z, *a;
+  float *mean1, *rstd1, *mean2, *rstd2, *lse, *x_mid;
+  size_t bytes;
+};
+BlockSaved block_saved(void* base, int B, int N, int D, int H, int hid) {
+  Carver c(base);
+  const size_t M = size_t(B) * N;
+  BlockSaved s;
+  s.wqkv = c.take<bf16>(size_t(3) * D * D);
+  s.wproj = c.take<bf16>(size_t(D) * D);
+  s.w1 = c.take<bf16>(size_t(hid) * D);
+  s.w2 = c.take<bf16>(size_t(D) * hid);
+  s.mean1 = c.take<float>(M);
+  s.rstd1 = c.take<float>(M);
+  s.mean2 = c.take<float>(M);
+  s.rstd2 = c.take<float>(M);
+  s.h1 = c.take<bf16>(M * D);
+  s.qkv = c.take<bf16>(M * 3 * D);
+  s.lse = c.take<float>(size_t(B) * H * N);
+  s.o = c.take<bf16>(M * D);
+  s.x_mid = c.take<float>(M * D);
+  s.h2 = c.take<bf16>(M * D);
+  s.z = c.take<bf16>(M * hid);
+  s.a = c.take<bf16>(M * hid);
+  s.bytes = align_up(c.off, 256);
+  return s;
+}
+struct BlockWs {
+  bf16 *g, *big, *dh, *d_o;
+  float *dx_mid, *delta;
+  size_t bytes;
+};
+BlockWs block_ws(void* base, int B, int N, int D, int H, int hid) {
+  Carver c(base);
+  const size_t M = size_t(B) * N;
+  BlockWs w;
+  w.g = c.take<bf16>(M * D);
+  w.big = c.take<bf16>(M * std::max(hid, 3 * D));
+  w.dh = c.take<bf16>(M * D);
+  w.d_o = c.take<bf16>(M * D);
+  w.dx_mid = c.take<float>(M * D);
+  w.delta = c.take<float>(size_t(B) * H * N);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+
+// --------------------------------------------------------------------------------------------------- decoder head
+struct HeadSaved {
+  bf16 *enc_b, *wpc, *wq, *wkv, *wproj, *w1, *w2, *qn, *cn, *q, *kv, *o, *h, *z, *a;
+  float *queries, *context, *qmean, *qrstd, *cmean, *crstd, *omean, *orstd, *lse, *x0;
+  size_t bytes;
+};
+HeadSaved head_saved(void* base, const mmae_decoder_index& ix, int De, int H, int hid) {
+  Carver c(base);
+  const size_t Dd = ix.dim, Mq = size_t(ix.batch) * ix.num_queries,
+               Mc = size_t(ix.batch) * (ix.num_visible + ix.num_global);
+  HeadSaved s;
+  s.enc_b = c.take<bf16>(Mc * De);
+  s.wpc = c.take<bf16>(Dd * De);
+  s.wq = c.take<bf16>(Dd * Dd);
+  s.wkv = c.take<bf16>(2 * Dd * Dd);
+  s.wproj = c.take<bf16>(Dd * Dd);
+  s.w1 = c.take<bf16>(size_t(hid) * Dd);
+  s.w2 = c.take<bf16>(Dd * hid);
+  s.queries = c.take<float>(Mq * Dd);
+  s.context = c.take<float>(Mc * Dd);
+  s.qmean = c.take<float>(Mq);
+  s.qrstd = c.take<float>(Mq);
+  s.cmean = c.take<float>(Mc);
+  s.crstd = c.take<float>(Mc);
+  s.omean = c.take<float>(Mq);
+  s.orstd = c.take<float>(Mq);
+  s.qn = c.take<bf16>(Mq * Dd);
+  s.cn = c.take<bf16>(Mc * Dd);
+  s.q = c.take<bf16>(Mq * Dd);
+  s.kv = c.take<bf16>(Mc * 2 * Dd);
+  s.lse = c.take<float>(size_t(ix.batch) * H * ix.num_queries);
+  s.o = c.take<bf16>(Mq * Dd);
+  s.x0 = c.take<float>(Mq * Dd);
+  s.h = c.take<bf16>(Mq * Dd);
+  s.z = c.take<bf16>(Mq * hid);
+  s.a = c.take<bf16>(Mq * hid);
+  s.bytes = align_up(c.off, 256);
+  return s;
+}
+struct HeadWs {
+  float *ctx, *dx0, *dqueries, *dcontext, *dctx, *delta;
+  bf16 *g, *dz, *dh, *d_o, *dq, *dkv, *dqn, *dcn, *dctx_b;
+  size_t bytes;
+};
+HeadWs head_ws(void* base, const mmae_decoder_index& ix, int De, int H, int hid) {
+  Carver c(base);
+  const size_t Dd = ix.dim, Mq = size_t(ix.batch) * ix.num_queries,
+               Mc = size_t(ix.batch) * (ix.num_visible + ix.num_global);
+  HeadWs w;
+  w.ctx = c.take<float>(Mc * Dd);
+  w.dx0 = c.take<float>(Mq * Dd);
+  w.dqueries = c.take<float>(Mq * Dd);
+  w.dcontext = c.take<float>(Mc * Dd);
+  w.dctx = c.take<float>(Mc * Dd);
+  w.delta = c.take<float>(size_t(ix.batch) * H * ix.num_queries);
+  w.g = c.take<bf16>(Mq * Dd);
+  w.dz = c.take<bf16>(Mq * hid);
+  w.dh = c.take<bf16>(Mq * Dd);
+  w.d_o = c.take<bf16>(Mq * Dd);
+  w.dq = c.take<bf16>(Mq * Dd);
+  w.dkv = c.take<bf16>(Mc * 2 * Dd);
+  w.dqn = c.take<bf16>(Mq * Dd);
+  w.dcn = c.take<bf16>(Mc * Dd);
+  w.dctx_b = c.take<bf16>(Mc * Dd);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------------ embed
+struct EmbedSaved {
+  bf16* A;
+  int *row_task, *row_patch;
+  size_t bytes;
+};
+EmbedSaved embed_saved(void* base, const mmae_embed_layout& L, int B, int T) {
+  Carver c(base);
+  EmbedSaved s;
+  s.A = c.take<bf16>(size_t(B) * T * L.k_offset[L.num_tasks]);
+  s.row_task = c.take<int>(size_t(B) * T);
+  s.row_patch = c.take<int>(size_t(B) * T);
+  s.bytes = align_up(c.off, 256);
+  return s;
+}
+struct EmbedWs {
+  bf16 *Wcat, *dC, *dA;
+  float* Cmat;
+  size_t bytes;
+};
+EmbedWs embed_ws(void* base, const mmae_embed_layout& L, int B, int T, int D) {
+  Carver c(base);
+  EmbedWs w;
+  const size_t Kcat = L.k_offset[L.num_tasks];
+  size_t kmax = 0;
+  for (int t = 0; t < L.num_tasks; ++t) kmax = std::max<size_t>(kmax, L.k_offset[t + 1] - L.k_offset[t]);
+  w.Wcat = c.take<bf16>(size_t(D) * Kcat);
+  w.Cmat = c.take<float>(size_t(B) * T * D);
+  w.dC = c.take<bf16>(size_t(B) * T * D);
+  w.dA = c.take<bf16>(size_t(B) * T * kmax);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+
+}  // namespace
+}  // namespace mmae
+
+using namespace mmae;
+
+// ====================================================================================================== block
+extern "C" int64_t mmae_block_saved_bytes(int B, int N, int D, int H, int hidden) {
+  return (int64_t)block_saved(nullptr, B, N, D, H, hidden).bytes;
+}
+extern "C" int64_t mmae_block_workspace_bytes(int B, int N, int D, int H, int hidden) {
+  return (int64_t)block_ws(nullptr, B, N, D, H, hidden).bytes;
+}
+
+extern "C" int mmae_block_forward(const float* x_in, float* x_out, int B, int N, int D, int H, int hidden, float eps,
+                                  const mmae_block_params* p, void* saved, void* ws, void* st) {
+  (void)ws;
+  MMAE_CHECK(x_in && x_out && p && saved && B > 0 && N > 0 && H > 0 && D % H == 0, MMAE_ERR_ARG,
+             "mmae_block_forward: bad args");
+  const int M = B * N, dh = D / H;
+  BlockSaved s = block_saved(saved, B, N, D, H, hidden);
+  RUN(mmae_cast_f32_to_bf16(p->qkv_w, s.wqkv, int64_t(3) * D * D, st));
+  RUN(mmae_cast_f32_to_bf16(p->proj_w, s.wproj, int64_t(D) * D, st));
+  RUN(mmae_cast_f32_to_bf16(p->fc1_w, s.w1, int64_t(hidden) * D, st));
+  RUN(mmae_cast_f32_to_bf16(p->fc2_w, s.w2, int64_t(D) * hidden, st));
+  // x = x + attn(norm1(x))                                       multimae_utils.py:230
+  RUN(mmae_layernorm_forward(x_in, D, p->norm1_w, p->norm1_b, s.h1, D, nullptr, 0, s.mean1, s.rstd1, M, D, eps, st));
+  RUN(linear_bf16(s.h1, s.wqkv, p->qkv_b, s.qkv, M, 3 * D, D, st));
+  RUN(mmae_attention_forward(s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o, D, s.lse, B, H, N, N, dh,
+                             1.0f / sqrtf((float)dh), st));
+  RUN(linear_f32(s.o, s.wproj, p->proj_b, x_in, s.x_mid, M, D, D, st));
+  // x = x + mlp(norm2(x))                                        multimae_utils.py:231
+  RUN(mmae_layernorm_forward(s.x_mid, D, p->norm2_w, p->norm2_b, s.h2, D, nullptr, 0, s.mean2, s.rstd2, M, D, eps, st));
+  RUN(linear_gelu(s.h2, s.w1, p->fc1_b, s.z, s.a, M, hidden, D, st));
+  RUN(linear_f32(s.a, s.w2, p->fc2_b, s.x_mid, x_out, M, D, hidden, st));
+  return MMAE_OK;
+}
+
+extern "C" int mmae_block_backward(const float* x_in, const float* dx_out, float* dx_in, int B, int N, int D, int H,
+                                   int hidden, const mmae_block_params* p, const mmae_block_grads* g, const void* saved,
+                                   void* ws, void* st) {
+  MMAE_CHECK(x_in && dx_out && dx_in && p && g && saved && ws, MMAE_ERR_ARG, "mmae_block_backward: bad args");
+  const int M = B * N, dh = D / H;
+  BlockSaved s = block_saved(const_cast<void*>(saved), B, N, D, H, hidden);
+  BlockWs w = block_ws(ws, B, N, D, H, hidden);
+  // ---- MLP branch
+  RUN(mmae_cast_colsum_f32(dx_out, D, w.g, D, g->fc2_b, M, D, st));
+  RUN(dgrad_bf16(w.g, D, s.w2, s.z, w.big, M, D, hidden, st));               // dz = (g W2) * gelu'(z)
+  RUN(wgrad(w.g, D, s.a, hidden, g->fc2_w, M, D, hidden, st));
+  RUN(mmae_colsum_bf16(w.big, hidden, g->fc1_b, M, hidden, st));
+  RUN(wgrad(w.big, hidden, s.h2, D, g->fc1_w, M, hidden, D, st));
+  RUN(dgrad_bf16(w.big, hidden, s.w1, nullptr, w.dh, M, hidden, D, st));
+  RUN(mmae_layernorm_backward(w.dh, 1, D, s.x_mid, D, s.mean2, s.rstd2, p->norm2_w, dx_out, D, w.dx_mid, D, g->norm2_w,
+                              g->norm2_b, M, D, st));
+  // ---- attention branch
+  RUN(mmae_cast_colsum_f32(w.dx_mid, D, w.g, D, g->proj_b, M, D, st));
+  RUN(wgrad(w.g, D, s.o, D, g->proj_w, M, D, D, st));
+  RUN(dgrad_bf16(w.g, D, s.wproj, nullptr, w.d_o, M, D, D, st));
+  bf16* dqkv = w.big;
+  RUN(mmae_attention_backward(s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o, D, w.d_o, D, s.lse, w.delta,
+                              dqkv, 3 * D, dqkv + D, 3 * D, dqkv + 2 * D, 3 * D, B, H, N, N, dh,
+                              1.0f / sqrtf((float)dh), st));
+  RUN(mmae_colsum_bf16(dqkv, 3 * D, g->qkv_b, M, 3 * D, st));
+  RUN(wgrad(dqkv, 3 * D, s.h1, D, g->qkv_w, M, 3 * D, D, st));
+  RUN(dgrad_bf16(dqkv, 3 * D, s.wqkv, nullptr, w.dh, M, 3 * D, D, st));
+  RUN(mmae_layernorm_backward(w.dh, 1, D, x_in, D, s.mean1, s.rstd1, p->norm1_w, w.dx_mid, D, dx_in, D, g->norm1_w,
+                              g->norm1_b, M, D, st));
+  return MMAE_OK;
+}
+
+// ================================================================================================ decoder head
+extern "C" int64_t mmae_dechead_saved_bytes(const mmae_decoder_index* ix, int D_enc, int H, int hidden) {
+  return (int64_t)head_saved(nullptr, *ix, D_enc, H, hidden).bytes;
+}
+extern "C" int64_t mmae_dechead_workspace_bytes(const mmae_decoder_index* ix, int D_enc, int H, int hidden) {
+  return (int64_t)head_ws(nullptr, *ix, D_enc, H, hidden).bytes;
+}
+
+extern "C" int mmae_dechead_forward(const float* enc, int De, const mmae_decoder_index* ixp, int H, int hidden, float eps,
+                                    const mmae_dechead_params* p, float* x_out, void* saved, void* ws, void* st) {
+  MMAE_CHECK(enc && ixp && p && x_out && saved && ws, MMAE_ERR_ARG, "mmae_dechead_forward: bad args");
+  const mmae_decoder_index& ix = *ixp;
+  const int Dd = ix.dim, B = ix.batch, P = ix.num_queries, Nc = ix.num_visible + ix.num_global;
+  MMAE_CHECK(Dd % H == 0 && ix.num_tasks <= MMAE_MAX_TASKS && ix.own_task >= 0 && ix.own_task < ix.num_tasks,
+             MMAE_ERR_ARG, "mmae_dechead_forward: bad decoder index");
+  const int Mq = B * P, Mc = B * Nc, dh = Dd / H;
+  HeadSaved s = head_saved(saved, ix, De, H, hidden);
+  HeadWs w = head_ws(ws, ix, De, H, hidden);
+  cudaStream_t cst = reinterpret_cast<cudaStream_t>(st);
+  RUN(mmae_cast_f32_to_bf16(enc, s.enc_b, int64_t(Mc) * De, st));
+  RUN(mmae_cast_f32_to_bf16(p->proj_context_w, s.wpc, int64_t(Dd) * De, st));
+  RUN(mmae_cast_f32_to_bf16(p->q_w, s.wq, int64_t(Dd) * Dd, st));
+  RUN(mmae_cast_f32_to_bf16(p->kv_w, s.wkv, int64_t(2) * Dd * Dd, st));
+  RUN(mmae_cast_f32_to_bf16(p->proj_w, s.wproj, int64_t(Dd) * Dd, st));
+  RUN(mmae_cast_f32_to_bf16(p->fc1_w, s.w1, int64_t(hidden) * Dd, st));
+  RUN(mmae_cast_f32_to_bf16(p->fc2_w, s.w2, int64_t(Dd) * hidden, st));
+  // proj_context                                                   output_adapters.py:258
+  RUN(linear_f32(s.enc_b, s.wpc, p->proj_context_b, nullptr, w.ctx, Mc, Dd, De, st));
+  // queries / context                                              output_adapters.py:183-234
+  TaskEmbPtrs te;
+  for (int t = 0; t < MMAE_MAX_TASKS; ++t) te.p[t] = p->task_emb[t];
+  RUN(launch_dec_build(w.ctx, ix, p->mask_token, te, p->pos, s.queries, s.context, cst));
+  // decoder(query_norm(q), context_norm(c))                        output_adapters.py:265
+  RUN(mmae_layernorm_forward(s.queries, Dd, p->query_norm_w, p->query_norm_b, s.qn, Dd, nullptr, 0, s.qmean, s.qrstd, Mq,
+                             Dd, eps, st));
+  RUN(mmae_layernorm_forward(s.context, Dd, p->context_norm_w, p->context_norm_b, s.cn, Dd, nullptr, 0, s.cmean, s.crstd,
+                             Mc, Dd, eps, st));
+  RUN(linear_bf16(s.qn, s.wq, p->q_b, s.q, Mq, Dd, Dd, st));
+  RUN(linear_bf16(s.cn, s.wkv, p->kv_b, s.kv, Mc, 2 * Dd, Dd, st));
+  RUN(mmae_attention_forward(s.q, Dd, s.kv, 2 * Dd, s.kv + Dd, 2 * Dd, s.o, Dd, s.lse, B, H, P, Nc, dh,
+                             1.0f / sqrtf((float)dh), st));
+  RUN(linear_f32(s.o, s.wproj, p->proj_b, nullptr, s.x0, Mq, Dd, Dd, st));
+  // x = x + mlp(out_norm(x))                                       output_adapters.py:266
+  RUN(mmae_layernorm_forward(s.x0, Dd, p->out_norm_w, p->out_norm_b, s.h, Dd, nullptr, 0, s.omean, s.orstd, Mq, Dd, eps,
+                             st));
+  RUN(linear_gelu(s.h, s.w1, p->fc1_b, s.z, s.a, Mq, hidden, Dd, st));
+  RUN(linear_f32(s.a, s.w2, p->fc2_b, s.x0, x_out, Mq, Dd, hidden, st));
+  return MMAE_OK;
+}
+
+extern "C" int mmae_dechead_backward(const float* enc, int De, const mmae_decoder_index* ixp, int H, int hidden,
+                                     const mmae_dechead_params* p, const mmae_dechead_grads* g, const float* dx_out,
+                                     float* denc, const void* saved, void* ws, void* st) {
+  (void)enc;
+  MMAE_CHECK(ixp && p && g && dx_out && denc && saved && ws, MMAE_ERR_ARG, "mmae_dechead_backward: bad args");
+  const mmae_decoder_index& ix = *ixp;
+  const int Dd = ix.dim, B = ix.batch, P = ix.num_queries, Nc = ix.num_visible + ix.num_global;
+  const int Mq = B * P, Mc = B * Nc, dh = Dd / H;
+  HeadSaved s = head_saved(const_cast<void*>(saved), ix, De, H, hidden);
+  HeadWs w = head_ws(ws, ix, De, H, hidden);
+  cudaStream_t cst = reinterpret_cast<cudaStream_t>(st);
+  // ---- MLP
+  RUN(mmae_cast_colsum_f32(dx_out, Dd, w.g, Dd, g->fc2_b, Mq, Dd, st));
+  RUN(dgrad_bf16(w.g, Dd, s.w2, s.z, w.dz, Mq, Dd, hidden, st));
+  RUN(wgrad(w.g, Dd, s.a, hidden, g->fc2_w, Mq, Dd, hidden, st));
+  RUN(mmae_colsum_bf16(w.dz, hidden, g->fc1_b, Mq, hidden, st));
+  RUN(wgrad(w.dz, hidden, s.h, Dd, g->fc1_w, Mq, hidden, Dd, st));
+  RUN(dgrad_bf16(w.dz, hidden, s.w1, nullptr, w.dh, Mq, hidden, Dd, st));
+  RUN(mmae_layernorm_backward(w.dh, 1, Dd, s.x0, Dd, s.omean, s.orstd, p->out_norm_w, dx_out, Dd, w.dx0, Dd,
+                              g->out_norm_w, g->out_norm_b, Mq, Dd, st));
+  // ---- cross attention (no residual around it)
+  RUN(mmae_cast_colsum_f32(w.dx0, Dd, w.g, Dd, g->proj_b, Mq, Dd, st));
+  RUN(wgrad(w.g, Dd, s.o, Dd, g->proj_w, Mq, Dd, Dd, st));
+  RUN(dgrad_bf16(w.g, Dd, s.wproj, nullptr, w.d_o, Mq, Dd, Dd, st));
+  RUN(mmae_attention_backward(s.q, Dd, s.kv, 2 * Dd, s.kv + Dd, 2 * Dd, s.o, Dd, w.d_o, Dd, s.lse, w.delta, w.dq, Dd,
+                              w.dkv, 2 * Dd, w.dkv + Dd, 2 * Dd, B, H, P, Nc, dh, 1.0f / sqrtf((float)dh), st));
+  RUN(mmae_colsum_bf16(w.dq, Dd, g->q_b, Mq, Dd, st));
+  RUN(wgrad(w.dq, Dd, s.qn, Dd, g->q_w, Mq, Dd, Dd, st));
+  RUN(dgrad_bf16(w.dq, Dd, s.wq, nullptr, w.dqn, Mq, Dd, Dd, st));
+  RUN(mmae_colsum_bf16(w.dkv, 2 * Dd, g->kv_b, Mc, 2 * Dd, st));
+  RUN(wgrad(w.dkv, 2 * Dd, s.cn, Dd, g->kv_w, Mc, 2 * Dd, Dd, st));
+  RUN(dgrad_bf16(w.dkv, 2 * Dd, s.wkv, nullptr, w.dcn, Mc, 2 * Dd, Dd, st));
+  RUN(mmae_layernorm_backward(w.dqn, 1, Dd, s.queries, Dd, s.qmean, s.qrstd, p->query_norm_w, nullptr, 0, w.dqueries, Dd,
+                              g->query_norm_w, g->query_norm_b, Mq, Dd, st));
+  RUN(mmae_layernorm_backward(w.dcn, 1, Dd, s.context, Dd, s.cmean, s.crstd, p->context_norm_w, nullptr, 0, w.dcontext,
+                              Dd, g->context_norm_w, g->context_norm_b, Mc, Dd, st));
+  // ---- queries / context construction
+  TaskEmbGradPtrs dte;
+  for (int t = 0; t < MMAE_MAX_TASKS; ++t) dte.p[t] = g->task_emb[t];
+  RUN(launch_dec_build_bwd(w.dqueries, w.dcontext, ix, w.dctx, g->mask_token, dte, cst));
+  // ---- proj_context
+  RUN(mmae_cast_colsum_f32(w.dctx, Dd, w.dctx_b, Dd, g->proj_context_b, Mc, Dd, st));
+  RUN(wgrad(w.dctx_b, Dd, s.enc_b, De, g->proj_context_w, Mc, Dd, De, st));
+  {
+    mmae_gemm_epilogue ep = ep_zero();
+    ep.accumulate = 1;
+    ep.out_f32 = denc;
+    ep.ld_out_f32 = De;
+    RUN(mmae_gemm_bf16(w.dctx_b, Dd, 0, s.wpc, De, 1, Mc, De, Dd, 1, &ep, st));
+  }
+  return MMAE_OK;
+}
+
+// ================================================================================================ decoder tail
+namespace {
+struct TailSaved {
+  bf16 *x_b, *w_b;
+  size_t bytes;
+};
+TailSaved tail_saved(void* base, int B, int nh, int nw, int Dd, int C, int P) {
+  Carver c(base);
+  TailSaved s;
+  s.x_b = c.take<bf16>(size_t(B) * nh * nw * Dd);
+  s.w_b = c.take<bf16>(size_t(C) * P * P * Dd);
+  s.bytes = align_up(c.off, 256);
+  return s;
+}
+struct TailWs {
+  float* y;
+  bf16* dy;
+  size_t bytes;
+};
+TailWs tail_ws(void* base, int B, int nh, int nw, int Dd, int C, int P) {
+  (void)Dd;
+  Carver c(base);
+  TailWs w;
+  w.y = c.take<float>(size_t(B) * nh * nw * C * P * P);
+  w.dy = c.take<bf16>(size_t(B) * nh * nw * C * P * P);
+  w.bytes = align_up(c.off, 256);
+  return w;
+}
+}  // namespace
+
+extern "C" int64_t mmae_dectail_saved_bytes(int B, int nh, int nw, int Dd, int C, int P) {
+  return (int64_t)tail_saved(nullptr, B, nh, nw, Dd, C, P).bytes;
+}
+extern "C" int64_t mmae_dectail_workspace_bytes(int B, int nh, int nw, int Dd, int C, int P) {
+  return (int64_t)tail_ws(nullptr, B, nh, nw, Dd, C, P).bytes;
+}
+
+extern "C" int mmae_dectail_forward(const float* x, int B, int nh, int nw, int Dd, int C, int P, const float* out_w,
+                                    const float* out_b, float* pred, void* saved, void* ws, void* st) {
+  MMAE_CHECK(x && out_w && out_b && pred && saved && ws, MMAE_ERR_ARG, "mmae_dectail_forward: bad args");
+  const int M = B * nh * nw, Nout = C * P * P;
+  TailSaved s = tail_saved(saved, B, nh, nw, Dd, C, P);
+  TailWs w = tail_ws(ws, B, nh, nw, Dd, C, P);
+  RUN(mmae_cast_f32_to_bf16(x, s.x_b, int64_t(M) * Dd, st));
+  RUN(mmae_cast_f32_to_bf16(out_w, s.w_b, int64_t(Nout) * Dd, st));
+  RUN(linear_f32(s.x_b, s.w_b, out_b, nullptr, w.y, M, Nout, Dd, st));       // output_adapters.py:274
+  RUN(mmae_unpatchify(w.y, Nout, pred, B, C, nh, nw, P, st));               // output_adapters.py:277-280
+  return MMAE_OK;
+}
+
+extern "C" int mmae_dectail_backward(const float* dpred, int B, int nh, int nw, int Dd, int C, int P, const float* out_w,
+                                     float* d_out_w, float* d_out_b, float* dx, const void* saved, void* ws, void* st) {
+  (void)out_w;
+  MMAE_CHECK(dpred && d_out_w && d_out_b && dx && saved && ws, MMAE_ERR_ARG, "mmae_dectail_backward: bad args");
+  const int M = B * nh * nw, Nout = C * P * P;
+  TailSaved s = tail_saved(const_cast<void*>(saved), B, nh, nw, Dd, C, P);
+  TailWs w = tail_ws(ws, B, nh, nw, Dd, C, P);
+  RUN(mmae_patchify_bf16(dpred, w.dy, Nout, B, C, nh, nw, P, st));
+  RUN(mmae_colsum_bf16(w.dy, Nout, d_out_b, M, Nout, st));
+  RUN(wgrad(w.dy, Nout, s.x_b, Dd, d_out_w, M, Nout, Dd, st));
+  {
+    mmae_gemm_epilogue ep = ep_zero();
+    ep.out_f32 = dx;
+    ep.ld_out_f32 = Dd;
+    RUN(mmae_gemm_bf16(w.dy, Nout, 0, s.w_b, Dd, 1, M, Dd, Nout, 1, &ep, st));
+  }
+  return MMAE_OK;
+}
+
+// ====================================================================================================== embed
+extern "C" int64_t mmae_embed_saved_bytes(const mmae_embed_layout* L, int B, int T, int D) {
+  (void)D;
+  return (int64_t)embed_saved(nullptr, *L, B, T).bytes;
+}
+extern "C" int64_t mmae_embed_workspace_bytes(const mmae_embed_layout* L, int B, int T, int D) {
+  return (int64_t)embed_ws(nullptr, *L, B, T, D).bytes;
+}
+
+extern "C" int mmae_embed_forward(const mmae_embed_layout* Lp, const mmae_embed_inputs* in, const mmae_embed_params* prm,
+                                  const int64_t* ids_keep, int B, int T, int G, int D, float* x_out, void* saved, void* ws,
+                                  void* st) {
+  MMAE_CHECK(Lp && in && prm && ids_keep && x_out && saved && ws && B > 0 && T > 0 && G >= 0 && D % 8 == 0, MMAE_ERR_ARG,
+             "mmae_embed_forward: bad args");
+  const mmae_embed_layout& L = *Lp;
+  MMAE_CHECK(L.num_tasks >= 1 && L.num_tasks <= MMAE_MAX_TASKS, MMAE_ERR_ARG, "mmae_embed_forward: bad task count");
+  const int Kcat = L.k_offset[L.num_tasks];
+  MMAE_CHECK(Kcat % 8 == 0, MMAE_ERR_UNSUPPORTED, "mmae_embed_forward: K segments must be multiples of 8");
+  EmbedSaved s = embed_saved(saved, L, B, T);
+  EmbedWs w = embed_ws(ws, L, B, T, D);
+  cudaStream_t cst = reinterpret_cast<cudaStream_t>(st);
+  for (int t = 0; t < L.num_tasks; ++t) {
+    const int Kt = L.k_offset[t + 1] - L.k_offset[t];
+    MMAE_CHECK(Kt % 8 == 0 && L.k_offset[t] % 8 == 0, MMAE_ERR_UNSUPPORTED, "mmae_embed_forward: K_t %% 8 != 0");
+    RUN(launch_cast2d(prm->weight[t], Kt, w.Wcat + L.k_offset[t], Kcat, D, Kt, cst));
+  }
+  RUN(launch_embed_gather(L, *in, ids_keep, B, T, s.A, s.row_task, s.row_patch, cst));
+  {
+    mmae_gemm_epilogue ep = ep_zero();
+    ep.out_f32 = w.Cmat;
+    ep.ld_out_f32 = D;
+    RUN(mmae_gemm_bf16(s.A, Kcat, 0, w.Wcat, Kcat, 0, B * T, D, Kcat, 1, &ep, st));
+  }
+  RUN(launch_embed_assemble(w.Cmat, *prm, s.row_task, s.row_patch, B, T, G, D, x_out, cst));
+  return MMAE_OK;
+}
+
+extern "C" int mmae_embed_backward(const mmae_embed_layout* Lp, const mmae_embed_inputs* in, const mmae_embed_params* prm,
+                                   const mmae_embed_grads* g, const int64_t* ids_keep, int B, int T, int G, int D,
+                                   const float* dx, const void* saved, void* ws, void* st) {
+  MMAE_CHECK(Lp && in && prm && g && ids_keep && dx && saved && ws, MMAE_ERR_ARG, "mmae_embed_backward: bad args");
+  const mmae_embed_layout& L = *Lp;
+  const int Kcat = L.k_offset[L.num_tasks];
+  EmbedSaved s = embed_saved(const_cast<void*>(saved), L, B, T);
+  EmbedWs w = embed_ws(ws, L, B, T, D);
+  cudaStream_t cst = reinterpret_cast<cudaStream_t>(st);
+  RUN(launch_embed_assemble_bwd(dx, B, T, G, D, s.row_task, w.dC, *g, L.num_tasks, cst));
+  for (int t = 0; t < L.num_tasks; ++t) {
+    const int Kt = L.k_offset[t + 1] - L.k_offset[t];
+    // dW_t[D, K_t] += dC^T A_cat[:, segment t]      (rows of other tasks are zero in this segment)
+    RUN(wgrad(w.dC, D, s.A + L.k_offset[t], Kcat, g->weight[t], B * T, D, Kt, st));
+    if (L.is_semseg[t] && g->class_emb[t] != nullptr) {
+      // dA = dC W_t  ->  scatter-add into the class-embedding table      input_adapters.py:229
+      bf16* Wt = w.Wcat;  // reuse: [D, K_t] contiguous
+      RUN(mmae_cast_f32_to_bf16(prm->weight[t], Wt, int64_t(D) * Kt, st));
+      RUN(dgrad_bf16(w.dC, D, Wt, nullptr, w.dA, B * T, D, Kt, st));
+      RUN(launch_semseg_emb_bwd(w.dA, Kt, reinterpret_cast<const int64_t*>(in->data[t]), ids_keep, s.row_task,
+                                s.row_patch, t, T, B * T, L.grid_w[t], L.grid_h[t], L.patch[t], L.channels[t],
+                                L.num_classes[t], g->class_emb[t], cst));
+    }
+  }
+  return MMAE_OK;
+}

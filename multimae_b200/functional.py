@@ -1,0 +1,426 @@
+"""torch.autograd.Function wrappers over the module-level C ABI (include/multimae_b200.h).
+
+PyTorch supplies device memory, streams and the autograd tape; every FLOP runs in libmultimae_b200.so.  There is no
+CPU/eager fallback: CPU tensors raise.
+
+Gradient storage: parameters' gradients are accumulated by the kernels directly into a flat fp32 `GradArena` owned by
+the model (zeroed once per forward), and the per-parameter views are what backward returns — or, in "owned" mode
+(data-parallel trainer), what `p.grad` permanently aliases so the arena can be all-reduced in place.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib as L
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise L.MmaeError("multimae_b200.%s needs CUDA tensors: the path is sm_100a kernels only (no CPU fallback)" % what)
+
+
+class Workspace:
+    """One growable scratch buffer per device, reused by every Function (all launches are stream-ordered)."""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, nbytes, device):
+        key = (device.type, device.index)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+class GradArena:
+    """Flat fp32 gradient storage for a list of (name, parameter); views are 16-byte aligned."""
+
+    def __init__(self, named_params, device):
+        self.offsets = {}
+        off = 0
+        for name, p in named_params:
+            self.offsets[name] = (off, p.numel(), tuple(p.shape))
+            off += (p.numel() + 3) // 4 * 4
+        self.numel = off
+        self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=device)
+        self.views = {name: self.flat[o:o + n].view(shape) for name, (o, n, shape) in self.offsets.items()}
+        self.owned = False     # True: p.grad aliases the views and backward returns None for parameters
+
+    def zero_(self):
+        self.flat.zero_()
+
+    def view(self, name):
+        return self.views[name]
+
+
+def _grad_ptr(arena, name):
+    return arena.views[name].data_ptr()
+
+
+def _ret_grads(arena, names, params):
+    """What backward returns for parameter inputs."""
+    out = []
+    for n, p in zip(names, params):
+        if p is None or not p.requires_grad:
+            out.append(None)
+            continue
+        v = arena.views[n]
+        if arena.owned or (p.grad is not None and p.grad.data_ptr() == v.data_ptr()):
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
+            out.append(None)
+        else:
+            out.append(v)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# transformer block
+# ---------------------------------------------------------------------------------------------------------------------
+BLOCK_PARAM_NAMES = ["norm1.weight", "norm1.bias", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight",
+                     "attn.proj.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight",
+                     "mlp.fc2.bias"]
+
+
+class BlockFunction(torch.autograd.Function):
+    """Block.forward (multimae/multimae_utils.py:229-232) as one fused sequence of kernels."""
+
+    @staticmethod
+    def forward(ctx, x, meta, *params):
+        _require_cuda(x, "Block")
+        B, N, D = x.shape
+        H, hidden, eps = meta["heads"], meta["hidden"], meta["eps"]
+        x = x.contiguous().float()
+        lib = L.lib()
+        saved = torch.empty(lib.mmae_block_saved_bytes(B, N, D, H, hidden), dtype=torch.uint8, device=x.device)
+        out = torch.empty_like(x)
+        prm = L.BlockParams(*[p.data_ptr() for p in params])
+        L.check(lib.mmae_block_forward(x.data_ptr(), out.data_ptr(), B, N, D, H, hidden, eps, ctypes.byref(prm),
+                                       saved.data_ptr(), None, L.current_stream()), "mmae_block_forward")
+        ctx.meta = meta
+        ctx.params = params
+        ctx.save_for_backward(x, saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, saved = ctx.saved_tensors
+        meta, params = ctx.meta, ctx.params
+        B, N, D = x.shape
+        H, hidden = meta["heads"], meta["hidden"]
+        arena, prefix = meta["arena"], meta["prefix"]
+        names = [prefix + n for n in BLOCK_PARAM_NAMES]
+        lib = L.lib()
+        ws = Workspace.get(lib.mmae_block_workspace_bytes(B, N, D, H, hidden), x.device)
+        dout = dout.contiguous().float()
+        dx = torch.empty_like(x)
+        prm = L.BlockParams(*[p.data_ptr() for p in params])
+        grd = L.BlockGrads(*[_grad_ptr(arena, n) for n in names])
+        L.check(lib.mmae_block_backward(x.data_ptr(), dout.data_ptr(), dx.data_ptr(), B, N, D, H, hidden,
+                                        ctypes.byref(prm), ctypes.byref(grd), saved.data_ptr(), ws.data_ptr(),
+                                        L.current_stream()), "mmae_block_backward")
+        if meta.get("on_grads_ready") is not None:
+            meta["on_grads_ready"](names)
+        return (dx, None) + tuple(_ret_grads(arena, names, params))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# gather-first patch embedding
+# ---------------------------------------------------------------------------------------------------------------------
+class EmbedFunction(torch.autograd.Function):
+    """input adapters + token selection + global-token append (multimae/multimae.py:312-347) as one GEMM + 2 kernels.
+
+    args: meta (dict), ids_keep, then per task [data, weight, bias, class_emb-or-None], then global_tokens."""
+
+    @staticmethod
+    def forward(ctx, meta, ids_keep, *tensors):
+        lib = L.lib()
+        layout = meta["layout"]
+        T_tasks = layout.num_tasks
+        per_task = [tensors[4 * t:4 * t + 4] for t in range(T_tasks)]
+        global_tokens = tensors[4 * T_tasks]
+        B, T = ids_keep.shape
+        G, D = global_tokens.shape[-2], global_tokens.shape[-1]
+        _require_cuda(ids_keep, "embed")
+        ins, prm = L.EmbedInputs(), L.EmbedParams()
+        keep_alive = []
+        for t, (data, w, b, cemb) in enumerate(per_task):
+            _require_cuda(data, "embed")
+            data = data.contiguous()
+            if layout.is_semseg[t]:
+                assert data.dtype == torch.int64
+            else:
+                data = data.float()
+            keep_alive.append(data)
+            ins.data[t] = data.data_ptr()
+            ins.class_emb[t] = cemb.data_ptr() if cemb is not None else None
+            prm.weight[t] = w.data_ptr()
+            prm.bias[t] = b.data_ptr()
+            prm.pos[t] = meta["pos"][t].data_ptr()
+        prm.global_tokens = global_tokens.data_ptr()
+        dev = ids_keep.device
+        saved = torch.empty(lib.mmae_embed_saved_bytes(ctypes.byref(layout), B, T, D), dtype=torch.uint8, device=dev)
+        ws = Workspace.get(lib.mmae_embed_workspace_bytes(ctypes.byref(layout), B, T, D), dev)
+        out = torch.empty((B, T + G, D), dtype=torch.float32, device=dev)
+        ids_keep = ids_keep.contiguous()
+        L.check(lib.mmae_embed_forward(ctypes.byref(layout), ctypes.byref(ins), ctypes.byref(prm), ids_keep.data_ptr(), B,
+                                       T, G, D, out.data_ptr(), saved.data_ptr(), ws.data_ptr(), L.current_stream()),
+                "mmae_embed_forward")
+        ctx.meta = meta
+        ctx.tensors = tensors
+        ctx.keep_alive = keep_alive
+        ctx.dims = (B, T, G, D)
+        ctx.save_for_backward(ids_keep, saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, dx):
+        lib = L.lib()
+        ids_keep, saved = ctx.saved_tensors
+        meta, tensors = ctx.meta, ctx.tensors
+        layout, arena, names = meta["layout"], meta["arena"], meta["names"]
+        T_tasks = layout.num_tasks
+        B, T, G, D = ctx.dims
+        ins, prm, grd = L.EmbedInputs(), L.EmbedParams(), L.EmbedGrads()
+        flat_names, flat_params = [], []
+        for t in range(T_tasks):
+            data, w, b, cemb = tensors[4 * t:4 * t + 4]
+            ins.data[t] = ctx.keep_alive[t].data_ptr()
+            ins.class_emb[t] = cemb.data_ptr() if cemb is not None else None
+            prm.weight[t] = w.data_ptr()
+            prm.bias[t] = b.data_ptr()
+            prm.pos[t] = meta["pos"][t].data_ptr()
+            wn, bn, cn = names[t]
+            grd.weight[t] = _grad_ptr(arena, wn)
+            grd.bias[t] = _grad_ptr(arena, bn)
+            grd.class_emb[t] = _grad_ptr(arena, cn) if cn is not None else None
+            flat_names += [None, wn, bn, cn]
+            flat_params += [None, w, b, cemb]
+        gt = tensors[4 * T_tasks]
+        prm.global_tokens = gt.data_ptr()
+        grd.global_tokens = _grad_ptr(arena, "global_tokens")
+        flat_names.append("global_tokens")
+        flat_params.append(gt)
+        ws = Workspace.get(lib.mmae_embed_workspace_bytes(ctypes.byref(layout), B, T, D), dx.device)
+        dx = dx.contiguous().float()
+        L.check(lib.mmae_embed_backward(ctypes.byref(layout), ctypes.byref(ins), ctypes.byref(prm), ctypes.byref(grd),
+                                        ids_keep.data_ptr(), B, T, G, D, dx.data_ptr(), saved.data_ptr(), ws.data_ptr(),
+                                        L.current_stream()), "mmae_embed_backward")
+        real = [(n, p) for n, p in zip(flat_names, flat_params) if n is not None]
+        if meta.get("on_grads_ready") is not None:
+            meta["on_grads_ready"]([n for n, _ in real])
+        rets = iter(_ret_grads(arena, [n for n, _ in real], [p for _, p in real]))
+        out = [None if n is None else next(rets) for n in flat_names]
+        return (None, None) + tuple(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# decoder head / tail
+# ---------------------------------------------------------------------------------------------------------------------
+HEAD_PARAM_NAMES = ["proj_context.weight", "proj_context.bias", "mask_token", "context_norm.weight", "context_norm.bias",
+                    "query_norm.weight", "query_norm.bias", "out_norm.weight", "out_norm.bias", "decoder.q.weight",
+                    "decoder.q.bias", "decoder.kv.weight", "decoder.kv.bias", "decoder.proj.weight",
+                    "decoder.proj.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"]
+
+
+def _fill_head_struct(st, vals, task_vals):
+    """vals follow HEAD_PARAM_NAMES order; task_vals is the per-context-task pointer list."""
+    (st.proj_context_w, st.proj_context_b, st.mask_token, st.context_norm_w, st.context_norm_b, st.query_norm_w,
+     st.query_norm_b, st.out_norm_w, st.out_norm_b, st.q_w, st.q_b, st.kv_w, st.kv_b, st.proj_w, st.proj_b, st.fc1_w,
+     st.fc1_b, st.fc2_w, st.fc2_b) = vals
+    for t, v in enumerate(task_vals):
+        st.task_emb[t] = v
+
+
+class DecoderHeadFunction(torch.autograd.Function):
+    """proj_context .. x + mlp(out_norm(x)) of SpatialOutputAdapter.forward (multimae/output_adapters.py:258-266).
+
+    args: enc, meta, ids_keep, ids_restore, then the 19 HEAD_PARAM_NAMES tensors, then one task embedding (or None)
+    per context task."""
+
+    @staticmethod
+    def forward(ctx, enc, meta, ids_keep, ids_restore, *params):
+        _require_cuda(enc, "SpatialOutputAdapter")
+        lib = L.lib()
+        enc = enc.contiguous().float()
+        B, Nc, De = enc.shape
+        ix = L.DecoderIndex()
+        ix.batch, ix.dim, ix.num_global = B, meta["dim"], meta["num_global"]
+        ix.num_visible = Nc - meta["num_global"]
+        ix.num_queries, ix.total_tokens = meta["num_queries"], meta["tok_offset"][-1]
+        ix.num_tasks, ix.own_task = len(meta["tok_offset"]) - 1, meta["own_task"]
+        for i, o in enumerate(meta["tok_offset"]):
+            ix.tok_offset[i] = o
+        ids_keep = ids_keep.contiguous()
+        ids_restore = ids_restore.contiguous()
+        ix.ids_keep, ix.ids_restore = ids_keep.data_ptr(), ids_restore.data_ptr()
+        H, hidden, eps = meta["heads"], meta["hidden"], meta["eps"]
+        main, task = params[:len(HEAD_PARAM_NAMES)], params[len(HEAD_PARAM_NAMES):]
+        prm = L.DecHeadParams()
+        _fill_head_struct(prm, [p.data_ptr() for p in main], [None if p is None else p.data_ptr() for p in task])
+        prm.pos = meta["pos"].data_ptr()
+        saved = torch.empty(lib.mmae_dechead_saved_bytes(ctypes.byref(ix), De, H, hidden), dtype=torch.uint8,
+                            device=enc.device)
+        ws = Workspace.get(lib.mmae_dechead_workspace_bytes(ctypes.byref(ix), De, H, hidden), enc.device)
+        out = torch.empty((B, ix.num_queries, ix.dim), dtype=torch.float32, device=enc.device)
+        L.check(lib.mmae_dechead_forward(enc.data_ptr(), De, ctypes.byref(ix), H, hidden, eps, ctypes.byref(prm),
+                                         out.data_ptr(), saved.data_ptr(), ws.data_ptr(), L.current_stream()),
+                "mmae_dechead_forward")
+        ctx.meta, ctx.params, ctx.ix = meta, params, ix
+        ctx.save_for_backward(enc, saved, ids_keep, ids_restore)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.lib()
+        enc, saved, ids_keep, ids_restore = ctx.saved_tensors
+        meta, params, ix = ctx.meta, ctx.params, ctx.ix
+        B, Nc, De = enc.shape
+        H, hidden = meta["heads"], meta["hidden"]
+        arena, prefix = meta["arena"], meta["prefix"]
+        main, task = params[:len(HEAD_PARAM_NAMES)], params[len(HEAD_PARAM_NAMES):]
+        names = [prefix + n for n in HEAD_PARAM_NAMES]
+        task_names = [None if p is None else prefix + "task_embeddings." + tn for p, tn in zip(task, meta["task_names"])]
+        prm, grd = L.DecHeadParams(), L.DecHeadGrads()
+        _fill_head_struct(prm, [p.data_ptr() for p in main], [None if p is None else p.data_ptr() for p in task])
+        prm.pos = meta["pos"].data_ptr()
+        _fill_head_struct(grd, [_grad_ptr(arena, n) for n in names],
+                          [None if n is None else _grad_ptr(arena, n) for n in task_names])
+        ws = Workspace.get(lib.mmae_dechead_workspace_bytes(ctypes.byref(ix), De, H, hidden), enc.device)
+        dout = dout.contiguous().float()
+        denc = torch.zeros_like(enc)
+        L.check(lib.mmae_dechead_backward(enc.data_ptr(), De, ctypes.byref(ix), H, hidden, ctypes.byref(prm),
+                                          ctypes.byref(grd), dout.data_ptr(), denc.data_ptr(), saved.data_ptr(),
+                                          ws.data_ptr(), L.current_stream()), "mmae_dechead_backward")
+        all_names = names + [n for n in task_names if n is not None]
+        if meta.get("on_grads_ready") is not None:
+            meta["on_grads_ready"](all_names)
+        g_main = _ret_grads(arena, names, main)
+        g_task = [None if n is None else _ret_grads(arena, [n], [p])[0] for n, p in zip(task_names, task)]
+        return (denc, None, None, None) + tuple(g_main) + tuple(g_task)
+
+
+class DecoderTailFunction(torch.autograd.Function):
+    """out_proj + un-patchify (multimae/output_adapters.py:274-280)."""
+
+    @staticmethod
+    def forward(ctx, x, meta, weight, bias):
+        _require_cuda(x, "SpatialOutputAdapter")
+        lib = L.lib()
+        x = x.contiguous().float()
+        B, _, Dd = x.shape
+        nh, nw, C, P = meta["nh"], meta["nw"], meta["channels"], meta["patch"]
+        saved = torch.empty(lib.mmae_dectail_saved_bytes(B, nh, nw, Dd, C, P), dtype=torch.uint8, device=x.device)
+        ws = Workspace.get(lib.mmae_dectail_workspace_bytes(B, nh, nw, Dd, C, P), x.device)
+        pred = torch.empty((B, C, nh * P, nw * P), dtype=torch.float32, device=x.device)
+        L.check(lib.mmae_dectail_forward(x.data_ptr(), B, nh, nw, Dd, C, P, weight.data_ptr(), bias.data_ptr(),
+                                         pred.data_ptr(), saved.data_ptr(), ws.data_ptr(), L.current_stream()),
+                "mmae_dectail_forward")
+        ctx.meta, ctx.dims, ctx.params = meta, (B, nh, nw, Dd, C, P), (weight, bias)
+        ctx.save_for_backward(saved)
+        return pred
+
+    @staticmethod
+    def backward(ctx, dpred):
+        lib = L.lib()
+        (saved,) = ctx.saved_tensors
+        meta = ctx.meta
+        B, nh, nw, Dd, C, P = ctx.dims
+        weight, bias = ctx.params
+        arena, prefix = meta["arena"], meta["prefix"]
+        names = [prefix + "out_proj.weight", prefix + "out_proj.bias"]
+        ws = Workspace.get(lib.mmae_dectail_workspace_bytes(B, nh, nw, Dd, C, P), dpred.device)
+        dpred = dpred.contiguous().float()
+        dx = torch.empty((B, nh * nw, Dd), dtype=torch.float32, device=dpred.device)
+        L.check(lib.mmae_dectail_backward(dpred.data_ptr(), B, nh, nw, Dd, C, P, weight.data_ptr(),
+                                          _grad_ptr(arena, names[0]), _grad_ptr(arena, names[1]), dx.data_ptr(),
+                                          saved.data_ptr(), ws.data_ptr(), L.current_stream()), "mmae_dectail_backward")
+        if meta.get("on_grads_ready") is not None:
+            meta["on_grads_ready"](names)
+        gw, gb = _ret_grads(arena, names, [weight, bias])
+        return dx, None, gw, gb
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# masked losses
+# ---------------------------------------------------------------------------------------------------------------------
+class MaskedLossFunction(torch.autograd.Function):
+    """multimae/criterion.py losses; kind 0 = MSE, 1 = L1, 2 = cross-entropy."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mask, kind, norm_pix, scale, label_smoothing):
+        _require_cuda(pred, "criterion")
+        lib = L.lib()
+        pred = pred.contiguous().float()
+        B, C, H, W = pred.shape
+        if kind == 2:
+            target = target.contiguous().long()
+        else:
+            target = target.contiguous().float()
+        if mask is not None:
+            mask = mask.contiguous().long()
+        ws = torch.empty(2 * B, dtype=torch.float32, device=pred.device)
+        loss = torch.empty((), dtype=torch.float32, device=pred.device)
+        L.check(lib.mmae_masked_loss_forward(kind, int(norm_pix), float(label_smoothing), pred.data_ptr(),
+                                             target.data_ptr(), L.ptr(mask), B, C, H, W, scale, ws.data_ptr(),
+                                             loss.data_ptr(), L.current_stream()), "mmae_masked_loss_forward")
+        ctx.cfg = (kind, int(norm_pix), scale, float(label_smoothing))
+        ctx.save_for_backward(pred, target, mask, ws)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        lib = L.lib()
+        pred, target, mask, ws = ctx.saved_tensors
+        kind, norm_pix, scale, smoothing = ctx.cfg
+        B, C, H, W = pred.shape
+        gout = gout.contiguous().float()
+        dpred = torch.empty_like(pred)
+        L.check(lib.mmae_masked_loss_backward(kind, norm_pix, smoothing, pred.data_ptr(), target.data_ptr(), L.ptr(mask),
+                                              B, C, H, W, scale, ws.data_ptr(), gout.data_ptr(), dpred.data_ptr(),
+                                              L.current_stream()), "mmae_masked_loss_backward")
+        return dpred, None, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mask sampler (no autograd)
+# ---------------------------------------------------------------------------------------------------------------------
+def sample_masks(shares, noise_task, noise_all, tokens_per_task, num_encoded):
+    """Pure function of the random draws -> (mask_all [B,total] int64, ids_keep, ids_restore); one kernel launch."""
+    _require_cuda(noise_all, "generate_random_masks")
+    B, total = noise_all.shape
+    dev = noise_all.device
+    shares = shares.to(device=dev, dtype=torch.float32).contiguous()
+    noise_task = noise_task.contiguous().float()
+    noise_all = noise_all.contiguous().float()
+    masks = torch.empty((B, total), dtype=torch.int64, device=dev)
+    ids_keep = torch.empty((B, num_encoded), dtype=torch.int64, device=dev)
+    ids_restore = torch.empty((B, total), dtype=torch.int64, device=dev)
+    arr = (ctypes.c_int * len(tokens_per_task))(*tokens_per_task)
+    L.check(L.lib().mmae_sample_masks(shares.data_ptr(), noise_task.data_ptr(), noise_all.data_ptr(), B,
+                                      len(tokens_per_task), arr, num_encoded, masks.data_ptr(), ids_keep.data_ptr(),
+                                      ids_restore.data_ptr(), L.current_stream()), "mmae_sample_masks")
+    return masks, ids_keep, ids_restore
+
+
+def grad_unscale_norm(flat, inv_scale=1.0, post_scale=1.0, inv_scale_tensor=None):
+    """In-place flat *= inv_scale*post_scale; returns (norm tensor [1], out2 = [sum_sq, found_inf])."""
+    _require_cuda(flat, "grad_unscale_norm")
+    out2 = torch.empty(2, dtype=torch.float32, device=flat.device)
+    norm = torch.empty((), dtype=torch.float32, device=flat.device)
+    L.check(L.lib().mmae_grad_unscale_norm(flat.data_ptr(), flat.numel(), L.ptr(inv_scale_tensor), float(inv_scale),
+                                           float(post_scale), out2.data_ptr(), norm.data_ptr(), L.current_stream()),
+            "mmae_grad_unscale_norm")
+    return norm, out2
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, found_inf=None):
+    L.check(L.lib().mmae_adamw_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                    params.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                    float(weight_decay), int(step), L.ptr(found_inf), L.current_stream()),
+            "mmae_adamw_step")
+
+
+_ = math

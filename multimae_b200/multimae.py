@@ -1,0 +1,365 @@
+"""MultiMAE / MultiViT with the reference's module API (multimae/multimae.py), executing on sm_100a kernels.
+
+Same constructor signature, parameter names / shapes (state_dict schema of SURVEY.md §A.1), factories registered under
+the same names, and the same `forward` contract — `(preds, task_masks)` — so run_pretraining_multimae.py can drive it
+unchanged.  What differs is the execution plan: gather-first patch embedding, one mask-sampler kernel,
+fused transformer blocks, fused decoder head/tail, gradients accumulated into one flat arena.
+"""
+import itertools
+import math
+import warnings
+from collections import OrderedDict
+from functools import partial
+from typing import Dict, List, Optional, Union
+
+import torch
+from torch import nn
+from torch.distributions.dirichlet import Dirichlet
+
+from . import _lib as L
+from . import functional as Fn
+from .multimae_utils import Block, trunc_normal_
+
+try:  # the reference's timm-style registry, when the reference tree is importable (drop-in overlay); else a local one
+    from utils.registry import register_model  # type: ignore
+except Exception:  # noqa: BLE001
+    _LOCAL_REGISTRY = {}
+
+    def register_model(fn):
+        _LOCAL_REGISTRY[fn.__name__] = fn
+        return fn
+
+__all__ = ["pretrain_multimae_base", "pretrain_multimae_large", "multivit_base", "multivit_large"]
+
+
+def _build_layout(adapters, x):
+    """EmbedLayout + per-task metadata for the ordered (name, adapter, tensor) triples."""
+    layout = L.EmbedLayout()
+    layout.num_tasks = len(adapters)
+    if layout.num_tasks > L.MAX_TASKS:
+        raise L.MmaeError("multimae_b200: at most %d input modalities" % L.MAX_TASKS)
+    tok, k = 0, 0
+    for t, (name, ad) in enumerate(adapters):
+        nh, nw = ad.grid(x[name])
+        assert ad.P_H == ad.P_W, "multimae_b200: square patches only"
+        layout.grid_h[t], layout.grid_w[t] = nh, nw
+        layout.tok_offset[t], layout.k_offset[t] = tok, k
+        layout.patch[t] = ad.P_H
+        layout.channels[t] = ad.embed_channels()
+        layout.is_semseg[t] = 1 if ad.is_semseg else 0
+        layout.num_classes[t] = ad.num_classes if ad.is_semseg else 0
+        tok += nh * nw
+        k += ad.embed_channels() * ad.P_H * ad.P_W
+    layout.tok_offset[layout.num_tasks] = tok
+    layout.k_offset[layout.num_tasks] = k
+    return layout
+
+
+def _embed(adapters, x, ids_keep, global_tokens, arena, prefix_of, on_grads_ready=None):
+    """Gather-first embedding of the tokens listed in ids_keep (+ global tokens appended last)."""
+    layout = _build_layout(adapters, x)
+    names, tensors, pos = [], [], []
+    for t, (name, ad) in enumerate(adapters):
+        pre = prefix_of(name)
+        cemb = ad.class_emb.weight if ad.is_semseg else None
+        names.append((pre + "proj.weight", pre + "proj.bias", pre + "class_emb.weight" if ad.is_semseg else None))
+        tensors += [x[name], ad.proj.weight, ad.proj.bias, cemb]
+        pos.append(ad._resized_pos(layout.grid_h[t], layout.grid_w[t], ad.pos_mode))
+    meta = dict(layout=layout, arena=arena, names=names, pos=pos, on_grads_ready=on_grads_ready)
+    return Fn.EmbedFunction.apply(meta, ids_keep, *tensors, global_tokens.reshape(-1, global_tokens.shape[-1]))
+
+
+def embed_all_patches(adapter, x):
+    """Stand-alone input-adapter forward: every patch of one modality -> [B, N, D] (reference adapter.forward)."""
+    if not x.is_cuda:
+        raise L.MmaeError("multimae_b200 input adapters need CUDA tensors (no CPU fallback)")
+    nh, nw = adapter.grid(x)
+    B = x.shape[0]
+    ids = torch.arange(nh * nw, device=x.device).unsqueeze(0).expand(B, -1).contiguous()
+    named = [(n, p) for n, p in adapter.named_parameters() if p.requires_grad]
+    dummy = torch.zeros(1, 0, adapter.dim_tokens, device=x.device, requires_grad=False)
+    arena = Fn.GradArena(named + [("global_tokens", dummy)], x.device)
+    return _embed([("x", adapter)], {"x": x}, ids, dummy, arena, lambda name: "")
+
+
+class MultiMAE(nn.Module):
+    """MultiMAE: Multi-task Multi-modal Masked Autoencoder (performs masking in its forward pass)."""
+
+    def __init__(self, input_adapters: Dict[str, nn.Module], output_adapters: Optional[Dict[str, nn.Module]],
+                 num_global_tokens: int = 1, dim_tokens: int = 768, depth: int = 12, num_heads: int = 12,
+                 mlp_ratio: float = 4.0, qkv_bias: bool = True, drop_rate: float = 0.0, attn_drop_rate: float = 0.0,
+                 drop_path_rate: float = 0.0, norm_layer: nn.Module = partial(nn.LayerNorm, eps=1e-6)):
+        super().__init__()
+        for adapter in input_adapters.values():
+            adapter.init(dim_tokens=dim_tokens)
+        self.input_adapters = nn.ModuleDict(input_adapters)
+        if output_adapters is not None:
+            for adapter in output_adapters.values():
+                adapter.init(dim_tokens_enc=dim_tokens)
+            self.output_adapters = nn.ModuleDict(output_adapters)
+        else:
+            self.output_adapters = None
+
+        self.num_global_tokens = num_global_tokens
+        self.global_tokens = nn.Parameter(torch.zeros(1, num_global_tokens, dim_tokens))
+        trunc_normal_(self.global_tokens, std=0.02)
+
+        dpr = [v.item() for v in torch.linspace(0, drop_path_rate, depth)]
+        self.encoder = nn.Sequential(*[
+            Block(dim=dim_tokens, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, drop=drop_rate,
+                  attn_drop=attn_drop_rate, drop_path=dpr[i], norm_layer=norm_layer) for i in range(depth)])
+
+        self._init_all_weights()
+        self._arena = None
+        self._grad_callback = None
+        self._warned_fp32 = False
+
+    # ------------------------------------------------------------------------------------------------------------
+    # initialisation, same scheme as multimae/multimae.py:100-125
+    # ------------------------------------------------------------------------------------------------------------
+    def _init_all_weights(self):
+        for name, m in self.named_modules():
+            if isinstance(m, nn.Linear):
+                fan_out, fan_in = m.weight.shape
+                if "qkv" in name:       # q, k, v initialised as three separate square-ish matrices
+                    fan_out //= 3
+                elif "kv" in name:
+                    fan_out //= 2
+                bound = math.sqrt(6.0 / float(fan_out + fan_in))
+                nn.init.uniform_(m.weight, -bound, bound)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+            elif isinstance(m, nn.Conv2d) and ".proj" in name:
+                w = m.weight.data
+                nn.init.xavier_uniform_(w.view([w.shape[0], -1]))   # like nn.Linear (MAE)
+
+    def get_num_layers(self):
+        return len(self.encoder)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        no_wd = {"global_tokens"}
+        for group, adapters in (("input_adapters", self.input_adapters), ("output_adapters", self.output_adapters or {})):
+            for task, adapter in adapters.items():
+                if hasattr(adapter, "no_weight_decay"):
+                    no_wd |= {f"{group}.{task}.{n}" for n in adapter.no_weight_decay()}
+        return no_wd
+
+    # ------------------------------------------------------------------------------------------------------------
+    # gradient arena (flat fp32 buffer the kernels accumulate into)
+    # ------------------------------------------------------------------------------------------------------------
+    def grad_arena(self, device=None):
+        device = device if device is not None else self.global_tokens.device
+        if self._arena is None or self._arena.flat.device != device:
+            named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+            self._arena = Fn.GradArena(named, device)
+            self._bind()
+        return self._arena
+
+    def set_grad_callback(self, fn):
+        """fn(names) is called from backward as soon as the gradients of `names` are complete in the arena."""
+        self._grad_callback = fn
+        if self._arena is not None:
+            self._bind()
+
+    def _bind(self):
+        for i, blk in enumerate(self.encoder):
+            blk.bind(self._arena, "encoder.%d." % i, self._grad_callback)
+        if self.output_adapters is not None:
+            for key, ad in self.output_adapters.items():
+                if hasattr(ad, "bind"):
+                    ad.bind(self._arena, "output_adapters.%s." % key, self._grad_callback)
+
+    def own_gradients(self, owned=True):
+        """`owned`: every p.grad permanently aliases its arena view (flat all-reduce / fused optimizer)."""
+        arena = self.grad_arena()
+        arena.owned = owned
+        if owned:
+            for n, p in self.named_parameters():
+                if p.requires_grad:
+                    p.grad = arena.views[n]
+        return arena
+
+    # ------------------------------------------------------------------------------------------------------------
+    # mask sampling (multimae/multimae.py:148-218)
+    # ------------------------------------------------------------------------------------------------------------
+    def sample_alphas(self, B: int, n_tasks: int, alphas: float = 1.0, eps: float = 1e-5):
+        choices = torch.Tensor([list(i) for i in itertools.product([0, 1], repeat=n_tasks)][1:])
+        pick = torch.randint(0, len(choices), (B,))
+        return torch.index_select(choices, 0, pick) * torch.tensor(alphas) + eps
+
+    def generate_random_masks(self, input_tokens: Dict[str, torch.Tensor], num_encoded_tokens: int,
+                              alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False):
+        """Dirichlet task shares on the host (as the reference), uniform noise with torch's device generator in the
+        reference's consumption order, then ONE kernel for everything else."""
+        first = list(input_tokens.values())[0]
+        B, device = first.shape[0], first.device
+        alphas = [alphas] * len(input_tokens) if isinstance(alphas, float) else alphas
+        if sample_tasks_uniformly:
+            shares = Dirichlet(self.sample_alphas(B, len(input_tokens), alphas=alphas)).sample()
+        else:
+            shares = Dirichlet(torch.Tensor(alphas)).sample((B,))
+        counts = [t.shape[1] for t in input_tokens.values()]
+        noise_task = torch.cat([torch.rand(B, n, device=device) for n in counts], dim=1)
+        noise_all = torch.rand(B, sum(counts), device=device)
+        mask_all, ids_keep, ids_restore = Fn.sample_masks(shares, noise_task, noise_all, counts, num_encoded_tokens)
+        task_masks = dict(zip(input_tokens.keys(), torch.split(mask_all, counts, dim=1)))
+        return task_masks, ids_keep, ids_restore
+
+    @staticmethod
+    def make_mask(N_H, N_W, xy_idxs, full_tasks=[], indicate_visible=True, flatten=True, device="cuda"):
+        """Masks for each task from lists of un-masked (x, y) coordinates (multimae/multimae.py:220-248)."""
+        masks = {}
+        for k, v in xy_idxs.items():
+            m = torch.ones(N_H, N_W, device=device)
+            idx = torch.as_tensor(v, dtype=torch.long)
+            if len(idx) > 0:
+                m[idx[:, 1], idx[:, 0]] = 0
+            if k in full_tasks:
+                m[:] = 0
+            masks[k] = m
+        if not indicate_visible:
+            masks = {k: 1 - v for k, v in masks.items()}
+        if flatten:
+            masks = {k: v.flatten().unsqueeze(0) for k, v in masks.items()}
+        return masks
+
+    def generate_input_info(self, input_task_tokens, image_size):
+        info = OrderedDict()
+        info["tasks"] = {}
+        i = 0
+        for domain, tensor in input_task_tokens.items():
+            n = tensor.shape[1]
+            info["tasks"][domain] = {"num_tokens": n, "has_2d_posemb": True, "start_idx": i, "end_idx": i + n}
+            i += n
+        info["image_size"] = image_size
+        info["num_task_tokens"] = i
+        info["num_global_tokens"] = self.num_global_tokens
+        return info
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _prepare(self, x):
+        x = {"rgb": x} if isinstance(x, torch.Tensor) else x
+        if "rgb" in x:
+            B, _, H, W = x["rgb"].shape
+        elif "semseg" in x:
+            B, H, W = x["semseg"].shape
+            H *= self.input_adapters["semseg"].stride_level
+            W *= self.input_adapters["semseg"].stride_level
+        else:
+            B, _, H, W = list(x.values())[0].shape
+        adapters = [(d, self.input_adapters[d]) for d in x if d in self.input_adapters]
+        if not adapters:
+            raise ValueError("no input modality matches the model's input adapters")
+        dev = x[adapters[0][0]].device
+        if dev.type != "cuda":
+            raise L.MmaeError("multimae_b200.MultiMAE.forward needs CUDA inputs: the path is sm_100a kernels only "
+                              "(no CPU fallback)")
+        # token placeholders: only B / N_t / device are read downstream (the tokens are never materialised)
+        placeholders = OrderedDict()
+        for name, ad in adapters:
+            nh, nw = ad.grid(x[name])
+            placeholders[name] = torch.empty((B, nh * nw, 0), device=dev)
+        return x, adapters, placeholders, B, H, W, dev
+
+    def forward(self, x: Union[Dict[str, torch.Tensor], torch.Tensor], mask_inputs: bool = True,
+                task_masks: Dict[str, torch.Tensor] = None, num_encoded_tokens: int = 128,
+                alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False,
+                fp32_output_adapters: List[str] = []):
+        x, adapters, placeholders, B, H, W, dev = self._prepare(x)
+        input_info = self.generate_input_info(input_task_tokens=placeholders, image_size=(H, W))
+        total = input_info["num_task_tokens"]
+        if not mask_inputs:
+            num_encoded_tokens = total
+        elif num_encoded_tokens is None:
+            num_encoded_tokens = self.num_encoded_tokens
+
+        if task_masks is None:
+            task_masks, ids_keep, ids_restore = self.generate_random_masks(
+                placeholders, num_encoded_tokens, alphas=alphas, sample_tasks_uniformly=sample_tasks_uniformly)
+        else:
+            # fixed masks: visible tokens first, original order kept (stable).  The reference derives ONE count from
+            # the whole batch (multimae/multimae.py:338, correct only for B=1); here every sample must expose the same
+            # number of visible tokens and that per-sample count is used.
+            mask_all = torch.cat([task_masks[t].to(dev) for t in placeholders], dim=1)
+            ids_shuffle = torch.argsort(mask_all, dim=1, stable=True)
+            ids_restore = torch.argsort(ids_shuffle, dim=1, stable=True)
+            n_vis = (mask_all == 0).sum(dim=1)
+            if not bool((n_vis == n_vis[0]).all()):
+                raise ValueError("multimae_b200: fixed task_masks must keep the same number of visible tokens per sample")
+            ids_keep = ids_shuffle[:, :int(n_vis[0])]
+
+        arena = self.grad_arena(dev)
+        if torch.is_grad_enabled() and self.training:
+            arena.zero_()
+        seq = _embed(adapters, x, ids_keep, self.global_tokens, arena, lambda d: "input_adapters.%s." % d,
+                     self._grad_callback)
+        encoder_tokens = self.encoder(seq)
+        if self.output_adapters is None:
+            return encoder_tokens, task_masks
+
+        if fp32_output_adapters and not self._warned_fp32:
+            warnings.warn("multimae_b200: fp32_output_adapters=%s run with bf16 tensor-core operands and fp32 accumulate "
+                          "(bf16 has fp32's exponent range, which removes the fp16 overflow the flag works around)"
+                          % list(fp32_output_adapters))
+            self._warned_fp32 = True
+        preds = {domain: self.output_adapters[domain](encoder_tokens=encoder_tokens, input_info=input_info,
+                                                      ids_keep=ids_keep, ids_restore=ids_restore)
+                 for domain in self.output_adapters}
+        return preds, task_masks
+
+
+@register_model
+def pretrain_multimae_base(input_adapters: Dict[str, nn.Module], output_adapters: Optional[Dict[str, nn.Module]], **kwargs):
+    return MultiMAE(input_adapters=input_adapters, output_adapters=output_adapters, dim_tokens=768, depth=12, num_heads=12,
+                    mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+@register_model
+def pretrain_multimae_large(input_adapters: Dict[str, nn.Module], output_adapters: Optional[Dict[str, nn.Module]], **kwargs):
+    return MultiMAE(input_adapters=input_adapters, output_adapters=output_adapters, dim_tokens=1024, depth=24,
+                    num_heads=16, mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+class MultiViT(MultiMAE):
+    """MultiMAE without masking (multimae/multimae.py:419-502): all tokens of all given modalities are encoded."""
+
+    def process_input(self, x):
+        x, adapters, placeholders, B, H, W, dev = self._prepare(x)
+        input_info = self.generate_input_info(input_task_tokens=placeholders, image_size=(H, W))
+        total = input_info["num_task_tokens"]
+        ids = torch.arange(total, device=dev).unsqueeze(0).expand(B, -1).contiguous()
+        arena = self.grad_arena(dev)
+        if torch.is_grad_enabled() and self.training:
+            arena.zero_()
+        seq = _embed(adapters, x, ids, self.global_tokens, arena, lambda d: "input_adapters.%s." % d, self._grad_callback)
+        return seq, input_info
+
+    def forward(self, x, return_all_layers=False, **kwargs):
+        tokens, input_info = self.process_input(x)
+        if not return_all_layers:
+            encoder_tokens = self.encoder(tokens)
+        else:
+            encoder_tokens = []
+            for block in self.encoder:
+                tokens = block(tokens)
+                encoder_tokens.append(tokens)
+        if self.output_adapters is None:
+            return encoder_tokens
+        return {domain: self.output_adapters[domain](encoder_tokens=encoder_tokens, input_info=input_info)
+                for domain in self.output_adapters}
+
+
+@register_model
+def multivit_base(input_adapters: Dict[str, nn.Module], output_adapters: Optional[Dict[str, nn.Module]], **kwargs):
+    return MultiViT(input_adapters=input_adapters, output_adapters=output_adapters, dim_tokens=768, depth=12, num_heads=12,
+                    mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+@register_model
+def multivit_large(input_adapters: Dict[str, nn.Module], output_adapters: Optional[Dict[str, nn.Module]], **kwargs):
+    return MultiViT(input_adapters=input_adapters, output_adapters=output_adapters, dim_tokens=1024, depth=24,
+                    num_heads=16, mlp_ratio=4, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)

@@ -1,0 +1,127 @@
+"""NativeScalerWithGradNormCount with the reference's call contract (utils/native_scaler.py:14-46):
+scaled backward -> unscale -> global grad-norm (-> clip / skip) -> optimizer step -> scale update.
+
+When the parameters are backed by a model GradArena (multimae_b200.MultiMAE), unscale + non-finite check + L2 norm are
+ONE pass over the flat gradient buffer (mmae_grad_unscale_norm) instead of ~344 per-tensor launches, and an optimizer
+that exposes `fused_step(found_inf=...)` (multimae_b200.optim.FlatAdamW) is skipped on the device without a host sync.
+The loss scale lives on the device; state_dict() has GradScaler's keys so checkpoints interoperate."""
+import torch
+
+from . import functional as Fn
+
+inf = float("inf")
+
+
+def get_grad_norm_(parameters, norm_type: float = 2.0) -> torch.Tensor:
+    """Generic per-tensor path (reference utils/native_scaler.py:49-62) for parameters that are not arena-backed."""
+    if isinstance(parameters, torch.Tensor):
+        parameters = [parameters]
+    parameters = [p for p in parameters if p.grad is not None]
+    norm_type = float(norm_type)
+    if len(parameters) == 0:
+        return torch.tensor(0.0)
+    device = parameters[0].grad.device
+    if norm_type == inf:
+        return max(p.grad.detach().abs().max().to(device) for p in parameters)
+    return torch.norm(torch.stack([torch.norm(p.grad.detach(), norm_type).to(device) for p in parameters]), norm_type)
+
+
+def _find_arena(optimizer, parameters):
+    arena = getattr(optimizer, "mmae_arena", None)
+    if arena is not None:
+        return arena
+    return None
+
+
+class NativeScalerWithGradNormCount:
+    state_dict_key = "amp_scaler"
+
+    def __init__(self, enabled=True, init_scale=2.0 ** 16, growth_factor=2.0, backoff_factor=0.5, growth_interval=2000):
+        self._enabled = enabled
+        self._init_scale = float(init_scale)
+        self._growth_factor, self._backoff_factor, self._growth_interval = growth_factor, backoff_factor, growth_interval
+        self._scale = None           # device tensors, created lazily on the loss's device
+        self._growth_tracker = None
+        self._arena = None
+
+    def attach_arena(self, arena):
+        """Tell the scaler which flat gradient buffer backs the parameters (MultiMAE.grad_arena())."""
+        self._arena = arena
+        return self
+
+    def _lazy_init(self, device):
+        if self._scale is None:
+            self._scale = torch.full((), self._init_scale if self._enabled else 1.0, dtype=torch.float32, device=device)
+            self._growth_tracker = torch.zeros((), dtype=torch.int32, device=device)
+
+    def __call__(self, loss, optimizer, clip_grad=None, skip_grad=None, parameters=None, create_graph=False,
+                 update_grad=True):
+        self._lazy_init(loss.device)
+        (loss * self._scale if self._enabled else loss).backward(create_graph=create_graph)
+        if not update_grad:
+            return None
+        arena = self._arena or _find_arena(optimizer, parameters)
+        if arena is not None:
+            inv = (1.0 / self._scale) if self._enabled else None
+            norm, out2 = Fn.grad_unscale_norm(arena.flat, inv_scale=1.0, inv_scale_tensor=inv)
+            found_inf = out2[1:2]
+            if not arena.owned and parameters is not None:
+                # autograd may have copied instead of aliasing the arena views: make p.grad the (unscaled) views
+                for (n, v), p in zip(arena.views.items(), [p for p in parameters if p.requires_grad]):
+                    if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                        p.grad = v
+        else:
+            params = [p for p in (parameters or []) if p.grad is not None]
+            inv = (1.0 / self._scale) if self._enabled else None
+            if inv is not None:
+                for p in params:
+                    p.grad.mul_(inv)
+            norm = get_grad_norm_(params)
+            found_inf = (~torch.isfinite(norm)).float().reshape(1)
+        if clip_grad is not None:
+            assert parameters is not None or arena is not None
+            coef = torch.clamp(clip_grad / (norm + 1e-6), max=1.0)
+            if arena is not None:
+                arena.flat.mul_(coef)
+            else:
+                for p in params:
+                    p.grad.mul_(coef)
+        elif skip_grad is not None:
+            if norm >= skip_grad:        # host sync, as in the reference (utils/native_scaler.py:30)
+                self._update(found_inf)
+                return norm
+        if hasattr(optimizer, "fused_step"):
+            optimizer.fused_step(found_inf=found_inf)
+        elif float(found_inf) == 0.0:    # host sync, as GradScaler.step does for stock optimizers
+            optimizer.step()
+        self._update(found_inf)
+        return norm
+
+    def _update(self, found_inf):
+        if not self._enabled:
+            return
+        bad = found_inf.reshape(()) > 0
+        grown = self._growth_tracker + 1
+        hit = grown >= self._growth_interval
+        self._scale = torch.where(bad, self._scale * self._backoff_factor,
+                                  torch.where(hit, self._scale * self._growth_factor, self._scale))
+        self._growth_tracker = torch.where(bad | hit, torch.zeros_like(grown), grown)
+
+    def state_dict(self):
+        if not self._enabled:
+            return {"scale": 1.0}
+        scale = float(self._scale) if self._scale is not None else self._init_scale
+        tracker = int(self._growth_tracker) if self._growth_tracker is not None else 0
+        return {"scale": scale, "growth_factor": self._growth_factor, "backoff_factor": self._backoff_factor,
+                "growth_interval": self._growth_interval, "_growth_tracker": tracker}
+
+    def load_state_dict(self, state_dict):
+        if not self._enabled or not state_dict:
+            return
+        self._init_scale = float(state_dict["scale"])
+        self._growth_factor = state_dict.get("growth_factor", self._growth_factor)
+        self._backoff_factor = state_dict.get("backoff_factor", self._backoff_factor)
+        self._growth_interval = state_dict.get("growth_interval", self._growth_interval)
+        if self._scale is not None:
+            self._scale.fill_(self._init_scale)
+            self._growth_tracker.fill_(int(state_dict.get("_growth_tracker", 0)))

@@ -10,6 +10,8 @@ Fixtures (all fp32, CPU, torch.save of plain dicts of tensors):
   sampler_*.pt : Dirichlet shares + uniform noises fed to / index triples returned by generate_random_masks
   tiny3.pt     : 3-modality MultiMAE (dim 32, depth 2) fwd + 4 losses + all parameter gradients
   interp.pt    : RGB-only model built with the default 224 pos-emb grid run on 32x32 inputs (bicubic/bilinear resize)
+  cuda_*.pt    : shapes the CUDA path supports (head_dim 64/32); weights come from tests/helpers.formula_fill_ (not
+                 stored) and gradients are stored as digests (norm + strided samples)
 """
 import math
 import os
@@ -95,9 +97,13 @@ def build_model(R, in_domains, dim, depth, heads, dec_dim, dec_depth, dec_heads,
     return model.float().train()
 
 
-def record_model(R, name, in_domains, B, size, num_encoded, seed, **kw):
+def record_model(R, name, in_domains, B, size, num_encoded, seed, formula=False, **kw):
     torch.manual_seed(seed)
     model = build_model(R, in_domains, **kw)
+    if formula:
+        sys.path.insert(0, os.path.dirname(HERE))
+        from helpers import digest, formula_fill_
+        formula_fill_(list(model.named_parameters()))
     g = torch.Generator().manual_seed(seed + 1)
     x = {}
     for d in in_domains:
@@ -118,15 +124,19 @@ def record_model(R, name, in_domains, B, size, num_encoded, seed, **kw):
     sum(losses.values()).backward()
     grads = {n: p_.grad.clone() for n, p_ in model.named_parameters() if p_.grad is not None}
     gnorm = torch.norm(torch.stack([g_.norm(2) for g_ in grads.values()]), 2)
+    if formula:
+        state, grads_out = None, {k: digest(v) for k, v in grads.items()}
+    else:
+        state, grads_out = {k: v.detach().clone() for k, v in model.state_dict().items()}, grads
     torch.save({
-        "config": dict(in_domains=list(in_domains), B=B, size=size, num_encoded=num_encoded, **kw),
-        "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+        "config": dict(in_domains=list(in_domains), B=B, size=size, num_encoded=num_encoded, formula=formula, **kw),
+        "state_dict": state,
         "inputs": x,
         "task_masks": {k: v.clone() for k, v in masks.items()},
         "ids_keep": triple[1].clone(), "ids_restore": triple[2].clone(),
         "preds": {k: v.detach().clone() for k, v in preds.items()},
         "losses": {k: v.detach().clone() for k, v in losses.items()},
-        "grads": grads, "grad_norm": gnorm,
+        "grads": grads_out, "grad_norm": gnorm,
     }, os.path.join(HERE, name))
     print("wrote", name, {k: round(float(v), 6) for k, v in losses.items()}, "grad_norm", float(gnorm))
 
@@ -140,3 +150,8 @@ if __name__ == "__main__":
                  dim=32, depth=2, heads=2, dec_dim=16, dec_depth=1, dec_heads=2, image_size=64)
     record_model(R, "interp.pt", ("rgb",), B=2, size=32, num_encoded=2, seed=11,
                  dim=32, depth=1, heads=2, dec_dim=16, dec_depth=1, dec_heads=2, image_size=224)
+    # CUDA-runnable shapes (head_dim 64 / 32, widths multiple of 128); weights from tests/helpers.formula_fill_
+    record_model(R, "cuda_small.pt", ("rgb", "depth", "semseg"), B=3, size=64, num_encoded=12, seed=21, formula=True,
+                 dim=128, depth=2, heads=2, dec_dim=128, dec_depth=1, dec_heads=4, image_size=64)
+    record_model(R, "cuda_interp.pt", ("rgb", "semseg"), B=2, size=96, num_encoded=20, seed=23, formula=True,
+                 dim=128, depth=1, heads=2, dec_dim=128, dec_depth=1, dec_heads=4, image_size=224)

@@ -1,0 +1,116 @@
+"""CPU: host-side contract of the drop-in modules (no kernel is executed here).
+
+ * the C-ABI library loads and exports every symbol include/multimae_b200.h declares;
+ * module constructors / parameter names / shapes follow the reference state_dict schema;
+ * the product path refuses to run without CUDA (no CPU fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import multimae_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(in_domains=("rgb", "depth", "semseg"), dim=128, depth=2, heads=2, dec_dim=128, dec_depth=1, dec_heads=4,
+           image_size=64):
+    from multimae_b200.input_adapters import PatchedInputAdapter, SemSegInputAdapter
+    from multimae_b200.multimae import MultiMAE
+    from multimae_b200.output_adapters import SpatialOutputAdapter
+    conf = {"rgb": (3, 1), "depth": (1, 1), "semseg": (133, 4)}
+    ins, outs = {}, {}
+    for d in in_domains:
+        if d == "semseg":
+            ins[d] = SemSegInputAdapter(num_classes=133, dim_class_emb=64, stride_level=4, patch_size_full=16,
+                                        image_size=image_size)
+        else:
+            ins[d] = PatchedInputAdapter(num_channels=conf[d][0], stride_level=1, patch_size_full=16, image_size=image_size)
+    for key in list(in_domains) + ["norm_rgb"]:
+        task = "rgb" if key == "norm_rgb" else key
+        ch, stride = conf[task]
+        outs[key] = SpatialOutputAdapter(num_channels=ch, stride_level=stride, patch_size_full=16, dim_tokens=dec_dim,
+                                         depth=dec_depth, num_heads=dec_heads, task=task, context_tasks=list(in_domains),
+                                         image_size=image_size)
+    return MultiMAE(ins, outs, num_global_tokens=1, dim_tokens=dim, depth=depth, num_heads=heads)
+
+
+def test_abi_exports_every_declared_symbol():
+    from multimae_b200 import _lib as L
+    from multimae_b200.build import build
+    build()
+    handle = L.lib()
+    header = open(os.path.join(ROOT, "include", "multimae_b200.h")).read()
+    declared = set(re.findall(r"\b(mmae_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(L.SIGNATURES), (declared ^ set(L.SIGNATURES))
+    for name in declared:
+        assert getattr(handle, name) is not None
+    assert handle.mmae_abi_version() == L.ABI_VERSION
+    assert handle.mmae_launch_count() == 0     # nothing launched on a CPU box
+
+
+def test_state_dict_schema_and_roundtrip(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "cuda_small.pt"), map_location="cpu", weights_only=False)
+    c = fx["config"]
+    model = _build(tuple(c["in_domains"]), c["dim"], c["depth"], c["heads"], c["dec_dim"], c["dec_depth"], c["dec_heads"],
+                   c["image_size"])
+    cfg = O.make_config(in_domains=tuple(c["in_domains"]))
+    cfg.dim, cfg.depth, cfg.heads = c["dim"], c["depth"], c["heads"]
+    cfg.dec_dim, cfg.dec_depth, cfg.dec_heads = c["dec_dim"], c["dec_depth"], c["dec_heads"]
+    cfg.posemb_grid = c["image_size"] // 16
+    ref = O.init_params(cfg)                       # schema pinned to the reference by test_oracle_golden
+    sd = model.state_dict()
+    assert set(sd) == set(ref)
+    for k, v in ref.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    for k in sd:
+        if k.endswith("pos_emb"):
+            torch.testing.assert_close(sd[k], ref[k], rtol=0, atol=1e-6)
+    assert {k for k, p in model.named_parameters() if not p.requires_grad} == {k for k in ref if k.endswith("pos_emb")}
+    model.load_state_dict(ref, strict=True)          # reference-schema checkpoint loads strictly
+    assert "global_tokens" in model.no_weight_decay()
+    assert "input_adapters.semseg.class_emb" in model.no_weight_decay()
+
+
+def test_full_size_parameter_count():
+    from multimae_b200.input_adapters import PatchedInputAdapter, SemSegInputAdapter
+    from multimae_b200.multimae import pretrain_multimae_base
+    from multimae_b200.output_adapters import SpatialOutputAdapter
+    ins = {"rgb": PatchedInputAdapter(3, 1, 16), "depth": PatchedInputAdapter(1, 1, 16),
+           "semseg": SemSegInputAdapter(133, 4, 16, dim_class_emb=64)}
+    outs = {}
+    for key, (ch, st, task) in {"rgb": (3, 1, "rgb"), "depth": (1, 1, "depth"), "semseg": (133, 4, "semseg"),
+                                "norm_rgb": (3, 1, "rgb")}.items():
+        outs[key] = SpatialOutputAdapter(ch, st, 16, dim_tokens=256, depth=2, num_heads=8, task=task,
+                                         context_tasks=["rgb", "depth", "semseg"])
+    model = pretrain_multimae_base(ins, outs, num_global_tokens=1, drop_path_rate=0.0)
+    trainable = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    assert trainable == 97_917_632 or abs(trainable - 97.92e6) < 0.01e6, trainable      # 97.92 M
+    assert model.get_num_layers() == 12
+
+
+def test_no_cpu_fallback():
+    from multimae_b200 import _lib as L
+    from multimae_b200.criterion import MaskedMSELoss
+    model = _build()
+    x = {"rgb": torch.randn(1, 3, 64, 64), "depth": torch.randn(1, 1, 64, 64),
+         "semseg": torch.randint(0, 133, (1, 16, 16))}
+    with pytest.raises(L.MmaeError):
+        model(x, num_encoded_tokens=12)
+    with pytest.raises(L.MmaeError):
+        MaskedMSELoss()(torch.randn(1, 3, 32, 32), torch.randn(1, 3, 32, 32))
+
+
+def test_grad_arena_layout():
+    from multimae_b200.functional import GradArena
+    model = _build()
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    arena = GradArena(named, torch.device("cpu"))
+    assert arena.numel >= sum(p.numel() for _, p in named)
+    for n, p in named:
+        v = arena.view(n)
+        assert v.shape == p.shape and v.data_ptr() % 16 == 0
+    arena.flat.fill_(1.0)
+    arena.zero_()
+    assert float(arena.flat.abs().sum()) == 0.0
