@@ -30,6 +30,12 @@ const char* mmae_last_error(void);
 /* number of kernel launches issued through this library by the calling process so far */
 int64_t mmae_launch_count(void);
 
+/* Optional device timing of every GEMM launch (cudaEvent pair on the launch stream); used by bench.py to report the
+ * achieved TFLOP/s of the dominant kernel.  mmae_profile_gemm(1) starts/resets, (0) stops; _read synchronises the
+ * recorded events and returns the summed algorithmic FLOPs (2*M*N*K), summed kernel milliseconds and launch count. */
+int mmae_profile_gemm(int enable);
+int mmae_profile_gemm_read(double* flops, double* ms, int64_t* launches);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM on the tcgen05 tensor cores (bf16 x bf16 -> fp32 accumulate in TMEM), TMA-fed.
  * Replaces every nn.Linear / nn.Conv2d(k=s=P) matmul of the path:

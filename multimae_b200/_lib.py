@@ -107,6 +107,9 @@ SIGNATURES = {
     "mmae_abi_version": (c_int, []),
     "mmae_last_error": (ctypes.c_char_p, []),
     "mmae_launch_count": (c_i64, []),
+    "mmae_profile_gemm": (c_int, [c_int]),
+    "mmae_profile_gemm_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                       ctypes.POINTER(c_i64)]),
     "mmae_gemm_bf16": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int,
                                ctypes.POINTER(GemmEpilogue), c_void_p]),
     "mmae_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),

@@ -15,6 +15,8 @@
 namespace mmae {
 
 void count_launch();
+bool gemm_profile_begin(cudaStream_t st, double flops);
+void gemm_profile_end(cudaStream_t st);
 
 namespace {
 
@@ -239,7 +241,9 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     configured = true;
   }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), split_k);
+  const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K);
   kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+  if (prof) gemm_profile_end(stream);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

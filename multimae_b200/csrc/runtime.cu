@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "../../include/multimae_b200.h"
@@ -20,6 +21,34 @@ void set_last_error(const char* fmt, ...) {
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-launch device timing of the GEMM kernel (bench.py roofline leg; off by default) -------------------
+struct GemmProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> begin, end;
+  std::vector<double> flops;
+  size_t used = 0;
+};
+static GemmProfile g_prof;
+static const size_t kProfCap = 8192;
+
+bool gemm_profile_begin(cudaStream_t st, double flops) {
+  if (!g_prof.on || g_prof.used >= kProfCap) return false;
+  if (g_prof.begin.size() <= g_prof.used) {
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return false;
+    g_prof.begin.push_back(a);
+    g_prof.end.push_back(b);
+    g_prof.flops.push_back(0.0);
+  }
+  g_prof.flops[g_prof.used] = flops;
+  cudaEventRecord(g_prof.begin[g_prof.used], st);
+  return true;
+}
+void gemm_profile_end(cudaStream_t st) {
+  cudaEventRecord(g_prof.end[g_prof.used], st);
+  g_prof.used++;
+}
 
 int sm_count() {
   static int cached = 0;
@@ -95,3 +124,23 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 extern "C" int mmae_abi_version(void) { return MMAE_ABI_VERSION; }
 extern "C" const char* mmae_last_error(void) { return mmae::g_err; }
 extern "C" int64_t mmae_launch_count(void) { return mmae::g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int mmae_profile_gemm(int enable) {
+  mmae::g_prof.on = enable != 0;
+  if (enable) mmae::g_prof.used = 0;   // (1) resets and starts, (0) stops and keeps the records for _read
+  return MMAE_OK;
+}
+extern "C" int mmae_profile_gemm_read(double* flops, double* ms, int64_t* launches) {
+  double f = 0.0, t = 0.0;
+  for (size_t i = 0; i < mmae::g_prof.used; ++i) {
+    if (cudaEventSynchronize(mmae::g_prof.end[i]) != cudaSuccess) return MMAE_ERR_CUDA;
+    float e = 0.f;
+    if (cudaEventElapsedTime(&e, mmae::g_prof.begin[i], mmae::g_prof.end[i]) != cudaSuccess) return MMAE_ERR_CUDA;
+    t += e;
+    f += mmae::g_prof.flops[i];
+  }
+  if (flops) *flops = f;
+  if (ms) *ms = t;
+  if (launches) *launches = (int64_t)mmae::g_prof.used;
+  return MMAE_OK;
+}

@@ -66,13 +66,12 @@ def _embed(adapters, x, ids_keep, global_tokens, arena, prefix_of, on_grads_read
         tensors += [x[name], ad.proj.weight, ad.proj.bias, cemb]
         pos.append(ad._resized_pos(layout.grid_h[t], layout.grid_w[t], ad.pos_mode))
     meta = dict(layout=layout, arena=arena, names=names, pos=pos, on_grads_ready=on_grads_ready)
-    return Fn.EmbedFunction.apply(meta, ids_keep, *tensors, global_tokens.reshape(-1, global_tokens.shape[-1]))
+    return Fn.EmbedFunction.apply(meta, ids_keep, *tensors, global_tokens)
 
 
 def embed_all_patches(adapter, x):
     """Stand-alone input-adapter forward: every patch of one modality -> [B, N, D] (reference adapter.forward)."""
-    if not x.is_cuda:
-        raise L.MmaeError("multimae_b200 input adapters need CUDA tensors (no CPU fallback)")
+    Fn._require_cuda(x, "input adapter")
     nh, nw = adapter.grid(x)
     B = x.shape[0]
     ids = torch.arange(nh * nw, device=x.device).unsqueeze(0).expand(B, -1).contiguous()
@@ -255,9 +254,7 @@ class MultiMAE(nn.Module):
         if not adapters:
             raise ValueError("no input modality matches the model's input adapters")
         dev = x[adapters[0][0]].device
-        if dev.type != "cuda":
-            raise L.MmaeError("multimae_b200.MultiMAE.forward needs CUDA inputs: the path is sm_100a kernels only "
-                              "(no CPU fallback)")
+        Fn._require_cuda(x[adapters[0][0]], "MultiMAE.forward")
         # token placeholders: only B / N_t / device are read downstream (the tokens are never materialised)
         placeholders = OrderedDict()
         for name, ad in adapters:

@@ -43,6 +43,12 @@ class NativeScalerWithGradNormCount:
         self._scale = None           # device tensors, created lazily on the loss's device
         self._growth_tracker = None
         self._arena = None
+        self._reducer = None
+
+    def attach_reducer(self, reducer):
+        """Data-parallel: join the bucketed all-reduce after backward and fold 1/world into the unscale pass."""
+        self._reducer = reducer
+        return self
 
     def attach_arena(self, arena):
         """Tell the scaler which flat gradient buffer backs the parameters (MultiMAE.grad_arena())."""
@@ -61,9 +67,10 @@ class NativeScalerWithGradNormCount:
         if not update_grad:
             return None
         arena = self._arena or _find_arena(optimizer, parameters)
+        post = self._reducer.finish() if self._reducer is not None else 1.0
         if arena is not None:
             inv = (1.0 / self._scale) if self._enabled else None
-            norm, out2 = Fn.grad_unscale_norm(arena.flat, inv_scale=1.0, inv_scale_tensor=inv)
+            norm, out2 = Fn.grad_unscale_norm(arena.flat, inv_scale=1.0, post_scale=post, inv_scale_tensor=inv)
             found_inf = out2[1:2]
             if not arena.owned and parameters is not None:
                 # autograd may have copied instead of aliasing the arena views: make p.grad the (unscaled) views

@@ -1,0 +1,94 @@
+"""Drop-in overlay: make `import multimae...` / `from utils import NativeScalerWithGradNormCount` resolve to this package
+so the reference's UNCHANGED run_pretraining_multimae.py drives the sm_100a path.
+
+    python -m multimae_b200.overlay /path/to/MultiMAE/run_pretraining_multimae.py -c cfg.yaml [script args...]
+
+What is replaced (north_star "Subsystems replaced"): multimae.multimae, multimae.multimae_utils, multimae.input_adapters,
+multimae.output_adapters (SpatialOutputAdapter), multimae.criterion, utils.native_scaler.NativeScalerWithGradNormCount
+and — because the model owns its bucketed gradient all-reduce — torch.nn.parallel.DistributedDataParallel is substituted
+by an identity wrapper.  Everything else (argument parsing, data pipeline, optimizer factory, logging, checkpoints)
+stays the reference's own code from `reference_root`."""
+import importlib
+import math
+import os
+import runpy
+import sys
+import types
+
+
+class _IdentityDDP:
+    """Stands in for DistributedDataParallel (run_pretraining_multimae.py:380-383): gradients are reduced in place by
+    multimae_b200.parallel.FlatGradReducer, so no wrapper logic is needed.  Exposes `.module` like DDP does."""
+
+    def __new__(cls, module, *args, **kwargs):
+        import torch
+        from .multimae import MultiMAE
+        from .parallel import attach_data_parallel, broadcast_parameters
+        if isinstance(module, MultiMAE) and torch.distributed.is_initialized():
+            broadcast_parameters(module)
+            module._mmae_reducer = attach_data_parallel(module)
+            return _Wrapped(module)
+        return _Wrapped(module)
+
+
+class _Wrapped:
+    def __init__(self, module):
+        self.__dict__["module"] = module
+
+    def __call__(self, *a, **k):
+        return self.module(*a, **k)
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["module"], name)
+
+
+def install(reference_root=None, replace_ddp=True):
+    """Install the overlay into sys.modules.  `reference_root`: checkout of EPFL-VILAB/MultiMAE (for its `utils` package)."""
+    if "torch._six" not in sys.modules:            # utils/native_scaler.py:11 imports a module removed in torch >= 2
+        six = types.ModuleType("torch._six")
+        six.inf = math.inf
+        sys.modules["torch._six"] = six
+    if reference_root is not None and reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    pkg = types.ModuleType("multimae")
+    pkg.__path__ = []                              # namespace-like: submodules are injected below
+    sys.modules["multimae"] = pkg
+    for sub in ("multimae_utils", "input_adapters", "output_adapters", "criterion", "multimae"):
+        mod = importlib.import_module("multimae_b200." + sub)
+        sys.modules["multimae." + sub] = mod
+        setattr(pkg, sub, mod)
+    from . import multimae as mm
+    # register the factories in the reference's registry if it only became importable now
+    try:
+        from utils.registry import _model_entrypoints, register_model  # type: ignore
+        for name in mm.__all__:
+            if name not in _model_entrypoints:
+                register_model(getattr(mm, name))
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        import utils  # type: ignore
+        from .native_scaler import NativeScalerWithGradNormCount, get_grad_norm_
+        utils.NativeScalerWithGradNormCount = NativeScalerWithGradNormCount
+        utils.native_scaler.NativeScalerWithGradNormCount = NativeScalerWithGradNormCount
+        utils.native_scaler.get_grad_norm_ = get_grad_norm_
+    except Exception:  # noqa: BLE001
+        pass
+    if replace_ddp:
+        import torch
+        torch.nn.parallel.DistributedDataParallel = _IdentityDDP
+    return pkg
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv:
+        raise SystemExit(__doc__)
+    script = os.path.abspath(argv[0])
+    install(reference_root=os.path.dirname(script))
+    sys.argv = [script] + argv[1:]
+    runpy.run_path(script, run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,231 @@
+"""GPU: parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star): indices bit-exact; floating point within 1e-2 relative L2 for the bf16 tensor-core
+path against the fp32 oracle (per tensor: ||a-b|| / ||b||); fp32-only kernels (LayerNorm, losses, index kernels) 1e-5.
+Nothing here reads /root/reference."""
+import os
+
+import pytest
+import torch
+
+from helpers import formula_fill_, rel_l2
+from oracle import multimae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2          # activations / predictions / losses, relative L2
+GRAD_TOL = 3e-2          # parameter gradients: global / median relative L2 (bf16 operands in dgrad and wgrad)
+PER_TENSOR_TOL = 0.25    # any single gradient tensor (see _check_grads)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), map_location="cpu", weights_only=False)
+
+
+def _build_model(c):
+    from test_host_api import _build
+    return _build(tuple(c["in_domains"]), c["dim"], c["depth"], c["heads"], c["dec_dim"], c["dec_depth"], c["dec_heads"],
+                  c["image_size"])
+
+
+def _oracle_cfg(c):
+    cfg = O.make_config(in_domains=tuple(c["in_domains"]))
+    cfg.dim, cfg.depth, cfg.heads = c["dim"], c["depth"], c["heads"]
+    cfg.dec_dim, cfg.dec_depth, cfg.dec_heads = c["dec_dim"], c["dec_depth"], c["dec_heads"]
+    cfg.posemb_grid = c["image_size"] // 16
+    return cfg
+
+
+def _check_grads(got, ref):
+    """All parameter gradients: global relative L2 over the concatenation < GRAD_TOL, median per-tensor < GRAD_TOL,
+    no single tensor beyond PER_TENSOR_TOL (small, cancellation-dominated tensors carry more bf16 noise)."""
+    errs = sorted(((rel_l2(got[k], ref[k]), k) for k in ref), reverse=True)
+    print("worst gradient tensors:", errs[:6])
+    for k in ref:
+        assert got[k] is not None and torch.isfinite(got[k]).all(), k
+    flat_g = torch.cat([got[k].detach().float().cpu().flatten() for k in ref])
+    flat_r = torch.cat([ref[k].detach().float().cpu().flatten() for k in ref])
+    glob = rel_l2(flat_g, flat_r)
+    median = errs[len(errs) // 2][0]
+    print("global rel-l2 %.4f, median %.4f, max %.4f (%s)" % (glob, median, errs[0][0], errs[0][1]))
+    assert glob < GRAD_TOL and median < GRAD_TOL, (glob, median)
+    assert errs[0][0] < PER_TENSOR_TOL, errs[0]
+
+
+def _loss_modules():
+    from multimae_b200.criterion import MaskedCrossEntropyLoss, MaskedL1Loss, MaskedMSELoss
+    return {"rgb": MaskedMSELoss(16, 1), "depth": MaskedL1Loss(16, 1), "semseg": MaskedCrossEntropyLoss(16, 4),
+            "norm_rgb": MaskedMSELoss(16, 1, norm_pix=True)}
+
+
+def _run_cuda_step(model, x, triple, dev):
+    model.generate_random_masks = lambda *a, **k: triple
+    preds, masks = model({k: v.to(dev) for k, v in x.items()}, num_encoded_tokens=triple[1].shape[1], alphas=1.0)
+    fns = _loss_modules()
+    losses = {}
+    for task in preds:
+        src = "rgb" if task == "norm_rgb" else task
+        losses[task] = fns[task](preds[task].float(), x[src].to(dev), mask=masks.get(src))
+    sum(losses.values()).backward()
+    torch.cuda.synchronize()
+    return preds, masks, losses
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["sampler_small.pt", "sampler_cfg2.pt", "sampler_alpha.pt"])
+def test_mask_sampler_bit_exact(golden_dir, dev, name):
+    from multimae_b200 import functional as Fn
+    fx = _load(golden_dir, name)
+    counts = [n.shape[1] for n in fx["noises"]]
+    masks, ids_keep, ids_restore = Fn.sample_masks(fx["shares"].to(dev), torch.cat(fx["noises"], 1).to(dev),
+                                                   fx["noise_all"].to(dev), counts, fx["num_encoded"])
+    assert torch.equal(ids_keep.cpu(), fx["ids_keep"])
+    assert torch.equal(ids_restore.cpu(), fx["ids_restore"])
+    assert torch.equal(masks.cpu(), torch.cat(fx["task_masks"], 1))
+    assert masks.dtype == torch.int64 and ids_keep.dtype == torch.int64
+
+
+def test_mask_sampler_large_and_properties(dev):
+    """448^2-sized problem (3 x 784 tokens, 392 kept) against the oracle + structural properties."""
+    from multimae_b200 import functional as Fn
+    g = torch.Generator().manual_seed(5)
+    B, counts, T = 32, [784, 784, 784], 392
+    shares = torch.distributions.Dirichlet(torch.ones(3)).sample((B,))
+    noises = [torch.rand(B, n, generator=g) for n in counts]
+    noise_all = torch.rand(B, sum(counts), generator=g)
+    ref_masks, ref_keep, ref_restore = O.sample_masks(shares, noises, noise_all, T)
+    masks, ids_keep, ids_restore = Fn.sample_masks(shares.to(dev), torch.cat(noises, 1).to(dev), noise_all.to(dev), counts, T)
+    assert torch.equal(ids_keep.cpu(), ref_keep) and torch.equal(ids_restore.cpu(), ref_restore)
+    assert torch.equal(masks.cpu(), torch.cat(ref_masks, 1))
+    assert bool(((masks == 0).sum(1) == T).all())                                   # exactly T visible per row
+    assert bool((torch.sort(ids_restore, 1).values == torch.arange(sum(counts), device=dev)).all())   # a permutation
+
+
+@pytest.mark.parametrize("name", ["cuda_small.pt", "cuda_interp.pt"])
+def test_model_against_golden_and_oracle(golden_dir, dev, name):
+    fx = _load(golden_dir, name)
+    c = fx["config"]
+    model = _build_model(c)
+    formula_fill_(list(model.named_parameters()))
+    model = model.to(dev).train()
+    triple = ({k: v.to(dev) for k, v in fx["task_masks"].items()}, fx["ids_keep"].to(dev), fx["ids_restore"].to(dev))
+    preds, masks, losses = _run_cuda_step(model, fx["inputs"], triple, dev)
+
+    for k, ref in fx["preds"].items():
+        assert rel_l2(preds[k], ref) < BF16_TOL, (k, rel_l2(preds[k], ref))
+    for k, ref in fx["losses"].items():
+        assert abs(float(losses[k]) - float(ref)) < BF16_TOL * abs(float(ref)), (k, float(losses[k]), float(ref))
+    for k in masks:
+        assert torch.equal(masks[k].cpu(), fx["task_masks"][k])
+
+    # gradients: full tensors against the oracle (run here on CPU, fp32), digests against the reference fixture
+    cfg = _oracle_cfg(c)
+    p = O.init_params(cfg)
+    train = O.trainable(p)
+    formula_fill_(list(train.items()))
+    for v in train.values():
+        v.requires_grad_(True)
+    o_losses, _ = O.step_losses(p, fx["inputs"], cfg, fx["task_masks"], fx["ids_keep"], fx["ids_restore"])
+    sum(o_losses.values()).backward()
+    named = dict(model.named_parameters())
+    _check_grads({k: named[k].grad for k in train}, {k: v.grad for k, v in train.items()})
+    for k in train:                                        # and the reference's own digests
+        d = fx["grads"][k]
+        assert abs(float(named[k].grad.float().norm()) - float(d["norm"])) < PER_TENSOR_TOL * float(d["norm"]) + 1e-6, k
+
+
+def test_full_size_model_against_oracle(dev):
+    """MultiMAE-B, rgb+depth+semseg, 224^2, 98 visible tokens (BASELINE config 2 at B=2) against the fp32 oracle."""
+    from test_host_api import _build
+    B = 2
+    model = _build(("rgb", "depth", "semseg"), 768, 12, 12, 256, 2, 8, 224)
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():                                   # non-zero biases / mask tokens so every term is live
+        for k, v in sd.items():
+            if k.endswith(".bias") or k.endswith("mask_token"):
+                v.add_(torch.randn(v.shape, generator=g) * 0.05)
+    model.load_state_dict(sd)
+    cfg = O.make_config()
+    x = O.synthetic_inputs(cfg, B, 224, seed=0)
+    shares, noises, noise_all = O.synthetic_mask_draws(cfg, B, 224, seed=1)
+    m, ids_keep, ids_restore = O.sample_masks(shares, noises, noise_all, 98)
+    tmask = {d.name: mm for d, mm in zip(cfg.in_domains, m)}
+
+    p = {k: v.clone() for k, v in sd.items()}
+    train = O.trainable(p)
+    for v in train.values():
+        v.requires_grad_(True)
+    o_losses, o_preds = O.step_losses(p, x, cfg, tmask, ids_keep, ids_restore)
+    sum(o_losses.values()).backward()
+
+    model = model.to(dev).train()
+    triple = ({k: v.to(dev) for k, v in tmask.items()}, ids_keep.to(dev), ids_restore.to(dev))
+    preds, masks, losses = _run_cuda_step(model, x, triple, dev)
+    for k in o_preds:
+        assert rel_l2(preds[k], o_preds[k]) < BF16_TOL, (k, rel_l2(preds[k], o_preds[k]))
+        assert abs(float(losses[k]) - float(o_losses[k])) < BF16_TOL * abs(float(o_losses[k])), k
+    named = dict(model.named_parameters())
+    _check_grads({k: named[k].grad for k in train}, {k: v.grad for k, v in train.items()})
+
+
+def test_losses_against_oracle(dev):
+    from multimae_b200.criterion import MaskedCrossEntropyLoss, MaskedL1Loss, MaskedMSELoss
+    g = torch.Generator().manual_seed(0)
+    B = 5
+    mask = (torch.rand(B, 196, generator=g) > 0.3).long()
+    mask[1] = 0                                               # a sample with no masked patch -> skipped by nanmean
+    cases = [
+        (MaskedMSELoss(16, 1), lambda p_, t, m: O.masked_mse(p_, t, m, 16, 1), torch.randn(B, 3, 224, 224, generator=g),
+         torch.randn(B, 3, 224, 224, generator=g)),
+        (MaskedMSELoss(16, 1, norm_pix=True), lambda p_, t, m: O.masked_mse(p_, t, m, 16, 1, norm_pix=True),
+         torch.randn(B, 3, 224, 224, generator=g), torch.randn(B, 3, 224, 224, generator=g) * 3 + 1),
+        (MaskedL1Loss(16, 1), lambda p_, t, m: O.masked_l1(p_, t, m, 16, 1), torch.randn(B, 1, 224, 224, generator=g),
+         torch.randn(B, 1, 224, 224, generator=g)),
+        (MaskedCrossEntropyLoss(16, 4), lambda p_, t, m: O.masked_ce(p_, t, m, 16, 4),
+         torch.randn(B, 133, 56, 56, generator=g) * 2, torch.randint(0, 133, (B, 56, 56), generator=g)),
+    ]
+    for mod, ofn, pred, tgt in cases:
+        for mk in (mask, None, torch.zeros_like(mask)):
+            pr = pred.clone().requires_grad_(True)
+            ref = ofn(pr, tgt, mk)
+            pc = pred.to(dev).requires_grad_(True)
+            got = mod(pc, tgt.to(dev), mask=None if mk is None else mk.to(dev))
+            assert abs(float(got) - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (type(mod).__name__, float(got), float(ref))
+            if ref.requires_grad:
+                ref.backward()
+                got.backward()
+                assert rel_l2(pc.grad, pr.grad) < 1e-5, type(mod).__name__
+            else:                                             # all-zero mask: constant 0 (criterion.py:42,100,157)
+                assert float(got) == 0.0
+
+
+def test_flat_adamw_matches_torch(dev):
+    from multimae_b200 import functional as Fn
+    torch.manual_seed(0)
+    n = 10007
+    p0 = torch.randn(n, device=dev)
+    g0 = torch.randn(n, device=dev)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    flat, m, v = p0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    for step in range(1, 4):
+        ref.grad = g0 * step
+        opt.step()
+        Fn.adamw_step(flat, g0 * step, m, v, 1e-3, (0.9, 0.95), 1e-8, 0.05, step)
+    assert rel_l2(flat, ref.data) < 1e-6
+    # grad norm / unscale
+    gflat = torch.randn(100003, device=dev)
+    ref_norm = (gflat * 0.5).norm()
+    norm, out2 = Fn.grad_unscale_norm(gflat, inv_scale=0.5)
+    assert abs(float(norm) - float(ref_norm)) < 1e-4 * float(ref_norm) and float(out2[1]) == 0.0
+    gflat[17] = float("inf")
+    _, out2 = Fn.grad_unscale_norm(gflat)
+    assert float(out2[1]) == 1.0

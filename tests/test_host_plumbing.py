@@ -1,0 +1,120 @@
+"""CPU: exercise the Python host layer end to end (autograd Functions, struct marshalling, gradient arena, scaler,
+flat optimizer bookkeeping) against a STUB of the C library that validates every call's argument count / ctypes
+convertibility and returns success without computing.  Numerical results are meaningless here; what is checked is
+the plumbing the GPU tests rely on."""
+import ctypes
+
+import pytest
+import torch
+
+from multimae_b200 import _lib as L
+from multimae_b200 import functional as Fn
+from test_host_api import _build
+
+
+class _StubLib:
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if name not in L.SIGNATURES:
+            raise AttributeError(name)
+        res, argtypes = L.SIGNATURES[name]
+
+        def fn(*args):
+            assert len(args) == len(argtypes), "%s: %d args for %d parameters" % (name, len(args), len(argtypes))
+            for a, t in zip(args, argtypes):
+                if isinstance(a, type(ctypes.byref(ctypes.c_int()))):
+                    continue
+                t.from_param(a)        # raises on a type the real ctypes call would reject
+            self.calls.append(name)
+            if name.endswith("_bytes"):
+                return 4096
+            if name == "mmae_abi_version":
+                return L.ABI_VERSION
+            if name == "mmae_last_error":
+                return b""
+            return 0
+        return fn
+
+
+@pytest.fixture()
+def stub(monkeypatch):
+    s = _StubLib()
+    monkeypatch.setattr(L, "lib", lambda: s)
+    monkeypatch.setattr(L, "current_stream", lambda: 0)
+    monkeypatch.setattr(Fn, "_require_cuda", lambda t, what: None)
+    return s
+
+
+def _inputs(B=2, size=64):
+    return {"rgb": torch.randn(B, 3, size, size), "depth": torch.randn(B, 1, size, size),
+            "semseg": torch.randint(0, 133, (B, size // 4, size // 4))}
+
+
+def test_forward_backward_plumbing(stub):
+    from multimae_b200.criterion import MaskedCrossEntropyLoss, MaskedL1Loss, MaskedMSELoss
+    model = _build().train()
+    x = _inputs()
+    preds, masks = model(x, num_encoded_tokens=12, alphas=1.0)
+    assert set(preds) == {"rgb", "depth", "semseg", "norm_rgb"} and set(masks) == {"rgb", "depth", "semseg"}
+    assert preds["rgb"].shape == (2, 3, 64, 64) and preds["semseg"].shape == (2, 133, 16, 16)
+    assert masks["rgb"].shape == (2, 16) and masks["rgb"].dtype == torch.int64
+    fns = {"rgb": MaskedMSELoss(16, 1), "depth": MaskedL1Loss(16, 1), "semseg": MaskedCrossEntropyLoss(16, 4),
+           "norm_rgb": MaskedMSELoss(16, 1, norm_pix=True)}
+    loss = sum(fns[k](preds[k].float(), x["rgb" if k == "norm_rgb" else k], mask=masks["rgb" if k == "norm_rgb" else k])
+               for k in preds)
+    loss.backward()
+    arena = model.grad_arena()
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            assert p.grad is not None and p.grad.shape == p.shape, n
+        else:
+            assert p.grad is None, n
+    # every module-level entry point was reached
+    for name in ("mmae_sample_masks", "mmae_embed_forward", "mmae_embed_backward", "mmae_block_forward",
+                 "mmae_block_backward", "mmae_dechead_forward", "mmae_dechead_backward", "mmae_dectail_forward",
+                 "mmae_dectail_backward", "mmae_masked_loss_forward", "mmae_masked_loss_backward"):
+        assert name in stub.calls, name
+    assert stub.calls.count("mmae_block_forward") == 2 + 4 * 1 and stub.calls.count("mmae_dechead_backward") == 4
+    assert arena.numel >= sum(p.numel() for p in model.parameters() if p.requires_grad)
+
+
+def test_owned_gradients_scaler_and_flat_optimizer(stub):
+    from multimae_b200.criterion import MaskedMSELoss
+    from multimae_b200.native_scaler import NativeScalerWithGradNormCount
+    from multimae_b200.optim import FlatAdamW
+    model = _build(in_domains=("rgb",)).train()
+    opt = FlatAdamW(model, lr=1e-3)
+    arena = model.grad_arena()
+    assert arena.owned and all(p.grad is not None and p.grad.data_ptr() == arena.views[n].data_ptr()
+                               for n, p in model.named_parameters() if p.requires_grad)
+    ready = []
+    model.set_grad_callback(lambda names: ready.extend(names))
+    scaler = NativeScalerWithGradNormCount(enabled=True).attach_arena(arena)
+    x = {"rgb": torch.randn(2, 3, 64, 64)}
+    preds, masks = model(x, num_encoded_tokens=4)
+    loss = sum(MaskedMSELoss(16, 1)(preds[k], x["rgb"], mask=masks["rgb"]) for k in preds)
+    opt.zero_grad()
+    norm = scaler(loss, opt, parameters=model.parameters())
+    assert norm is not None and "mmae_grad_unscale_norm" in stub.calls and "mmae_adamw_step" in stub.calls
+    assert set(ready) == {n for n, p in model.named_parameters() if p.requires_grad}     # every gradient announced once
+    assert len(ready) == len(set(ready))
+    sd = scaler.state_dict()
+    assert "scale" in sd and sd["scale"] > 0
+    # parameters were re-homed into one flat buffer and still expose the reference state_dict schema
+    assert all(p.data_ptr() >= opt.flat_params.data_ptr() for p in model.parameters() if p.requires_grad)
+
+
+def test_fixed_masks_and_no_masking(stub):
+    model = _build().train()
+    x = _inputs(B=1)
+    tm = {k: torch.ones(1, 16, dtype=torch.long) for k in ("rgb", "depth", "semseg")}
+    tm["rgb"][0, :5] = 0
+    tm["depth"][0, 3] = 0
+    preds, masks = model(x, task_masks=tm)
+    assert masks is tm and preds["rgb"].shape == (1, 3, 64, 64)
+    preds, masks = model(x, mask_inputs=False)
+    assert preds["depth"].shape == (1, 1, 64, 64)
+    with pytest.raises(ValueError):
+        model(_inputs(B=2), task_masks={k: torch.cat([v, torch.ones_like(v)]) for k, v in tm.items()})
