@@ -69,6 +69,10 @@ typedef struct mmae_gemm_epilogue {
   int64_t ld_residual, ld_dgelu_z, ld_preact, ld_out_f32, ld_out_bf16;
 } mmae_gemm_epilogue;
 
+/* Kernel variant selection for measurements: -1 = heuristic (default), 0 = one-tile-per-CTA 128x128,
+ * 1 = persistent 128x128 with double-buffered TMEM, 2 = persistent 128x256.  Env MMAE_GEMM_VARIANT sets the initial value. */
+int mmae_gemm_set_variant(int variant);
+
 int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                    int M, int N, int K, int split_k, const mmae_gemm_epilogue* ep, void* stream);
 
@@ -107,6 +111,8 @@ int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t lddy, const 
  * [b*N, (b+1)*N).  head_dim in {32, 64}.  lse[B,H,Nq] = log-sum-exp of the scaled scores (saved for backward).
  * backward: delta_ws is a [B,H,Nq] fp32 scratch; dq/dk/dv are written (not accumulated).
  * ---------------------------------------------------------------------------------------------- */
+/* 1 (default): tcgen05 kernels where supported (Nq, Nk <= 128, head_dim 64); 0: warp-MMA kernels everywhere */
+int mmae_attention_set_tc(int enable);
 int mmae_attention_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                            void* o, int64_t ldo, float* lse, int B, int H, int Nq, int Nk, int head_dim,
                            float scale, void* stream);

@@ -110,6 +110,7 @@ SIGNATURES = {
     "mmae_profile_gemm": (c_int, [c_int]),
     "mmae_profile_gemm_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                        ctypes.POINTER(c_i64)]),
+    "mmae_gemm_set_variant": (c_int, [c_int]),
     "mmae_gemm_bf16": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int,
                                ctypes.POINTER(GemmEpilogue), c_void_p]),
     "mmae_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
@@ -120,6 +121,7 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "mmae_layernorm_backward": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mmae_attention_set_tc": (c_int, [c_int]),
     "mmae_attention_forward": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p,
                                        c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "mmae_attention_backward": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p,

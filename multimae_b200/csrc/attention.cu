@@ -13,8 +13,16 @@
 #include "common.cuh"
 #include "../../include/multimae_b200.h"
 
+#include <cstdlib>
+
 namespace mmae {
 void count_launch();
+bool attn_tc_supported(int Nq, int Nk, int head_dim);
+int attn_tc_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                    float* lse, int B, int H, int Nq, int Nk, float scale, cudaStream_t st);
+int attn_tc_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+                     int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                     void* dv, int64_t lddv, int B, int H, int Nq, int Nk, float scale, cudaStream_t st);
 namespace {
 
 constexpr int ATT_ROWS = 64;    // stationary rows per CTA (4 warps x 16)
@@ -425,6 +433,16 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 using namespace mmae;
 
+// 1 = tcgen05 kernels for shapes they support (default), 0 = mma.sync kernels everywhere (A/B measurements)
+static int g_attn_tc = []() {
+  const char* e = getenv("MMAE_ATTN_TC");
+  return e ? atoi(e) : 1;
+}();
+extern "C" int mmae_attention_set_tc(int enable) {
+  g_attn_tc = enable;
+  return MMAE_OK;
+}
+
 extern "C" int mmae_attention_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                       void* o, int64_t ldo, float* lse, int B, int H, int Nq, int Nk, int head_dim,
                                       float scale, void* stream) {
@@ -435,6 +453,8 @@ extern "C" int mmae_attention_forward(const void* q, int64_t ldq, const void* k,
              MMAE_ERR_ARG, "mmae_attention_forward: 16-byte alignment / ld %% 8 required");
   dim3 grid(ceil_div(Nq, ATT_ROWS), H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (g_attn_tc && attn_tc_supported(Nq, Nk, head_dim))
+    return attn_tc_forward(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, scale, st);
   const bf16 *qp = (const bf16*)q, *kp = (const bf16*)k, *vp = (const bf16*)v;
   if (head_dim == 64)
     attn_fwd_kernel<64><<<grid, ATT_THREADS, 0, st>>>(qp, ldq, kp, ldk, vp, ldv, (bf16*)o, ldo, lse, Nq, Nk, H, scale);
@@ -461,6 +481,13 @@ extern "C" int mmae_attention_backward(const void* q, int64_t ldq, const void* k
   const bf16 *qp = (const bf16*)q, *kp = (const bf16*)k, *vp = (const bf16*)v, *op = (const bf16*)o,
              *dop = (const bf16*)d_o;
   dim3 gq(ceil_div(Nq, ATT_ROWS), H, B), gk(ceil_div(Nk, ATT_ROWS), H, B);
+  if (g_attn_tc && attn_tc_supported(Nq, Nk, head_dim)) {
+    attn_delta_kernel<64><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
+    count_launch();
+    MMAE_LAUNCH_OK();
+    return attn_tc_backward(q, ldq, k, ldk, v, ldv, d_o, lddo, lse, delta_ws, dq, lddq, dk, lddk, dv, lddv, B, H, Nq, Nk,
+                            scale, st);
+  }
   if (head_dim == 64) {
     attn_delta_kernel<64><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
     attn_bwd_dq_kernel<64><<<gq, ATT_THREADS, 0, st>>>(qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dq,

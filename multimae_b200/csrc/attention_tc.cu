@@ -1,0 +1,417 @@
+// tcgen05 fused attention for short sequences (Nq, Nk <= 128, head_dim 64): the encoder MHSA of MultiMAE-B/L
+// (99 x 99 x 64 per (batch, head) problem), forward and backward.  One CTA per (b, h); the whole problem lives on chip:
+//
+//   forward : TMA (3D map, zero-filled past the sequence end) -> Q, K, V tiles in 128B-swizzled smem
+//             S = Q K^T      tcgen05.mma 128 x Nk16 x 64, fp32 accumulator in TMEM columns [0,128)
+//             softmax        one thread per query row: tcgen05.ld, exp2, P -> bf16 K-major swizzled smem (aliases Q|K)
+//             O = P V        tcgen05.mma 128 x 64 x Nk16 (V consumed as an MN-major operand straight from its row-major
+//                            tile), accumulator aliases the S columns; epilogue scales by 1/l and stores bf16 rows
+//   backward: S and dP = dO V^T recomputed on the tensor cores, P/dS written once to smem and consumed by three more
+//             UMMAs in two roles: K-major A (dQ = dS K) and MN-major A (dV = P^T dO, dK = dS^T Q) -- the same bytes.
+//
+// Replaces multimae/multimae_utils.py:175-179 (q@k^T*scale -> softmax -> @v) and its autograd backward for the
+// encoder; other shapes (decoder head_dim 32, longer sequences) run on the mma.sync kernels in attention.cu.
+#include "common.cuh"
+#include "../../include/multimae_b200.h"
+
+namespace mmae {
+void count_launch();
+namespace {
+
+constexpr int TQ = 128;          // query rows per CTA (one TMEM lane each)
+constexpr int DH = 64;           // head dim: 64 bf16 = one 128-byte swizzle row
+constexpr int TILE_BYTES = TQ * DH * 2;   // 16 KB: a [128 x 64] bf16 tile
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+// byte offset of element (row r, 16-byte chunk j) inside a [rows x 128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t swz128(int r, int j) { return uint32_t(r) * 128u + uint32_t((j ^ (r & 7)) << 4); }
+
+// write 32 consecutive bf16 values (already packed 2 per u32) of row r, columns [c0, c0+32) of a K-major tile made of
+// 64-column panels of TILE_BYTES each
+__device__ __forceinline__ void store_row32(uint8_t* tile, int r, int c0, const uint32_t (&pk)[16]) {
+  uint8_t* panel = tile + (c0 >> 6) * TILE_BYTES;
+  const int j0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 v = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    *reinterpret_cast<uint4*>(panel + swz128(r, j0 + j)) = v;
+  }
+}
+
+struct AttnTcParams {
+  int Nq, Nk, H;
+  float scale;
+  bf16* O;
+  int64_t ldo;
+  float* lse;
+};
+
+__global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                          const __grid_constant__ CUtensorMap tmK,
+                                                          const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;                      // 16 KB   } P (two 64-key panels, 32 KB) aliases Q|K once S is complete
+  uint8_t* sK = smem + TILE_BYTES;         // 16 KB   }
+  uint8_t* sV = smem + 2 * TILE_BYTES;     // 16 KB
+  uint8_t* sP = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES);   // [0] loads, [1] S ready, [2] O ready
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk16 = (p.Nk + 15) & ~15;      // UMMA N of S / K extent of P V
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      mbar_init(&bars[2], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], 3 * TILE_BYTES);
+    tma_load_3d(sQ, &tmQ, &bars[0], h * DH, 0, b);
+    tma_load_3d(sK, &tmK, &bars[0], h * DH, 0, b);
+    tma_load_3d(sV, &tmV, &bars[0], h * DH, 0, b);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    // S[128 x nk16] = Q K^T : both operands K-major, K = 64 -> 4 UMMA steps
+    const uint32_t idesc = umma_idesc_bf16(128, nk16, 0, 0);
+#pragma unroll
+    for (int j = 0; j < DH / 16; ++j) {
+      const uint64_t da = umma_smem_desc_sw128(smem_u32(sQ) + j * 32, 16, 1024);
+      const uint64_t db = umma_smem_desc_sw128(smem_u32(sK) + j * 32, 16, 1024);
+      tc_mma_f16_ss(tmem, da, db, idesc, j != 0 ? 1u : 0u);
+    }
+    tc_commit(&bars[1]);
+  }
+  __syncwarp();
+
+  // ---------------------------------------------------------------- softmax: thread = query row
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
+  const float sl2 = p.scale * LOG2E_F;
+  float mx = -INFINITY;
+  for (int c0 = 0; c0 < nk16; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(trow + c0, r);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c0 + i < p.Nk) mx = fmaxf(mx, __uint_as_float(r[i]));
+  }
+  const float moff = mx * sl2;
+  float sum = 0.f;
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t pk[16];
+    if (c0 < nk16) {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + c0, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float a = c0 + 2 * i < p.Nk ? exp2f(__uint_as_float(r[2 * i]) * sl2 - moff) : 0.f;
+        const float c = c0 + 2 * i + 1 < p.Nk ? exp2f(__uint_as_float(r[2 * i + 1]) * sl2 - moff) : 0.f;
+        sum += a + c;
+        pk[i] = pack_bf16x2(a, c);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    }
+    // the S reads of every row must be finished before P overwrites the Q|K tiles that MMA1 consumed: MMA1 has
+    // completed (bars[1]); P rows are private to this thread, so no further hazard
+    store_row32(sP, row, c0, pk);
+  }
+  fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+  tc_fence_before();
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    // O[128 x 64] = P V : A = P (K-major, 64-key panels), B = V (MN-major: row-major [key][dh] tile as is)
+    const uint32_t idesc = umma_idesc_bf16(128, DH, 0, 1);
+    const int ksteps = nk16 / 16;
+    for (int j = 0; j < ksteps; ++j) {
+      const uint32_t a_addr = smem_u32(sP) + (j >> 2) * TILE_BYTES + (j & 3) * 32;
+      const uint64_t da = umma_smem_desc_sw128(a_addr, 16, 1024);
+      const uint64_t db = umma_smem_desc_sw128(smem_u32(sV) + j * (16 * 128), TILE_BYTES, 1024);
+      tc_mma_f16_ss(tmem, da, db, idesc, j != 0 ? 1u : 0u);
+    }
+    tc_commit(&bars[2]);
+  }
+  __syncwarp();
+
+  // ---------------------------------------------------------------- epilogue
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int c0 = 0; c0 < DH; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(trow + c0, r);
+    tc_wait_ld();
+    if (row < p.Nq) {
+      bf16* dst = p.O + (int64_t(b) * p.Nq + row) * p.ldo + h * DH + c0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+        v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+        v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+        v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + 8 * j) = v;
+      }
+    }
+  }
+  if (p.lse != nullptr && row < p.Nq) p.lse[(int64_t(b) * p.H + h) * p.Nq + row] = mx * p.scale + logf(sum);
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+// =====================================================================================================================
+// backward
+// =====================================================================================================================
+struct AttnTcBwdParams {
+  int Nq, Nk, H;
+  float scale;
+  const float* lse;
+  const float* delta;
+  bf16 *dQ, *dK, *dV;
+  int64_t lddq, lddk, lddv;
+};
+
+// TMEM columns: S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
+__global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                          const __grid_constant__ CUtensorMap tmK,
+                                                          const __grid_constant__ CUtensorMap tmV,
+                                                          const __grid_constant__ CUtensorMap tmdO,
+                                                          const AttnTcBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + 1 * TILE_BYTES;
+  uint8_t* sV = smem + 2 * TILE_BYTES;
+  uint8_t* sdO = smem + 3 * TILE_BYTES;
+  uint8_t* sP = smem + 4 * TILE_BYTES;     // 32 KB: [q][key] bf16, two 64-key panels
+  uint8_t* sdS = smem + 6 * TILE_BYTES;    // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * TILE_BYTES);   // [0] loads, [1] S & dP ready, [2] grads ready
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3);
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk16 = (p.Nk + 15) & ~15;
+  const int nq16 = (p.Nq + 15) & ~15;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      tma_prefetch_desc(&tmdO);
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      mbar_init(&bars[2], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], 4 * TILE_BYTES);
+    tma_load_3d(sQ, &tmQ, &bars[0], h * DH, 0, b);
+    tma_load_3d(sK, &tmK, &bars[0], h * DH, 0, b);
+    tma_load_3d(sV, &tmV, &bars[0], h * DH, 0, b);
+    tma_load_3d(sdO, &tmdO, &bars[0], h * DH, 0, b);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, nk16, 0, 0);
+#pragma unroll
+    for (int j = 0; j < DH / 16; ++j) {   // S = Q K^T
+      tc_mma_f16_ss(tmem, umma_smem_desc_sw128(smem_u32(sQ) + j * 32, 16, 1024),
+                    umma_smem_desc_sw128(smem_u32(sK) + j * 32, 16, 1024), idesc, j != 0 ? 1u : 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < DH / 16; ++j) {   // dP = dO V^T
+      tc_mma_f16_ss(tmem + 128, umma_smem_desc_sw128(smem_u32(sdO) + j * 32, 16, 1024),
+                    umma_smem_desc_sw128(smem_u32(sV) + j * 32, 16, 1024), idesc, j != 0 ? 1u : 0u);
+    }
+    tc_commit(&bars[1]);
+  }
+  __syncwarp();
+
+  // ---------------------------------------------------------------- P and dS: thread = query row
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
+  const float sl2 = p.scale * LOG2E_F;
+  const bool row_ok = row < p.Nq;
+  const float lse2 = row_ok ? p.lse[(int64_t(b) * p.H + h) * p.Nq + row] * LOG2E_F : INFINITY;   // +inf -> P = 0
+  const float del = row_ok ? p.delta[(int64_t(b) * p.H + h) * p.Nq + row] : 0.f;
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t pp[16], ds[16];
+    if (c0 < nk16) {
+      uint32_t s[32], d[32];
+      tmem_ld_32x32(trow + c0, s);
+      tmem_ld_32x32(trow + 128 + c0, d);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = c0 + 2 * i < p.Nk ? exp2f(__uint_as_float(s[2 * i]) * sl2 - lse2) : 0.f;
+        const float p1 = c0 + 2 * i + 1 < p.Nk ? exp2f(__uint_as_float(s[2 * i + 1]) * sl2 - lse2) : 0.f;
+        pp[i] = pack_bf16x2(p0, p1);
+        ds[i] = pack_bf16x2(p0 * (__uint_as_float(d[2 * i]) - del), p1 * (__uint_as_float(d[2 * i + 1]) - del));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pp[i] = ds[i] = 0u;
+    }
+    store_row32(sP, row, c0, pp);
+    store_row32(sdS, row, c0, ds);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    // dV[key x dh] = P^T dO : A = P as MN-major (rows = keys; 64-key panels are TILE_BYTES apart), B = dO MN-major
+    // dK[key x dh] = dS^T Q : same with dS / Q.    K extent = queries (nq16), 16 query rows (2048 B) per UMMA step
+    const uint32_t idesc_t = umma_idesc_bf16(128, DH, 1, 1);
+    for (int j = 0; j < nq16 / 16; ++j) {
+      const uint64_t db_do = umma_smem_desc_sw128(smem_u32(sdO) + j * 2048, TILE_BYTES, 1024);
+      const uint64_t db_q = umma_smem_desc_sw128(smem_u32(sQ) + j * 2048, TILE_BYTES, 1024);
+      tc_mma_f16_ss(tmem + 256, umma_smem_desc_sw128(smem_u32(sP) + j * 2048, TILE_BYTES, 1024), db_do, idesc_t,
+                    j != 0 ? 1u : 0u);
+      tc_mma_f16_ss(tmem + 320, umma_smem_desc_sw128(smem_u32(sdS) + j * 2048, TILE_BYTES, 1024), db_q, idesc_t,
+                    j != 0 ? 1u : 0u);
+    }
+    // dQ[q x dh] = dS K : A = dS K-major, B = K MN-major; K extent = keys
+    const uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);
+    for (int j = 0; j < nk16 / 16; ++j) {
+      const uint32_t a_addr = smem_u32(sdS) + (j >> 2) * TILE_BYTES + (j & 3) * 32;
+      tc_mma_f16_ss(tmem + 384, umma_smem_desc_sw128(a_addr, 16, 1024),
+                    umma_smem_desc_sw128(smem_u32(sK) + j * 2048, TILE_BYTES, 1024), idesc_q, j != 0 ? 1u : 0u);
+    }
+    tc_commit(&bars[2]);
+  }
+  __syncwarp();
+
+  // ---------------------------------------------------------------- epilogue: rows = keys for dV/dK, queries for dQ
+  mbar_wait(&bars[2], 0);
+  tc_fence_after();
+#pragma unroll
+  for (int which = 0; which < 3; ++which) {
+    const int limit = which == 2 ? p.Nq : p.Nk;
+    bf16* base = which == 0 ? p.dV : (which == 1 ? p.dK : p.dQ);
+    const int64_t ld = which == 0 ? p.lddv : (which == 1 ? p.lddk : p.lddq);
+    const float mul = which == 0 ? 1.0f : p.scale;
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + 256 + which * 64 + c0, r);
+      tc_wait_ld();
+      if (row < limit) {
+        bf16* dst = base + (int64_t(b) * limit + row) * ld + h * DH + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]) * mul, __uint_as_float(r[8 * j + 1]) * mul);
+          v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * mul, __uint_as_float(r[8 * j + 3]) * mul);
+          v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * mul, __uint_as_float(r[8 * j + 5]) * mul);
+          v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * mul, __uint_as_float(r[8 * j + 7]) * mul);
+          *reinterpret_cast<uint4*>(dst + 8 * j) = v;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int make_maps(CUtensorMap* out, const void* ptr, int64_t ld, int B, int N, int H) {
+  // [B][N][H*64] view with row pitch ld; box = 64 columns x 128 rows x 1 sample; rows past N are zero-filled
+  return make_tmap_3d_bf16(out, ptr, (uint64_t)H * DH, (uint64_t)N, (uint64_t)B, (uint64_t)ld, (uint64_t)N * ld, DH, TQ, 1);
+}
+
+}  // namespace
+
+bool attn_tc_supported(int Nq, int Nk, int head_dim) { return head_dim == DH && Nq <= TQ && Nk <= TQ && Nq >= 1 && Nk >= 1; }
+
+int attn_tc_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                    float* lse, int B, int H, int Nq, int Nk, float scale, cudaStream_t st) {
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_maps(&tq, q, ldq, B, Nq, H)) || (rc = make_maps(&tk, k, ldk, B, Nk, H)) ||
+      (rc = make_maps(&tv, v, ldv, B, Nk, H)))
+    return rc;
+  AttnTcParams p;
+  p.Nq = Nq; p.Nk = Nk; p.H = H; p.scale = scale;
+  p.O = reinterpret_cast<bf16*>(o);
+  p.ldo = ldo;
+  p.lse = lse;
+  constexpr int SMEM = 3 * TILE_BYTES + 64 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MMAE_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  attn_tc_fwd_kernel<<<dim3(H, B), 128, SMEM, st>>>(tq, tk, tv, p);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+int attn_tc_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+                     int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                     void* dv, int64_t lddv, int B, int H, int Nq, int Nk, float scale, cudaStream_t st) {
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = make_maps(&tq, q, ldq, B, Nq, H)) || (rc = make_maps(&tk, k, ldk, B, Nk, H)) ||
+      (rc = make_maps(&tv, v, ldv, B, Nk, H)) || (rc = make_maps(&tdo, d_o, lddo, B, Nq, H)))
+    return rc;
+  AttnTcBwdParams p;
+  p.Nq = Nq; p.Nk = Nk; p.H = H; p.scale = scale;
+  p.lse = lse; p.delta = delta;
+  p.dQ = reinterpret_cast<bf16*>(dq); p.dK = reinterpret_cast<bf16*>(dk); p.dV = reinterpret_cast<bf16*>(dv);
+  p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
+  constexpr int SMEM = 8 * TILE_BYTES + 64 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    MMAE_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  attn_tc_bwd_kernel<<<dim3(H, B), 128, SMEM, st>>>(tq, tk, tv, tdo, p);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+}  // namespace mmae

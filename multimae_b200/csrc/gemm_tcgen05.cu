@@ -9,6 +9,9 @@
 // Replaces the cuBLAS/cuDNN calls behind nn.Linear / nn.Conv2d(k=s=P) on the reference path
 // (multimae/multimae_utils.py:149-153,172,180,203-212; multimae/input_adapters.py:110,232;
 //  multimae/output_adapters.py:258,274) and their autograd dgrad/wgrad.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/multimae_b200.h"
 
@@ -44,6 +47,71 @@ struct GemmSmem {
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
+}
+
+
+// Fused epilogue for 32 consecutive accumulator columns of one output row (held by one thread).
+__device__ __forceinline__ void epilogue_chunk32(const uint32_t (&r)[32], int row, bool row_ok, int nb, const GemmParams& p,
+                                                 bool first_split, bool atomic_out) {
+  const mmae_gemm_epilogue& ep = p.ep;
+  const float* bias = first_split ? ep.bias : nullptr;
+  const float* resid = first_split ? ep.residual : nullptr;
+  const bf16* zptr = reinterpret_cast<const bf16*>(ep.dgelu_z);
+  bf16* preact = reinterpret_cast<bf16*>(ep.preact_bf16);
+  bf16* out_b = reinterpret_cast<bf16*>(ep.out_bf16);
+  float* out_f = ep.out_f32;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int n = nb + g * 8;
+    if (!row_ok || n >= p.N) continue;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * ep.alpha;
+    if (bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (preact) {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(preact + int64_t(row) * ep.ld_preact + n) = o;
+    }
+    if (ep.act == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    }
+    if (zptr) {
+      const uint4 z = __ldg(reinterpret_cast<const uint4*>(zptr + int64_t(row) * ep.ld_dgelu_z + n));
+      const float2 z0 = unpack_bf16x2(z.x), z1 = unpack_bf16x2(z.y), z2 = unpack_bf16x2(z.z), z3 = unpack_bf16x2(z.w);
+      v[0] *= dgelu_erf(z0.x); v[1] *= dgelu_erf(z0.y); v[2] *= dgelu_erf(z1.x); v[3] *= dgelu_erf(z1.y);
+      v[4] *= dgelu_erf(z2.x); v[5] *= dgelu_erf(z2.y); v[6] *= dgelu_erf(z3.x); v[7] *= dgelu_erf(z3.y);
+    }
+    if (resid) {
+      const float4 r0 = __ldg(reinterpret_cast<const float4*>(resid + int64_t(row) * ep.ld_residual + n));
+      const float4 r1 = __ldg(reinterpret_cast<const float4*>(resid + int64_t(row) * ep.ld_residual + n + 4));
+      v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+      v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    }
+    if (out_f) {
+      float* dst = out_f + int64_t(row) * ep.ld_out_f32 + n;
+      if (atomic_out) {
+        red_add_v4(dst, v[0], v[1], v[2], v[3]);
+        red_add_v4(dst + 4, v[4], v[5], v[6], v[7]);
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+    if (out_b) {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(out_b + int64_t(row) * ep.ld_out_bf16 + n) = o;
+    }
+  }
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
@@ -152,15 +220,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < p.M;
-    const mmae_gemm_epilogue& ep = p.ep;
     const bool first_split = blockIdx.z == 0;
-    const bool atomic_out = ep.accumulate != 0 || gridDim.z > 1;
-    const float* bias = first_split ? ep.bias : nullptr;
-    const float* resid = first_split ? ep.residual : nullptr;
-    const bf16* zptr = reinterpret_cast<const bf16*>(ep.dgelu_z);
-    bf16* preact = reinterpret_cast<bf16*>(ep.preact_bf16);
-    bf16* out_b = reinterpret_cast<bf16*>(ep.out_bf16);
-    float* out_f = ep.out_f32;
+    const bool atomic_out = p.ep.accumulate != 0 || gridDim.z > 1;
 
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -169,59 +230,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
       tc_wait_ld();
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int n = nb + g * 8;
-        if (!row_ok || n >= p.N) continue;
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * ep.alpha;
-        if (bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        if (preact) {
-          uint4 o;
-          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(preact + int64_t(row) * ep.ld_preact + n) = o;
-        }
-        if (ep.act == 1) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
-        }
-        if (zptr) {
-          const uint4 z = __ldg(reinterpret_cast<const uint4*>(zptr + int64_t(row) * ep.ld_dgelu_z + n));
-          const float2 z0 = unpack_bf16x2(z.x), z1 = unpack_bf16x2(z.y), z2 = unpack_bf16x2(z.z),
-                       z3 = unpack_bf16x2(z.w);
-          v[0] *= dgelu_erf(z0.x); v[1] *= dgelu_erf(z0.y); v[2] *= dgelu_erf(z1.x); v[3] *= dgelu_erf(z1.y);
-          v[4] *= dgelu_erf(z2.x); v[5] *= dgelu_erf(z2.y); v[6] *= dgelu_erf(z3.x); v[7] *= dgelu_erf(z3.y);
-        }
-        if (resid) {
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(resid + int64_t(row) * ep.ld_residual + n));
-          const float4 r1 = __ldg(reinterpret_cast<const float4*>(resid + int64_t(row) * ep.ld_residual + n + 4));
-          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-          v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-        }
-        if (out_f) {
-          float* dst = out_f + int64_t(row) * ep.ld_out_f32 + n;
-          if (atomic_out) {
-            red_add_v4(dst, v[0], v[1], v[2], v[3]);
-            red_add_v4(dst + 4, v[4], v[5], v[6], v[7]);
-          } else {
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-          }
-        }
-        if (out_b) {
-          uint4 o;
-          o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-          o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(out_b + int64_t(row) * ep.ld_out_bf16 + n) = o;
-        }
-      }
+      epilogue_chunk32(r, row, row_ok, nb, p, first_split, atomic_out);
     }
   }
 
@@ -230,9 +239,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int split_k,
-                cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN>
+int launch_gemm1(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int split_k,
+                 cudaStream_t stream) {
+  constexpr int STAGES = 3;
   using L = GemmSmem<BN, STAGES>;
   auto kern = gemm_bf16_kernel<BN, STAGES, A_MN, B_MN>;
   static bool configured = false;
@@ -249,10 +259,231 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
   return MMAE_OK;
 }
 
+
+// =====================================================================================================================
+// v2: persistent CTAs (one per SM), double-buffered TMEM accumulators: the epilogue of work item i overlaps the
+// TMA/MMA mainloop of item i+1.  BN = 256 halves the shared-memory operand bandwidth per MMA relative to BN = 128
+// (a 128x128x16 UMMA consumes 128 B/clk of smem reads, the SM's limit; 128x256x16 needs 96 B/clk).
+//   warp 0 : TMA producer      warp 1 : TMEM alloc + MMA issuer      warps 2..2+EPI-1 : epilogue
+// Work item = (m tile, n tile, k split); items are dealt round-robin: item = blockIdx.x + i * gridDim.x, n fastest.
+// =====================================================================================================================
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int EPI_WARPS = BN == 256 ? 8 : 4;
+  static constexpr int THREADS = 64 + EPI_WARPS * 32;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256
+};
+
+struct Gemm2Sched {
+  int tiles_m, tiles_n, splits, total;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
+    gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                const GemmParams p, const Gemm2Sched sc) {
+  using C = Gemm2Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&tmem_full_bar[b], 1);
+        mbar_init(&tmem_empty_bar[b], C::EPI_WARPS);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto decode = [&](int item, int& m0, int& n0, int& kb_begin, int& nkb, int& z) {
+    z = item % sc.splits;
+    const int tile = item / sc.splits;
+    n0 = (tile % sc.tiles_n) * BN;
+    m0 = (tile / sc.tiles_n) * BM;
+    kb_begin = z * p.kb_per_split;
+    nkb = min(p.kb_per_split, p.num_kb - kb_begin);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < sc.total; item += gridDim.x) {
+        int m0, n0, kb_begin, nkb, z;
+        decode(item, m0, n0, kb_begin, nkb, z);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* sA = smem + stage * C::STAGE_BYTES;
+          uint8_t* sB = sA + C::A_BYTES;
+          const int k0 = (kb_begin + kb) * BK;
+          if constexpr (!A_MN) {
+            tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * (64 * BK * 2), &tmA, &full_bar[stage], m0 + c * 64, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + c * (64 * BK * 2), &tmB, &full_bar[stage], n0 + c * 64, k0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < sc.total; item += gridDim.x, ++it) {
+        int m0, n0, kb_begin, nkb, z;
+        decode(item, m0, n0, kb_begin, nkb, z);
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[buf], acc_phase ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(buf * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / UMMA_K; ++j) {
+            const uint64_t da = A_MN ? umma_smem_desc_sw128(a_addr + j * (UMMA_K * 128), 64 * BK * 2, 1024)
+                                     : umma_smem_desc_sw128(a_addr + j * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc_sw128(b_addr + j * (UMMA_K * 128), 64 * BK * 2, 1024)
+                                     : umma_smem_desc_sw128(b_addr + j * (UMMA_K * 2), 16, 1024);
+            tc_mma_f16_ss(tmem_d, da, db, idesc, (kb | j) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int e = warp - 2;                       // 0 .. EPI_WARPS-1
+    const int q = warp & 3;                       // TMEM lane quarter accessible to this warp
+    constexpr int COLS_PER_WARP = BN / (C::EPI_WARPS / 4);   // 128
+    const int col0 = (e >> 2) * COLS_PER_WARP;
+    int it = 0;
+    for (int item = blockIdx.x; item < sc.total; item += gridDim.x, ++it) {
+      int m0, n0, kb_begin, nkb, z;
+      decode(item, m0, n0, kb_begin, nkb, z);
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[buf], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool first_split = z == 0;
+      const bool atomic_out = p.ep.accumulate != 0 || sc.splits > 1;
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+        const int nb = n0 + col0 + c * 32;
+        if (nb >= p.N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN + col0 + c * 32), r);
+        tc_wait_ld();
+        epilogue_chunk32(r, row, row_ok, nb, p, first_split, atomic_out);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int split_k, cudaStream_t stream) {
+  using C = Gemm2Cfg<BN>;
+  auto kern = gemm_bf16_persistent_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    MMAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    configured = true;
+  }
+  Gemm2Sched sc;
+  sc.tiles_m = ceil_div(p.M, BM);
+  sc.tiles_n = ceil_div(p.N, BN);
+  sc.splits = split_k;
+  sc.total = sc.tiles_m * sc.tiles_n * split_k;
+  const int grid = std::min(sc.total, sm_count());
+  const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K);
+  kern<<<grid, C::THREADS, C::TOTAL, stream>>>(tmA, tmB, p, sc);
+  if (prof) gemm_profile_end(stream);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
 }  // namespace
 }  // namespace mmae
 
 using namespace mmae;
+
+static int g_gemm_variant = []() {
+  const char* e = getenv("MMAE_GEMM_VARIANT");
+  return e ? atoi(e) : -1;
+}();
+
+extern "C" int mmae_gemm_set_variant(int variant) {
+  g_gemm_variant = variant;
+  return MMAE_OK;
+}
 
 extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
                               int b_mn_major, int M, int N, int K, int split_k, const mmae_gemm_epilogue* ep,
@@ -281,6 +512,12 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
              MMAE_ERR_ARG, "mmae_gemm_bf16: epilogue tensors need 16-byte alignment and ld %% 8 == 0");
 #undef MMAE_LD_OK
 
+  // kernel variant: 0 = v1 (one tile per CTA, BN=128), 1 = persistent BN=128, 2 = persistent BN=256.
+  // MMAE_GEMM_VARIANT overrides the heuristic (for A/B measurements).
+  int variant = g_gemm_variant;
+  if (variant < 0) variant = (N >= 256) ? 2 : 1;
+  const int BNsel = variant == 2 ? 256 : 128;
+
   CUtensorMap tmA, tmB;
   int rc;
   if (!a_mn_major) {
@@ -290,9 +527,8 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
     rc = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BK);
   }
   if (rc) return rc;
-  constexpr int BN = 128;
   if (!b_mn_major) {
-    rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BN);
+    rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BNsel);
   } else {
     rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK);
   }
@@ -304,9 +540,15 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   p.kb_per_split = kb_per_split;
   p.ep = *ep;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  constexpr int STAGES = 3;
-  if (!a_mn_major && !b_mn_major) return launch_gemm<BN, STAGES, false, false>(tmA, tmB, p, split_k, st);
-  if (!a_mn_major && b_mn_major) return launch_gemm<BN, STAGES, false, true>(tmA, tmB, p, split_k, st);
-  if (a_mn_major && !b_mn_major) return launch_gemm<BN, STAGES, true, false>(tmA, tmB, p, split_k, st);
-  return launch_gemm<BN, STAGES, true, true>(tmA, tmB, p, split_k, st);
+#define MMAE_DISPATCH(FN, ...)                                                                   \
+  do {                                                                                           \
+    if (!a_mn_major && !b_mn_major) return FN<__VA_ARGS__, false, false>(tmA, tmB, p, split_k, st); \
+    if (!a_mn_major && b_mn_major) return FN<__VA_ARGS__, false, true>(tmA, tmB, p, split_k, st);   \
+    if (a_mn_major && !b_mn_major) return FN<__VA_ARGS__, true, false>(tmA, tmB, p, split_k, st);   \
+    return FN<__VA_ARGS__, true, true>(tmA, tmB, p, split_k, st);                                  \
+  } while (0)
+  if (variant == 2) MMAE_DISPATCH(launch_gemm2, 256);
+  if (variant == 1) MMAE_DISPATCH(launch_gemm2, 128);
+  MMAE_DISPATCH(launch_gemm1, 128);
+#undef MMAE_DISPATCH
 }

@@ -46,7 +46,12 @@ def attention_bwd(q,k,v,o,do,lse,dq,dk,dv,B,H,Nq,Nk,dh,scale):
     (torch.softmax(s,-1)@vf).transpose(1,2).reshape(B*Nq,H*dh).backward(do.float())
     dq.copy_(qf.grad.transpose(1,2).reshape(B*Nq,-1)); dk.copy_(kf.grad.transpose(1,2).reshape(B*Nk,-1)); dv.copy_(vf.grad.transpose(1,2).reshape(B*Nk,-1))
 m.attention_bwd=attention_bwd
-pkg = types.ModuleType("multimae_b200"); pkg.kernels = m; pkg.__path__=[]
+class _FakeLib:
+    def mmae_gemm_set_variant(self, v): return 0
+    def mmae_attention_set_tc(self, v): return 0
+libmod = types.ModuleType("multimae_b200._lib"); libmod.lib = lambda: _FakeLib()
+pkg = types.ModuleType("multimae_b200"); pkg.kernels = m; pkg._lib = libmod; pkg.__path__=[]
+sys.modules["multimae_b200._lib"]=libmod
 sys.modules["multimae_b200"]=pkg; sys.modules["multimae_b200.kernels"]=m
 _dev = torch.device
 torch.device = lambda *a, **k: _dev("cpu")
@@ -57,5 +62,5 @@ class _E:
 torch.cuda.Event=_E; torch.cuda.synchronize=lambda: None
 src=open("scripts/gpu_check_gemm.py").read()
 # shrink timing shapes for CPU
-src=src.replace("12672","128").replace("25088","128").replace("B_, H_, N_, dh_ = 128, 12, 99, 64","B_, H_, N_, dh_ = 2, 2, 9, 64").replace("iters=20","iters=1")
+src=src.replace("12672","128").replace("25088","128").replace("12544","128").replace("(2560, 2304, 768)","(256, 264, 128)").replace("B_, H_, N_, dh_ = 128, 12, 99, 64","B_, H_, N_, dh_ = 2, 2, 9, 64").replace("iters=20","iters=1")
 exec(compile(src,"gpu_check_gemm.py","exec"))

@@ -39,25 +39,31 @@ def gemm_case(M, N, K, a_mn, b_mn, split_k=1):
     out = torch.zeros(M, N, device=dev, dtype=torch.float32)
     KN.gemm(Ain, Bin, a_mn=a_mn, b_mn=b_mn, out_f32=out, split_k=split_k)
     torch.cuda.synchronize()
-    report("gemm M=%d N=%d K=%d a_mn=%d b_mn=%d split=%d" % (M, N, K, a_mn, b_mn, split_k), relerr(out, ref), 1e-5)
+    report("gemm M=%d N=%d K=%d a_mn=%d b_mn=%d split=%d" % (M, N, K, a_mn, b_mn, split_k), relerr(out, ref), 3e-5)
 
 
-# ---- correctness: the four operand-major combinations, small and ragged shapes
-for (M, N, K_) in [(128, 128, 64), (128, 128, 256), (256, 384, 768), (200, 136, 200), (396, 2128, 256)]:
-    for a_mn in (False, True):
-        for b_mn in (False, True):
-            if a_mn and M % 8:
-                continue
-            try:
-                gemm_case(M, N, K_, a_mn, b_mn)
-            except Exception as e:  # noqa: BLE001
-                fails += 1
-                print("gemm M=%d N=%d K=%d a_mn=%d b_mn=%d EXC %s" % (M, N, K_, a_mn, b_mn, e), flush=True)
+from multimae_b200 import _lib as LIB  # noqa: E402
 
-# split-K (wgrad shape): dW[768,768] = dY^T X with contraction 12672
-for split in (1, 4):
-    gemm_case(768, 768, 12672, True, True, split_k=split)
-gemm_case(768, 3072, 1280, True, True, split_k=3)
+# ---- correctness: the four operand-major combinations, small and ragged shapes, for every kernel variant
+for variant in (0, 1, 2):
+    LIB.lib().mmae_gemm_set_variant(variant)
+    print("== gemm variant", variant, flush=True)
+    for (M, N, K_) in [(128, 128, 64), (128, 128, 256), (256, 384, 768), (200, 136, 200), (396, 2128, 256),
+                       (1000, 768, 512), (2560, 2304, 768)]:
+        for a_mn in (False, True):
+            for b_mn in (False, True):
+                if a_mn and M % 8:
+                    continue
+                try:
+                    gemm_case(M, N, K_, a_mn, b_mn)
+                except Exception as e:  # noqa: BLE001
+                    fails += 1
+                    print("gemm M=%d N=%d K=%d a_mn=%d b_mn=%d EXC %s" % (M, N, K_, a_mn, b_mn, e), flush=True)
+    # split-K (wgrad shape): dW[768,768] = dY^T X with contraction 12672
+    for split in (1, 4):
+        gemm_case(768, 768, 12672, True, True, split_k=split)
+    gemm_case(768, 3072, 1280, True, True, split_k=3)
+LIB.lib().mmae_gemm_set_variant(-1)
 
 # ---- fused epilogues
 M, N, K_ = 384, 512, 256
@@ -172,13 +178,17 @@ def attn_case(B, H, Nq, Nk, dh, self_attn):
     report("attn bwd dv " + tag, relerr(dv, vf.grad.transpose(1, 2).reshape(B * Nk, D)), 1e-2)
 
 
-for args in [(3, 12, 99, 99, 64, True), (2, 8, 196, 99, 32, False), (2, 8, 196, 196, 32, True),
-             (1, 2, 393, 393, 64, True), (1, 2, 130, 70, 32, False), (2, 1, 17, 5, 64, False)]:
-    try:
-        attn_case(*args)
-    except Exception as e:  # noqa: BLE001
-        fails += 1
-        print("attn case %s EXC %s" % (str(args), e), flush=True)
+for tc in (0, 1):
+    LIB.lib().mmae_attention_set_tc(tc)
+    print("== attention tcgen05 path", tc, flush=True)
+    for args in [(3, 12, 99, 99, 64, True), (2, 8, 196, 99, 32, False), (2, 8, 196, 196, 32, True),
+                 (1, 2, 393, 393, 64, True), (1, 2, 130, 70, 32, False), (2, 1, 17, 5, 64, False),
+                 (2, 16, 99, 99, 64, True), (2, 3, 128, 128, 64, True), (1, 2, 100, 33, 64, False)]:
+        try:
+            attn_case(*args)
+        except Exception as e:  # noqa: BLE001
+            fails += 1
+            print("attn case %s EXC %s" % (str(args), e), flush=True)
 
 # ---- quick timing vs cuBLAS on the encoder shapes (device events, inputs > L2 not enforced here: indicative)
 def time_it(fn, iters=20):
@@ -197,21 +207,28 @@ def time_it(fn, iters=20):
 for (M, N, K_, a_mn, b_mn, split) in [(12672, 2304, 768, 0, 0, 1), (12672, 768, 768, 0, 0, 1),
                                       (12672, 3072, 768, 0, 0, 1), (12672, 768, 3072, 0, 0, 1),
                                       (12672, 768, 3072, 0, 1, 1), (3072, 768, 12672, 1, 1, 2),
-                                      (768, 768, 12672, 1, 1, 8), (25088, 1024, 256, 0, 0, 1)]:
+                                      (768, 768, 12672, 1, 1, 8), (25088, 1024, 256, 0, 0, 1), (25088, 256, 256, 0, 0, 1),
+                                      (25088, 256, 1024, 0, 0, 1), (25088, 768, 256, 0, 0, 1), (256, 256, 25088, 1, 1, 16),
+                                      (12544, 768, 2048, 0, 0, 1)]:
     A = rand_bf16(M, K_)
     B = rand_bf16(N, K_)
     Ain = A.t().contiguous() if a_mn else A
     Bin = B.t().contiguous() if b_mn else B
-    if split > 1:
-        out = torch.zeros(M, N, device=dev)
-        ms = time_it(lambda: KN.gemm(Ain, Bin, a_mn=bool(a_mn), b_mn=bool(b_mn), out_f32=out, split_k=split))
-    else:
-        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-        ms = time_it(lambda: KN.gemm(Ain, Bin, a_mn=bool(a_mn), b_mn=bool(b_mn), out_bf16=out))
-    ms_ref = time_it(lambda: torch.matmul(A, B.t()))
     fl = 2.0 * M * N * K_
-    print("time M=%d N=%d K=%d a_mn=%d b_mn=%d split=%d : ours %.3f ms (%.0f TF/s)  cublas %.3f ms (%.0f TF/s)" %
-          (M, N, K_, a_mn, b_mn, split, ms, fl / ms / 1e9, ms_ref, fl / ms_ref / 1e9), flush=True)
+    res = []
+    for variant in (0, 1, 2):
+        LIB.lib().mmae_gemm_set_variant(variant)
+        if split > 1:
+            out = torch.zeros(M, N, device=dev)
+            ms = time_it(lambda: KN.gemm(Ain, Bin, a_mn=bool(a_mn), b_mn=bool(b_mn), out_f32=out, split_k=split))
+        else:
+            out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            ms = time_it(lambda: KN.gemm(Ain, Bin, a_mn=bool(a_mn), b_mn=bool(b_mn), out_bf16=out))
+        res.append("v%d %.3f ms (%.0f TF/s)" % (variant, ms, fl / ms / 1e9))
+    LIB.lib().mmae_gemm_set_variant(-1)
+    ms_ref = time_it(lambda: torch.matmul(A, B.t()))
+    print("time M=%d N=%d K=%d a_mn=%d b_mn=%d split=%d : %s | cublas %.3f ms (%.0f TF/s)" %
+          (M, N, K_, a_mn, b_mn, split, "  ".join(res), ms_ref, fl / ms_ref / 1e9), flush=True)
 
 
 # attention timing at the encoder shape
@@ -220,14 +237,34 @@ qkv = rand_bf16(B_ * N_, 3 * H_ * dh_)
 D_ = H_ * dh_
 q, k, v = qkv[:, :D_], qkv[:, D_:2 * D_], qkv[:, 2 * D_:]
 o = torch.empty(B_ * N_, D_, device=dev, dtype=torch.bfloat16)
-ms = time_it(lambda: KN.attention_fwd(q, k, v, B_, H_, N_, N_, dh_, 0.125, out=o))
 fl = 4.0 * B_ * H_ * N_ * N_ * dh_
-print("time attn fwd enc: %.3f ms (%.1f TF/s useful)" % (ms, fl / ms / 1e9), flush=True)
-o, lse = KN.attention_fwd(q, k, v, B_, H_, N_, N_, dh_, 0.125)
 do = rand_bf16(B_ * N_, D_)
 dqkv = torch.empty_like(qkv)
-ms = time_it(lambda: KN.attention_bwd(q, k, v, o, do, lse, dqkv[:, :D_], dqkv[:, D_:2 * D_], dqkv[:, 2 * D_:], B_, H_, N_, N_, dh_, 0.125))
-print("time attn bwd enc: %.3f ms (%.1f TF/s useful)" % (ms, 2.5 * fl / ms / 1e9), flush=True)
+for tc in (0, 1):
+    LIB.lib().mmae_attention_set_tc(tc)
+    ms = time_it(lambda: KN.attention_fwd(q, k, v, B_, H_, N_, N_, dh_, 0.125, out=o))
+    print("time attn fwd enc (tc=%d): %.3f ms (%.1f TF/s useful)" % (tc, ms, fl / ms / 1e9), flush=True)
+    o2, lse = KN.attention_fwd(q, k, v, B_, H_, N_, N_, dh_, 0.125)
+    ms = time_it(lambda: KN.attention_bwd(q, k, v, o2, do, lse, dqkv[:, :D_], dqkv[:, D_:2 * D_], dqkv[:, 2 * D_:], B_, H_, N_, N_, dh_, 0.125))
+    print("time attn bwd enc (tc=%d): %.3f ms (%.1f TF/s useful)" % (tc, ms, 2.5 * fl / ms / 1e9), flush=True)
+# decoder attention shapes (warp-MMA kernels)
+for (Nq_, Nk_, self_) in [(196, 196, True), (196, 99, False)]:
+    Dd_, Hd_ = 256, 8
+    if self_:
+        qkv_d = rand_bf16(B_ * Nq_, 3 * Dd_)
+        qd, kd, vd = qkv_d[:, :Dd_], qkv_d[:, Dd_:2 * Dd_], qkv_d[:, 2 * Dd_:]
+    else:
+        qd = rand_bf16(B_ * Nq_, Dd_)
+        kvd = rand_bf16(B_ * Nk_, 2 * Dd_)
+        kd, vd = kvd[:, :Dd_], kvd[:, Dd_:]
+    od, lsed = KN.attention_fwd(qd, kd, vd, B_, Hd_, Nq_, Nk_, 32, 32 ** -0.5)
+    ms = time_it(lambda: KN.attention_fwd(qd, kd, vd, B_, Hd_, Nq_, Nk_, 32, 32 ** -0.5, out=od))
+    fld = 4.0 * B_ * Hd_ * Nq_ * Nk_ * 32
+    dod = rand_bf16(B_ * Nq_, Dd_)
+    dq_, dk_, dv_ = torch.empty_like(qd), torch.empty_like(kd.contiguous()), torch.empty_like(vd.contiguous())
+    msb = time_it(lambda: KN.attention_bwd(qd, kd, vd, od, dod, lsed, dq_, dk_, dv_, B_, Hd_, Nq_, Nk_, 32, 32 ** -0.5))
+    print("time attn dec %dx%d: fwd %.3f ms (%.1f TF/s)  bwd %.3f ms (%.1f TF/s)" %
+          (Nq_, Nk_, ms, fld / ms / 1e9, msb, 2.5 * fld / msb / 1e9), flush=True)
 x = torch.randn(12672, 768, device=dev)
 gam = torch.ones(768, device=dev)
 bet = torch.zeros(768, device=dev)

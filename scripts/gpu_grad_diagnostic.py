@@ -18,7 +18,9 @@ model = _build_model(c)
 formula_fill_(list(model.named_parameters()))
 model = model.to(dev).train()
 triple = ({k: v.to(dev) for k, v in fx["task_masks"].items()}, fx["ids_keep"].to(dev), fx["ids_restore"].to(dev))
+print("running cuda step", flush=True)
 preds, masks, losses = _run_cuda_step(model, fx["inputs"], triple, dev)
+print("cuda step done", flush=True)
 
 
 def oracle_grads(device, autocast):
@@ -37,7 +39,9 @@ def oracle_grads(device, autocast):
 
 
 ref, ref_preds = oracle_grads(torch.device("cpu"), False)
+print("cpu oracle done", flush=True)
 amp, amp_preds = oracle_grads(dev, True)
+print("gpu amp oracle done", flush=True)
 named = dict(model.named_parameters())
 rows = []
 for k, g in ref.items():

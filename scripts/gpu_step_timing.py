@@ -16,10 +16,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--tiny", action="store_true")
+ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--variant", type=int, default=-1)
 a = ap.parse_args()
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
+from multimae_b200 import _lib as _L  # noqa: E402
+_L.lib().mmae_gemm_set_variant(a.variant)
 if a.tiny:
     model = _build(("rgb", "depth", "semseg"), 128, 2, 2, 128, 1, 4, 64)
     size, T = 64, 12
@@ -57,7 +61,7 @@ def step(timed=False):
     return loss, marks
 
 
-for _ in range(3):
+for _ in range(a.warmup):
     loss, _m = step()
 torch.cuda.synchronize()
 print("warm loss", float(loss))

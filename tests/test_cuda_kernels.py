@@ -1,0 +1,164 @@
+"""GPU: every primitive of the C ABI against a plain PyTorch fp32 computation of the same op on the same inputs.
+
+Tolerances: fp32-accumulating GEMM on bf16 inputs vs fp32 matmul of the same bf16 values: 3e-5 relative L2 (accumulation
+order only); outputs rounded to bf16: 4e-3; attention (bf16 P / dS operands): 1e-2; fp32 element-wise kernels: 1e-5."""
+import pytest
+import torch
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    torch.manual_seed(0)
+    return torch.device("cuda:0")
+
+
+def _bf16(dev, *shape, scale=0.5):
+    return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16)
+
+
+@pytest.fixture()
+def KN():
+    from multimae_b200 import _lib as L
+    from multimae_b200 import kernels
+    yield kernels
+    L.lib().mmae_gemm_set_variant(-1)
+    L.lib().mmae_attention_set_tc(1)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 768), (200, 136, 200), (396, 2128, 256), (1000, 768, 512),
+                                   (2560, 2304, 768)])
+def test_gemm_all_operand_majors(dev, KN, variant, shape):
+    from multimae_b200 import _lib as L
+    L.lib().mmae_gemm_set_variant(variant)
+    M, N, K = shape
+    A, B = _bf16(dev, M, K), _bf16(dev, N, K)
+    ref = A.float() @ B.float().t()
+    for a_mn in (False, True):
+        for b_mn in (False, True):
+            if a_mn and M % 8:
+                continue
+            out = torch.zeros(M, N, device=dev)
+            KN.gemm(A.t().contiguous() if a_mn else A, B.t().contiguous() if b_mn else B, a_mn=a_mn, b_mn=b_mn, out_f32=out)
+            assert rel_l2(out, ref) < 3e-5, (variant, shape, a_mn, b_mn, rel_l2(out, ref))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_gemm_split_k_wgrad_shapes(dev, KN, variant):
+    from multimae_b200 import _lib as L
+    L.lib().mmae_gemm_set_variant(variant)
+    for (M, N, K, split) in [(768, 768, 12672, 1), (768, 768, 12672, 4), (768, 3072, 1280, 3), (256, 256, 25088, 16)]:
+        A, B = _bf16(dev, M, K), _bf16(dev, N, K)
+        out = torch.zeros(M, N, device=dev)
+        KN.gemm(A.t().contiguous(), B.t().contiguous(), a_mn=True, b_mn=True, out_f32=out, split_k=split)
+        assert rel_l2(out, A.float() @ B.float().t()) < 3e-5
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_gemm_fused_epilogues(dev, KN, variant):
+    from multimae_b200 import _lib as L
+    L.lib().mmae_gemm_set_variant(variant)
+    M, N, K = 384, 512, 256
+    A, B = _bf16(dev, M, K), _bf16(dev, N, K)
+    bias, resid = torch.randn(N, device=dev), torch.randn(M, N, device=dev)
+    acc = A.float() @ B.float().t()
+    out = torch.empty(M, N, device=dev)
+    KN.gemm(A, B, bias=bias, out_f32=out)
+    assert rel_l2(out, acc + bias) < 3e-5
+    outb = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    pre = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    KN.gemm(A, B, bias=bias, act=1, preact=pre, out_bf16=outb)
+    assert rel_l2(outb, torch.nn.functional.gelu(acc + bias)) < 4e-3 and rel_l2(pre, acc + bias) < 4e-3
+    KN.gemm(A, B, bias=bias, residual=resid, out_f32=out)
+    assert rel_l2(out, acc + bias + resid) < 3e-5
+    z = torch.randn(M, N, device=dev).to(torch.bfloat16)
+    zf = z.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).sum().backward()
+    KN.gemm(A, B, dgelu_z=z, out_bf16=outb)
+    assert rel_l2(outb, acc * zf.grad) < 4e-3
+    out = torch.ones(M, N, device=dev)
+    KN.gemm(A, B, out_f32=out, accumulate=True, alpha=0.5)
+    assert rel_l2(out, 1 + 0.5 * acc) < 3e-5
+
+
+def test_gemm_rejects_bad_arguments(dev, KN):
+    from multimae_b200 import _lib as L
+    A, B = _bf16(dev, 128, 64), _bf16(dev, 130, 64)          # N = 130 is not a multiple of 8
+    with pytest.raises(L.MmaeError):
+        KN.gemm(A, B, out_f32=torch.empty(128, 130, device=dev))
+    with pytest.raises(L.MmaeError):                          # no output
+        KN.gemm(A, _bf16(dev, 128, 64))
+
+
+def test_elementwise(dev, KN):
+    x = torch.randn(1000, 776, device=dev)
+    assert rel_l2(KN.cast_bf16(x), x.to(torch.bfloat16)) == 0.0
+    dst = torch.empty(1000, 776, device=dev, dtype=torch.bfloat16)
+    cs = torch.zeros(776, device=dev)
+    KN.cast_colsum(x, dst, cs)
+    assert rel_l2(dst, x.to(torch.bfloat16)) == 0.0 and rel_l2(cs, x.sum(0)) < 1e-5
+    cs2 = torch.zeros(776, device=dev)
+    KN.colsum_bf16(dst, cs2)
+    assert rel_l2(cs2, dst.float().sum(0)) < 1e-5
+    assert rel_l2(KN.transpose_bf16(dst), dst.t()) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(1000, 768), (396, 256), (130, 1024), (7, 128)])
+def test_layernorm(dev, KN, shape):
+    M, D = shape
+    x = torch.randn(M, D, device=dev) * 2 + 0.5
+    gam, bet = torch.randn(D, device=dev), torch.randn(D, device=dev)
+    yb, yf, mean, rstd = KN.layernorm_fwd(x, gam, bet, 1e-6, out_bf16=True, out_f32=True)
+    xr, gr, br = x.clone().requires_grad_(True), gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-6)
+    assert rel_l2(yf, ref) < 1e-5 and rel_l2(yb, ref) < 4e-3
+    dy, resid = torch.randn(M, D, device=dev), torch.randn(M, D, device=dev)
+    ref.backward(dy)
+    dgam, dbet = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    dx = KN.layernorm_bwd(dy, x, mean, rstd, gam, dgam, dbet, dx_resid=resid)
+    assert rel_l2(dx, xr.grad + resid) < 1e-5 and rel_l2(dgam, gr.grad) < 1e-4 and rel_l2(dbet, br.grad) < 1e-4
+
+
+ATTN_CASES = [(3, 12, 99, 99, 64, True), (2, 8, 196, 99, 32, False), (2, 8, 196, 196, 32, True), (1, 2, 393, 393, 64, True),
+              (1, 2, 130, 70, 32, False), (2, 1, 17, 5, 64, False), (2, 16, 99, 99, 64, True), (2, 3, 128, 128, 64, True),
+              (1, 2, 100, 33, 64, False)]
+
+
+@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_attention_forward_backward(dev, KN, tc, case):
+    from multimae_b200 import _lib as L
+    L.lib().mmae_attention_set_tc(tc)
+    B, H, Nq, Nk, dh, self_attn = case
+    D, scale = H * dh, dh ** -0.5
+    if self_attn:
+        qkv = _bf16(dev, B * Nq, 3 * D)
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    else:
+        q, kv = _bf16(dev, B * Nq, D), _bf16(dev, B * Nk, 2 * D)
+        k, v = kv[:, :D], kv[:, D:]
+    o, lse = KN.attention_fwd(q, k, v, B, H, Nq, Nk, dh, scale)
+    qf = q.float().reshape(B, Nq, H, dh).transpose(1, 2).detach().requires_grad_(True)
+    kf = k.float().reshape(B, Nk, H, dh).transpose(1, 2).detach().requires_grad_(True)
+    vf = v.float().reshape(B, Nk, H, dh).transpose(1, 2).detach().requires_grad_(True)
+    s = (qf @ kf.transpose(-2, -1)) * scale
+    ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(B * Nq, D)
+    assert rel_l2(o, ref) < 1e-2 and rel_l2(lse, torch.logsumexp(s, -1)) < 1e-4
+    do = _bf16(dev, B * Nq, D)
+    ref.backward(do.float())
+    if self_attn:
+        dqkv = torch.empty(B * Nq, 3 * D, device=dev, dtype=torch.bfloat16)
+        dq, dk, dv = dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:]
+    else:
+        dq = torch.empty(B * Nq, D, device=dev, dtype=torch.bfloat16)
+        dkv = torch.empty(B * Nk, 2 * D, device=dev, dtype=torch.bfloat16)
+        dk, dv = dkv[:, :D], dkv[:, D:]
+    KN.attention_bwd(q, k, v, o, do, lse, dq, dk, dv, B, H, Nq, Nk, dh, scale)
+    assert rel_l2(dq, qf.grad.transpose(1, 2).reshape(B * Nq, D)) < 1e-2
+    assert rel_l2(dk, kf.grad.transpose(1, 2).reshape(B * Nk, D)) < 1e-2
+    assert rel_l2(dv, vf.grad.transpose(1, 2).reshape(B * Nk, D)) < 1e-2

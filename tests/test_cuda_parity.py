@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 BF16_TOL = 1e-2          # activations / predictions / losses, relative L2
 GRAD_TOL = 3e-2          # parameter gradients: global / median relative L2 (bf16 operands in dgrad and wgrad)
-PER_TENSOR_TOL = 0.25    # any single gradient tensor (see _check_grads)
+PER_TENSOR_TOL = 5e-2    # any single gradient tensor, error scaled as described in _check_grads
 
 
 @pytest.fixture(scope="module")
@@ -43,19 +43,39 @@ def _oracle_cfg(c):
 
 
 def _check_grads(got, ref):
-    """All parameter gradients: global relative L2 over the concatenation < GRAD_TOL, median per-tensor < GRAD_TOL,
-    no single tensor beyond PER_TENSOR_TOL (small, cancellation-dominated tensors carry more bf16 noise)."""
-    errs = sorted(((rel_l2(got[k], ref[k]), k) for k in ref), reverse=True)
-    print("worst gradient tensors:", errs[:6])
-    for k in ref:
+    """Parameter gradients of the bf16 path against the fp32 oracle.
+
+    G = global gradient norm, fair_t = G * sqrt(numel_t / N) = the norm tensor t would have at the global RMS.
+      * global relative L2 over the concatenation of all gradients          < GRAD_TOL
+      * every tensor:  ||got - ref|| <= PER_TENSOR_TOL * max(||ref||, fair_t)
+        (tensors far below the global RMS are rounding-noise dominated: bound their absolute error by the scale that
+         matters for the update instead of their own vanishing norm)
+      * tensors carrying real signal (||ref|| >= 0.05 fair_t): median relative error < GRAD_TOL"""
+    names = list(ref)
+    for k in names:
         assert got[k] is not None and torch.isfinite(got[k]).all(), k
-    flat_g = torch.cat([got[k].detach().float().cpu().flatten() for k in ref])
-    flat_r = torch.cat([ref[k].detach().float().cpu().flatten() for k in ref])
+    flat_g = torch.cat([got[k].detach().float().cpu().flatten() for k in names])
+    flat_r = torch.cat([ref[k].detach().float().cpu().flatten() for k in names])
+    G, N = float(flat_r.norm()), flat_r.numel()
     glob = rel_l2(flat_g, flat_r)
-    median = errs[len(errs) // 2][0]
-    print("global rel-l2 %.4f, median %.4f, max %.4f (%s)" % (glob, median, errs[0][0], errs[0][1]))
-    assert glob < GRAD_TOL and median < GRAD_TOL, (glob, median)
-    assert errs[0][0] < PER_TENSOR_TOL, errs[0]
+    rows, signal = [], []
+    for k in names:
+        r = ref[k].detach().float().cpu()
+        g = got[k].detach().float().cpu()
+        fair = G * (r.numel() / N) ** 0.5
+        err = float((g - r).norm())
+        rows.append((err / max(float(r.norm()), fair), err / (float(r.norm()) + 1e-30), float(r.norm()) / fair, k))
+        if float(r.norm()) >= 0.05 * fair:
+            signal.append(err / float(r.norm()))
+    rows.sort(reverse=True)
+    signal.sort()
+    median = signal[len(signal) // 2]
+    print("global rel-l2 %.4f; median rel over %d signal tensors %.4f (max %.4f); worst scaled error %.4f (%s)" %
+          (glob, len(signal), median, signal[-1], rows[0][0], rows[0][3]))
+    print("worst tensors (scaled err, rel err, share):", [(round(a, 4), round(b, 3), round(c, 4), k) for a, b, c, k in rows[:5]])
+    assert glob < GRAD_TOL, glob
+    assert median < GRAD_TOL, median
+    assert rows[0][0] < PER_TENSOR_TOL, rows[0]
 
 
 def _loss_modules():
@@ -137,7 +157,8 @@ def test_model_against_golden_and_oracle(golden_dir, dev, name):
     _check_grads({k: named[k].grad for k in train}, {k: v.grad for k, v in train.items()})
     for k in train:                                        # and the reference's own digests
         d = fx["grads"][k]
-        assert abs(float(named[k].grad.float().norm()) - float(d["norm"])) < PER_TENSOR_TOL * float(d["norm"]) + 1e-6, k
+        fair = float(fx["grad_norm"]) * (named[k].numel() / sum(v.numel() for v in train.values())) ** 0.5
+        assert abs(float(named[k].grad.float().norm()) - float(d["norm"])) < PER_TENSOR_TOL * max(float(d["norm"]), fair), k
 
 
 def test_full_size_model_against_oracle(dev):
