@@ -35,6 +35,8 @@ int64_t mmae_launch_count(void);
  * recorded events and returns the summed algorithmic FLOPs (2*M*N*K), summed kernel milliseconds and launch count. */
 int mmae_profile_gemm(int enable);
 int mmae_profile_gemm_read(double* flops, double* ms, int64_t* launches);
+/* text dump, one line per recorded launch: "M N K flags ms" (flags: bit0 A MN-major, bit1 B MN-major, bits 8+ split_k) */
+int64_t mmae_profile_gemm_dump(char* buf_host, int64_t capacity);
 
 /* ------------------------------------------------------------------------------------------------
  * GEMM on the tcgen05 tensor cores (bf16 x bf16 -> fp32 accumulate in TMEM), TMA-fed.

@@ -110,6 +110,7 @@ SIGNATURES = {
     "mmae_profile_gemm": (c_int, [c_int]),
     "mmae_profile_gemm_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                        ctypes.POINTER(c_i64)]),
+    "mmae_profile_gemm_dump": (c_i64, [ctypes.c_char_p, c_i64]),
     "mmae_gemm_set_variant": (c_int, [c_int]),
     "mmae_gemm_bf16": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int,
                                ctypes.POINTER(GemmEpilogue), c_void_p]),

@@ -18,7 +18,7 @@
 namespace mmae {
 
 void count_launch();
-bool gemm_profile_begin(cudaStream_t st, double flops);
+bool gemm_profile_begin(cudaStream_t st, double flops, int M, int N, int K, int flags);
 void gemm_profile_end(cudaStream_t st);
 
 namespace {
@@ -251,7 +251,7 @@ int launch_gemm1(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParam
     configured = true;
   }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), split_k);
-  const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K);
+  const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K, (A_MN ? 1 : 0) | (B_MN ? 2 : 0) | (split_k << 8));
   kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
   if (prof) gemm_profile_end(stream);
   count_launch();
@@ -462,7 +462,7 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParam
   sc.splits = split_k;
   sc.total = sc.tiles_m * sc.tiles_n * split_k;
   const int grid = std::min(sc.total, sm_count());
-  const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K);
+  const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K, (A_MN ? 1 : 0) | (B_MN ? 2 : 0) | (split_k << 8));
   kern<<<grid, C::THREADS, C::TOTAL, stream>>>(tmA, tmB, p, sc);
   if (prof) gemm_profile_end(stream);
   count_launch();

@@ -27,12 +27,13 @@ struct GemmProfile {
   bool on = false;
   std::vector<cudaEvent_t> begin, end;
   std::vector<double> flops;
+  std::vector<long long> shape;   // packed M, N, K, flags per launch (4 entries each)
   size_t used = 0;
 };
 static GemmProfile g_prof;
 static const size_t kProfCap = 8192;
 
-bool gemm_profile_begin(cudaStream_t st, double flops) {
+bool gemm_profile_begin(cudaStream_t st, double flops, int M, int N, int K, int flags) {
   if (!g_prof.on || g_prof.used >= kProfCap) return false;
   if (g_prof.begin.size() <= g_prof.used) {
     cudaEvent_t a, b;
@@ -40,8 +41,13 @@ bool gemm_profile_begin(cudaStream_t st, double flops) {
     g_prof.begin.push_back(a);
     g_prof.end.push_back(b);
     g_prof.flops.push_back(0.0);
+    for (int i = 0; i < 4; ++i) g_prof.shape.push_back(0);
   }
   g_prof.flops[g_prof.used] = flops;
+  g_prof.shape[4 * g_prof.used + 0] = M;
+  g_prof.shape[4 * g_prof.used + 1] = N;
+  g_prof.shape[4 * g_prof.used + 2] = K;
+  g_prof.shape[4 * g_prof.used + 3] = flags;
   cudaEventRecord(g_prof.begin[g_prof.used], st);
   return true;
 }
@@ -143,4 +149,19 @@ extern "C" int mmae_profile_gemm_read(double* flops, double* ms, int64_t* launch
   if (ms) *ms = t;
   if (launches) *launches = (int64_t)mmae::g_prof.used;
   return MMAE_OK;
+}
+
+// one line per recorded launch: "M N K flags ms" (flags: bit0 a_mn, bit1 b_mn, bits 8.. split_k); returns bytes written
+extern "C" int64_t mmae_profile_gemm_dump(char* buf, int64_t cap) {
+  int64_t off = 0;
+  for (size_t i = 0; i < mmae::g_prof.used; ++i) {
+    if (cudaEventSynchronize(mmae::g_prof.end[i]) != cudaSuccess) return -1;
+    float e = 0.f;
+    cudaEventElapsedTime(&e, mmae::g_prof.begin[i], mmae::g_prof.end[i]);
+    const int n = snprintf(buf + off, (size_t)(cap - off), "%lld %lld %lld %lld %.6f\n", mmae::g_prof.shape[4 * i],
+                           mmae::g_prof.shape[4 * i + 1], mmae::g_prof.shape[4 * i + 2], mmae::g_prof.shape[4 * i + 3], e);
+    if (n <= 0 || off + n >= cap) break;
+    off += n;
+  }
+  return off;
 }

@@ -32,10 +32,10 @@ last = rows[-per_step:]
 tot = sum(ns for _, ns in last)
 agg = collections.OrderedDict()
 for name, ns in last:
-    short = re.sub(r"<.*", "", name.split("(")[0]).split("::")[-1]
-    if "gemm_bf16" in name:
-        m = re.search(r"gemm_bf16[a-z_]*kernel<[^>]*>", name)
-        short = m.group(0) if m else short
+    clean = name.replace("(anonymous namespace)::", "")
+    m = re.search(r"([A-Za-z_][A-Za-z0-9_]*)(<[^()]*>)?\(", clean)
+    short = (m.group(1) + (m.group(2) or "")) if m else clean[:60]
+    short = short.replace("(bool)", "")
     k = agg.setdefault(short, [0, 0.0])
     k[0] += 1
     k[1] += ns

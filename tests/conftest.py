@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def pytest_sessionstart(session):
+    # the CPU oracle collapses when torch oversubscribes a 100+-core host with tiny problems
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run with -m gpu on the B200 box)")
 
