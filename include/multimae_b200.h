@@ -72,7 +72,7 @@ typedef struct mmae_gemm_epilogue {
 } mmae_gemm_epilogue;
 
 /* Kernel variant selection for measurements: -1 = heuristic (default), 0 = one-tile-per-CTA 128x128,
- * 1 = persistent 128x128 with double-buffered TMEM, 2 = persistent 128x256.  Env MMAE_GEMM_VARIANT sets the initial value. */
+ * 1 = persistent 128x128 with double-buffered TMEM, 2 = persistent 128x256, 3 = persistent 128x192.  Env MMAE_GEMM_VARIANT sets the initial value. */
 int mmae_gemm_set_variant(int variant);
 
 int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,

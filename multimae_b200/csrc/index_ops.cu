@@ -264,22 +264,28 @@ __global__ void __launch_bounds__(256) dec_build_bwd_kernel(const float* __restr
 
 // ---------------------------------------------------------------------------------------------------------------------
 // unpatchify: tokens [B*nh*nw, C*P*P] (c, py, px) -> image [B, C, nh*P, nw*P]   (output_adapters.py:277-280)
+// One CTA per (b, patch row); one thread per (token, 4-column group): token-side accesses are contiguous across
+// threads, image-side accesses are 16-byte pieces of P-pixel row segments.
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool TO_IMAGE, typename TokT>
 __global__ void __launch_bounds__(256) unpatchify_kernel(TokT* __restrict__ tok, int64_t ld_tok, float* __restrict__ img,
                                                          int B, int C, int nh, int nw, int P) {
-  // one CTA per (b, c, image row y); threads over x
   const int W = nw * P, H = nh * P;
-  const int y = blockIdx.x % H, c = (blockIdx.x / H) % C, b = blockIdx.x / (H * C);
-  const int ph = y / P, py = y % P;
-  float* irow = img + ((int64_t(b) * C + c) * H + y) * W;
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    const int pw = x / P, px = x % P;
-    const int64_t ti = (int64_t(b) * nh * nw + ph * nw + pw) * ld_tok + (c * P + py) * P + px;
+  const int b = blockIdx.x / nh, ph = blockIdx.x % nh;
+  const int groups_per_tok = C * P * P / 4;
+  for (int idx = threadIdx.x; idx < nw * groups_per_tok; idx += blockDim.x) {
+    const int pw = idx / groups_per_tok, gcol = (idx % groups_per_tok) * 4;
+    const int c = gcol / (P * P), py = (gcol / P) % P, px = gcol % P;
+    float* ip = img + ((int64_t(b) * C + c) * H + ph * P + py) * W + pw * P + px;
+    TokT* tp = tok + (int64_t(b) * nh * nw + ph * nw + pw) * ld_tok + gcol;
     if constexpr (TO_IMAGE) {
-      irow[x] = (float)tok[ti];
+      *reinterpret_cast<float4*>(ip) = __ldg(reinterpret_cast<const float4*>(tp));
     } else {
-      tok[ti] = (TokT)irow[x];
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ip));
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y);
+      o.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(tp) = o;
     }
   }
 }
@@ -377,7 +383,8 @@ using namespace mmae;
 extern "C" int mmae_unpatchify(const float* tokens, int64_t ld_tok, float* image, int B, int C, int nh, int nw, int P,
                                void* stream) {
   MMAE_CHECK(tokens && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG, "mmae_unpatchify: bad args");
-  unpatchify_kernel<true, const float><<<B * C * nh * P, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_unpatchify: P and ld must be multiples of 4");
+  unpatchify_kernel<true, const float><<<B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       tokens, ld_tok, image, B, C, nh, nw, P);
   count_launch();
   MMAE_LAUNCH_OK();
@@ -388,7 +395,8 @@ extern "C" int mmae_patchify_bf16(const float* image, void* tokens_bf16, int64_t
                                   int P, void* stream) {
   MMAE_CHECK(tokens_bf16 && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG,
              "mmae_patchify_bf16: bad args");
-  unpatchify_kernel<false, bf16><<<B * C * nh * P, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_patchify_bf16: P and ld must be multiples of 4");
+  unpatchify_kernel<false, bf16><<<B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<bf16*>(tokens_bf16), ld_tok, const_cast<float*>(image), B, C, nh, nw, P);
   count_launch();
   MMAE_LAUNCH_OK();

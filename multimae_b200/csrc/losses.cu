@@ -12,7 +12,7 @@ void count_launch();
 namespace {
 
 constexpr int LOSS_THREADS = 256;
-constexpr int MAX_NW = 64;  // patches per strip (224/16 = 14, 448/16 = 28, 56/4 = 14 ...)
+constexpr int MAX_NW = 64;  // patches per strip for the CE kernel's mask cache (224/16 = 14, 448/16 = 28, 56/4 = 14 ...)
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -26,38 +26,9 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;  // valid on warp 0
 }
 
-// per-patch statistics of the target for norm_pix (unbiased variance over the C*P*P values of a patch)
-__device__ void strip_patch_stats(const float* __restrict__ tgt_b, int C, int H, int W, int P, int ph, int nw,
-                                  const unsigned char* pmask, float* pmean, float* prstd) {
-  const int n = C * P * P;
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) {
-    pmean[i] = 0.f;
-    prstd[i] = 0.f;
-  }
-  __syncthreads();
-  const int elems = C * P * W;
-  for (int idx = threadIdx.x; idx < elems; idx += blockDim.x) {
-    const int x = idx % W, py = (idx / W) % P, c = idx / (W * P);
-    const int pw = x / P;
-    if (pmask[pw]) atomicAdd(&pmean[pw], tgt_b[(int64_t(c) * H + ph * P + py) * W + x]);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) pmean[i] *= 1.0f / n;
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < elems; idx += blockDim.x) {
-    const int x = idx % W, py = (idx / W) % P, c = idx / (W * P);
-    const int pw = x / P;
-    if (pmask[pw]) {
-      const float d = tgt_b[(int64_t(c) * H + ph * P + py) * W + x] - pmean[pw];
-      atomicAdd(&prstd[pw], d * d);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nw; i += blockDim.x) prstd[i] = rsqrtf(prstd[i] / (n - 1) + 1e-6f);
-  __syncthreads();
-}
-
-// kind: 0 = MSE, 1 = L1.  BWD = false: accumulate sample_sum[b];  BWD = true: write dpred strip.
+// MSE / L1 with optional norm_pix: one CTA per (sample, patch row), one WARP per patch (patches pw = warp, warp+8, ...).
+// A patch is C*P rows of P contiguous floats; lane l of the warp owns float4 #(l % (P/4)) of row (l / (P/4)) + k*rows_per_it.
+// kind: 0 = MSE, 1 = L1.  BWD = false: accumulate sample_sum[b];  BWD = true: write dpred (zeros for unmasked patches).
 template <bool BWD>
 __global__ void __launch_bounds__(LOSS_THREADS) regr_loss_kernel(int kind, int norm_pix, const float* __restrict__ pred,
                                                                  const float* __restrict__ tgt,
@@ -66,36 +37,66 @@ __global__ void __launch_bounds__(LOSS_THREADS) regr_loss_kernel(int kind, int n
                                                                  const float* __restrict__ coef,
                                                                  const float* __restrict__ grad_out,
                                                                  float* __restrict__ dpred) {
-  __shared__ unsigned char pmask[MAX_NW];
-  __shared__ float pmean[MAX_NW], prstd[MAX_NW], red[LOSS_THREADS / 32];
+  __shared__ float red[LOSS_THREADS / 32];
   const int nh = H / P, nw = W / P;
   const int b = blockIdx.x / nh, ph = blockIdx.x % nh;
-  for (int i = threadIdx.x; i < nw; i += blockDim.x)
-    pmask[i] = mask == nullptr ? 1 : (mask[(int64_t(b) * nh + ph) * nw + i] != 0);
-  __syncthreads();
-  const float* pred_b = pred + int64_t(b) * C * H * W;
-  const float* tgt_b = tgt + int64_t(b) * C * H * W;
-  if (norm_pix) strip_patch_stats(tgt_b, C, H, W, P, ph, nw, pmask, pmean, prstd);
-  const int elems = C * P * W;
-  float acc = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vec_per_row = P / 4;                    // float4 per patch row (P = 16 -> 4, P = 4 -> 1)
+  const int rows_per_it = 32 / vec_per_row;         // patch rows covered by one warp iteration
+  const int prow = lane / vec_per_row, pvec = lane % vec_per_row;
+  const int nrows = C * P;                          // rows of one patch, ordered (c, py)
+  const int n = C * P * P;
+  const int64_t img_off = int64_t(b) * C * H * W;
   float gscale = 0.f;
   if constexpr (BWD) gscale = grad_out[0] * coef[b];
-  for (int idx = threadIdx.x; idx < elems; idx += blockDim.x) {
-    const int x = idx % W, py = (idx / W) % P, c = idx / (W * P);
-    const int pw = x / P;
-    const int64_t off = (int64_t(c) * H + ph * P + py) * W + x;
-    if (!pmask[pw]) {
-      if constexpr (BWD) dpred[int64_t(b) * C * H * W + off] = 0.f;
-      continue;
+  float acc = 0.f;
+
+  for (int pw = warp; pw < nw; pw += LOSS_THREADS / 32) {
+    const bool masked = mask == nullptr ? true : (mask[(int64_t(b) * nh + ph) * nw + pw] != 0);
+    if (!masked && !BWD) continue;
+    float mean = 0.f, rstd = 1.f;
+    if (masked && norm_pix) {                        // unbiased variance over the C*P*P target values of the patch
+      float s = 0.f;
+      for (int r = prow; r < nrows; r += rows_per_it) {
+        const int c = r / P, py = r % P;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(tgt + img_off + (int64_t(c) * H + ph * P + py) * W + pw * P + pvec * 4));
+        s += t.x + t.y + t.z + t.w;
+      }
+      mean = warp_sum(s) / n;
+      float q = 0.f;
+      for (int r = prow; r < nrows; r += rows_per_it) {
+        const int c = r / P, py = r % P;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(tgt + img_off + (int64_t(c) * H + ph * P + py) * W + pw * P + pvec * 4));
+        const float a = t.x - mean, bb = t.y - mean, cc = t.z - mean, d = t.w - mean;
+        q += a * a + bb * bb + cc * cc + d * d;
+      }
+      rstd = rsqrtf(warp_sum(q) / (n - 1) + 1e-6f);
     }
-    float t = tgt_b[off];
-    if (norm_pix) t = (t - pmean[pw]) * prstd[pw];
-    const float d = pred_b[off] - t;
-    if constexpr (BWD) {
-      const float g = kind == 0 ? 2.f * d : (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
-      dpred[int64_t(b) * C * H * W + off] = g * gscale;
-    } else {
-      acc += kind == 0 ? d * d : fabsf(d);
+    for (int r = prow; r < nrows; r += rows_per_it) {
+      const int c = r / P, py = r % P;
+      const int64_t off = img_off + (int64_t(c) * H + ph * P + py) * W + pw * P + pvec * 4;
+      if (!masked) {
+        if constexpr (BWD) *reinterpret_cast<float4*>(dpred + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      float4 t = __ldg(reinterpret_cast<const float4*>(tgt + off));
+      const float4 pr = __ldg(reinterpret_cast<const float4*>(pred + off));
+      if (norm_pix) {
+        t.x = (t.x - mean) * rstd; t.y = (t.y - mean) * rstd; t.z = (t.z - mean) * rstd; t.w = (t.w - mean) * rstd;
+      }
+      const float d0 = pr.x - t.x, d1 = pr.y - t.y, d2 = pr.z - t.z, d3 = pr.w - t.w;
+      if constexpr (BWD) {
+        float4 g;
+        if (kind == 0) {
+          g = make_float4(2.f * d0, 2.f * d1, 2.f * d2, 2.f * d3);
+        } else {
+          g = make_float4(d0 > 0.f ? 1.f : (d0 < 0.f ? -1.f : 0.f), d1 > 0.f ? 1.f : (d1 < 0.f ? -1.f : 0.f),
+                          d2 > 0.f ? 1.f : (d2 < 0.f ? -1.f : 0.f), d3 > 0.f ? 1.f : (d3 < 0.f ? -1.f : 0.f));
+        }
+        *reinterpret_cast<float4*>(dpred + off) = make_float4(g.x * gscale, g.y * gscale, g.z * gscale, g.w * gscale);
+      } else {
+        acc += kind == 0 ? d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 : fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
+      }
     }
   }
   if constexpr (!BWD) {
@@ -213,6 +214,8 @@ extern "C" int mmae_masked_loss_forward(int kind, int norm_pix, float label_smoo
   MMAE_CHECK(pred && target && ws && loss_out && B > 0 && C > 0 && scale > 0 && H % scale == 0 && W % scale == 0,
              MMAE_ERR_ARG, "mmae_masked_loss_forward: bad args");
   MMAE_CHECK(kind >= 0 && kind <= 2 && W / scale <= MAX_NW, MMAE_ERR_UNSUPPORTED, "mmae_masked_loss_forward: kind/width");
+  MMAE_CHECK(kind == 2 || (scale % 4 == 0 && 32 % (scale / 4) == 0 && W % 4 == 0), MMAE_ERR_UNSUPPORTED,
+             "mmae_masked_loss_forward: patch scale %d unsupported (multiple of 4, <= 128)", scale);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   float* sample_sum = ws;
   float* coef = ws + B;
@@ -241,6 +244,8 @@ extern "C" int mmae_masked_loss_backward(int kind, int norm_pix, float label_smo
   MMAE_CHECK(pred && target && ws && grad_out && dpred && B > 0 && C > 0 && scale > 0, MMAE_ERR_ARG,
              "mmae_masked_loss_backward: bad args");
   MMAE_CHECK(kind >= 0 && kind <= 2 && W / scale <= MAX_NW, MMAE_ERR_UNSUPPORTED, "mmae_masked_loss_backward: kind/width");
+  MMAE_CHECK(kind == 2 || (scale % 4 == 0 && 32 % (scale / 4) == 0 && W % 4 == 0), MMAE_ERR_UNSUPPORTED,
+             "mmae_masked_loss_backward: patch scale %d unsupported (multiple of 4, <= 128)", scale);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const float* coef = ws + B;
   const int nh = H / scale;

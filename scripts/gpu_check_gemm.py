@@ -45,7 +45,7 @@ def gemm_case(M, N, K, a_mn, b_mn, split_k=1):
 from multimae_b200 import _lib as LIB  # noqa: E402
 
 # ---- correctness: the four operand-major combinations, small and ragged shapes, for every kernel variant
-for variant in (0, 1, 2):
+for variant in (0, 1, 2, 3):
     LIB.lib().mmae_gemm_set_variant(variant)
     print("== gemm variant", variant, flush=True)
     for (M, N, K_) in [(128, 128, 64), (128, 128, 256), (256, 384, 768), (200, 136, 200), (396, 2128, 256),
@@ -216,7 +216,7 @@ for (M, N, K_, a_mn, b_mn, split) in [(12672, 2304, 768, 0, 0, 1), (12672, 768, 
     Bin = B.t().contiguous() if b_mn else B
     fl = 2.0 * M * N * K_
     res = []
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3):
         LIB.lib().mmae_gemm_set_variant(variant)
         if split > 1:
             out = torch.zeros(M, N, device=dev)

@@ -30,7 +30,7 @@ def KN():
     L.lib().mmae_attention_set_tc(1)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 @pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 768), (200, 136, 200), (396, 2128, 256), (1000, 768, 512),
                                    (2560, 2304, 768)])
 def test_gemm_all_operand_majors(dev, KN, variant, shape):
@@ -48,7 +48,7 @@ def test_gemm_all_operand_majors(dev, KN, variant, shape):
             assert rel_l2(out, ref) < 3e-5, (variant, shape, a_mn, b_mn, rel_l2(out, ref))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_gemm_split_k_wgrad_shapes(dev, KN, variant):
     from multimae_b200 import _lib as L
     L.lib().mmae_gemm_set_variant(variant)
@@ -59,7 +59,7 @@ def test_gemm_split_k_wgrad_shapes(dev, KN, variant):
         assert rel_l2(out, A.float() @ B.float().t()) < 3e-5
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_gemm_fused_epilogues(dev, KN, variant):
     from multimae_b200 import _lib as L
     L.lib().mmae_gemm_set_variant(variant)
