@@ -89,6 +89,12 @@ int mmae_cast_colsum_f32(const float* src, int64_t ld_src, void* dst_bf16, int64
                          int M, int N, void* stream);
 /* colsum[n] += sum_m src_bf16[m,n] */
 int mmae_colsum_bf16(const void* src_bf16, int64_t ld_src, float* colsum, int M, int N, void* stream);
+/* exact-erf GELU over a bf16 stream (nn.GELU, multimae/multimae_utils.py:139,150): backward = 0: io[i] = gelu(z[i]);
+ * backward = 1: io[i] *= gelu'(z[i]) in place.  n must be a multiple of 8. */
+int mmae_gelu_bf16(const void* z, void* io, int64_t n, int backward, void* stream);
+/* 1: the module-level entry points fuse GELU / GELU' into the GEMM epilogue; 0 (default): streaming kernel after the
+ * GEMM (measured faster: the epilogue is instruction-issue bound).  Env MMAE_FUSE_GELU sets the initial value. */
+int mmae_set_fuse_gelu(int enable);
 /* dst[N,M] = src[M,N]^T (bf16) */
 int mmae_transpose_bf16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int M, int N, void* stream);
 

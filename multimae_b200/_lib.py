@@ -117,6 +117,8 @@ SIGNATURES = {
     "mmae_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
     "mmae_cast_colsum_f32": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_int, c_int, c_void_p]),
     "mmae_colsum_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_void_p]),
+    "mmae_gelu_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "mmae_set_fuse_gelu": (c_int, [c_int]),
     "mmae_transpose_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p]),
     "mmae_layernorm_forward": (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64,
                                        c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),

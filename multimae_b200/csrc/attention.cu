@@ -18,6 +18,13 @@
 namespace mmae {
 void count_launch();
 bool attn_tc_supported(int Nq, int Nk, int head_dim);
+bool attn_tc_fwd_gen_supported(int H, int Nq, int Nk, int head_dim);
+bool attn_tc_bwd_gen_supported(int H, int Nq, int Nk, int head_dim);
+int attn_tc_backward_gen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+                         int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                         void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
+int attn_tc_forward_gen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                        int64_t ldo, float* lse, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
 int attn_tc_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                     float* lse, int B, int H, int Nq, int Nk, float scale, cudaStream_t st);
 int attn_tc_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
@@ -455,6 +462,8 @@ extern "C" int mmae_attention_forward(const void* q, int64_t ldq, const void* k,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (g_attn_tc && attn_tc_supported(Nq, Nk, head_dim))
     return attn_tc_forward(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, scale, st);
+  if (g_attn_tc >= 2 && attn_tc_fwd_gen_supported(H, Nq, Nk, head_dim))
+    return attn_tc_forward_gen(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, head_dim, scale, st);
   const bf16 *qp = (const bf16*)q, *kp = (const bf16*)k, *vp = (const bf16*)v;
   if (head_dim == 64)
     attn_fwd_kernel<64><<<grid, ATT_THREADS, 0, st>>>(qp, ldq, kp, ldk, vp, ldv, (bf16*)o, ldo, lse, Nq, Nk, H, scale);
@@ -487,6 +496,16 @@ extern "C" int mmae_attention_backward(const void* q, int64_t ldq, const void* k
     MMAE_LAUNCH_OK();
     return attn_tc_backward(q, ldq, k, ldk, v, ldv, d_o, lddo, lse, delta_ws, dq, lddq, dk, lddk, dv, lddv, B, H, Nq, Nk,
                             scale, st);
+  }
+  if (g_attn_tc >= 2 && attn_tc_bwd_gen_supported(H, Nq, Nk, head_dim)) {
+    if (head_dim == 64)
+      attn_delta_kernel<64><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
+    else
+      attn_delta_kernel<32><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
+    count_launch();
+    MMAE_LAUNCH_OK();
+    return attn_tc_backward_gen(q, ldq, k, ldk, v, ldv, d_o, lddo, lse, delta_ws, dq, lddq, dk, lddk, dv, lddv, B, H, Nq,
+                                Nk, head_dim, scale, st);
   }
   if (head_dim == 64) {
     attn_delta_kernel<64><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);

@@ -69,6 +69,36 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const void* __restrict
   }
 }
 
+// a = gelu(z)  /  dz *= gelu'(z): bf16 streams, 8 elements per thread.  Used when the GELU is NOT fused into the GEMM
+// epilogue: a tcgen05 epilogue has ~4 instruction-issue slots per clock next to a tile's MMA time, which the ~14
+// instructions/element of erf-GELU overrun; a full-occupancy streaming kernel does not.
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256) gelu_stream_kernel(const bf16* __restrict__ z, bf16* __restrict__ io, int64_t n) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x * 8;
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + i));
+    const uint32_t* zu = reinterpret_cast<const uint32_t*>(&zv);
+    uint4 ov;
+    uint32_t* ou = reinterpret_cast<uint32_t*>(&ov);
+    if constexpr (BACKWARD) {
+      const uint4 dv = *reinterpret_cast<const uint4*>(io + i);
+      const uint32_t* du = reinterpret_cast<const uint32_t*>(&dv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = unpack_bf16x2(zu[k]), d = unpack_bf16x2(du[k]);
+        ou[k] = pack_bf16x2(d.x * dgelu_erf(a.x), d.y * dgelu_erf(a.y));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = unpack_bf16x2(zu[k]);
+        ou[k] = pack_bf16x2(gelu_erf(a.x), gelu_erf(a.y));
+      }
+    }
+    *reinterpret_cast<uint4*>(io + i) = ov;
+  }
+}
+
 // 64x64 bf16 tile transpose through padded shared memory; block 256 threads
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restrict__ src, int64_t ld_src,
                                                              bf16* __restrict__ dst, int64_t ld_dst, int M, int N) {
@@ -151,6 +181,23 @@ extern "C" int mmae_transpose_bf16(const void* src, int64_t ld_src, void* dst, i
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
   transpose_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(src), ld_src, reinterpret_cast<bf16*>(dst), ld_dst, M, N);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+// a[i] = gelu(z[i]) (backward = 0)   or   dz[i] *= gelu'(z[i]) in place (backward = 1); n must be a multiple of 8
+extern "C" int mmae_gelu_bf16(const void* z, void* io, int64_t n, int backward, void* stream) {
+  MMAE_CHECK(z && io && n >= 0 && n % 8 == 0, MMAE_ERR_ARG, "mmae_gelu_bf16: bad args (n %% 8)");
+  if (n == 0) return MMAE_OK;
+  int64_t blocks = (n / 8 + 255) / 256;
+  const int64_t cap = int64_t(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (backward)
+    gelu_stream_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(io), n);
+  else
+    gelu_stream_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(io), n);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

@@ -115,80 +115,6 @@ __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&r)[32], int ro
 }
 
 
-// Coalesced variant used by the persistent kernels: the warp's 32 rows x 32 columns chunk (one row per lane, as
-// tcgen05.ld delivers it) is transposed through a 2 KB XOR-swizzled shared-memory tile, 16 columns at a time, so that
-// 4 consecutive lanes cover 64 contiguous bytes of ONE output row: residual / dGELU operand loads and all stores then
-// touch full 32-byte sectors instead of 16 bytes in each of 32 different rows.
-__device__ __forceinline__ void epilogue_chunk32_staged(const uint32_t (&r)[32], float* st, int lane, int row_base, int nb,
-                                                        const GemmParams& p, bool first_split, bool atomic_out) {
-  const mmae_gemm_epilogue& ep = p.ep;
-  const float* bias = first_split ? ep.bias : nullptr;
-  const float* resid = first_split ? ep.residual : nullptr;
-  const bf16* zptr = reinterpret_cast<const bf16*>(ep.dgelu_z);
-  bf16* preact = reinterpret_cast<bf16*>(ep.preact_bf16);
-  bf16* out_b = reinterpret_cast<bf16*>(ep.out_bf16);
-  float* out_f = ep.out_f32;
-  const int wsw = (lane >> 1) & 3;          // write swizzle of row `lane`
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int i0 = half * 16 + j * 4;
-      *reinterpret_cast<float4*>(st + lane * 16 + ((j ^ wsw) << 2)) =
-          make_float4(__uint_as_float(r[i0]), __uint_as_float(r[i0 + 1]), __uint_as_float(r[i0 + 2]),
-                      __uint_as_float(r[i0 + 3]));
-    }
-    __syncwarp();
-    const int c = lane & 3;
-    const int n = nb + half * 16 + c * 4;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int rr = it * 8 + (lane >> 2);
-      const float4 a = *reinterpret_cast<const float4*>(st + rr * 16 + ((c ^ ((rr >> 1) & 3)) << 2));
-      const int row = row_base + rr;
-      if (row >= p.M || n >= p.N) continue;
-      float v0 = a.x * ep.alpha, v1 = a.y * ep.alpha, v2 = a.z * ep.alpha, v3 = a.w * ep.alpha;
-      if (bias) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n));
-        v0 += b.x; v1 += b.y; v2 += b.z; v3 += b.w;
-      }
-      if (preact) {
-        uint2 o;
-        o.x = pack_bf16x2(v0, v1);
-        o.y = pack_bf16x2(v2, v3);
-        *reinterpret_cast<uint2*>(preact + int64_t(row) * ep.ld_preact + n) = o;
-      }
-      if (ep.act == 1) {
-        v0 = gelu_erf(v0); v1 = gelu_erf(v1); v2 = gelu_erf(v2); v3 = gelu_erf(v3);
-      }
-      if (zptr) {
-        const uint2 z = __ldg(reinterpret_cast<const uint2*>(zptr + int64_t(row) * ep.ld_dgelu_z + n));
-        const float2 z0 = unpack_bf16x2(z.x), z1 = unpack_bf16x2(z.y);
-        v0 *= dgelu_erf(z0.x); v1 *= dgelu_erf(z0.y); v2 *= dgelu_erf(z1.x); v3 *= dgelu_erf(z1.y);
-      }
-      if (resid) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(resid + int64_t(row) * ep.ld_residual + n));
-        v0 += q.x; v1 += q.y; v2 += q.z; v3 += q.w;
-      }
-      if (out_f) {
-        float* dst = out_f + int64_t(row) * ep.ld_out_f32 + n;
-        if (atomic_out) {
-          red_add_v4(dst, v0, v1, v2, v3);
-        } else {
-          *reinterpret_cast<float4*>(dst) = make_float4(v0, v1, v2, v3);
-        }
-      }
-      if (out_b) {
-        uint2 o;
-        o.x = pack_bf16x2(v0, v1);
-        o.y = pack_bf16x2(v2, v3);
-        *reinterpret_cast<uint2*>(out_b + int64_t(row) * ep.ld_out_bf16 + n) = o;
-      }
-    }
-  }
-}
-
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -351,8 +277,7 @@ struct Gemm2Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_OFFSET = BAR_OFFSET + 512;          // 2 KB transposition tile per epilogue warp
-  static constexpr int TOTAL = STAGING_OFFSET + EPI_WARPS * 2048 + 1024;
+  static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
   static constexpr uint32_t TMEM_COLS = BN > 128 ? 512 : 256;  // two accumulators, power-of-two allocation
 };
 
@@ -491,7 +416,6 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
     const int q = warp & 3;                       // TMEM lane quarter accessible to this warp
     constexpr int COLS_PER_WARP = BN / (C::EPI_WARPS / 4);   // 128 (BN 128 / 256) or 96 (BN 192)
     const int col0 = (e >> 2) * COLS_PER_WARP;
-    float* staging = reinterpret_cast<float*>(smem + C::STAGING_OFFSET + e * 2048);
     int it = 0;
     for (int item = blockIdx.x; item < sc.total; item += gridDim.x, ++it) {
       int m0, n0, kb_begin, nkb, z;
@@ -500,8 +424,12 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[buf], acc_phase);
       tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
       const bool first_split = z == 0;
       const bool atomic_out = p.ep.accumulate != 0 || sc.splits > 1;
+      // NOTE (measured, round 1): transposing the chunk through shared memory for row-contiguous global accesses made
+      // this epilogue SLOWER (it is issue/latency bound, not sector bound: QKV 900 -> 697 TF/s); one row per lane stays.
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
         const int nb = n0 + col0 + c * 32;
@@ -509,7 +437,7 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN + col0 + c * 32), r);
         tc_wait_ld();
-        epilogue_chunk32_staged(r, staging, lane, m0 + q * 32, nb, p, first_split, atomic_out);
+        epilogue_chunk32(r, row, row_ok, nb, p, first_split, atomic_out);
       }
       tc_fence_before();
       __syncwarp();

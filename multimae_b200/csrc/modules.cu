@@ -2,6 +2,8 @@
 // path, expressed as a fixed sequence of the kernels in this library (tcgen05 GEMMs with fused epilogues, LayerNorm,
 // fused attention, index kernels).  The host passes raw device pointers; all scratch ("ws") and saved-for-backward
 // ("saved") memory is caller-provided, sized by the *_bytes queries, so nothing here allocates.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace mmae {
@@ -54,26 +56,42 @@ int linear_f32(const bf16* x, const bf16* W, const float* b, const float* resid,
   ep.ld_out_f32 = N;
   return mmae_gemm_bf16(x, K, 0, W, K, 0, M, N, K, 1, &ep, st);
 }
+// 1: GELU / GELU' applied in the GEMM epilogue; 0: GEMM writes the pre-activation and a streaming kernel applies it
+int g_fuse_gelu = []() {
+  const char* e = getenv("MMAE_FUSE_GELU");
+  return e ? atoi(e) : 0;
+}();
+
 // z = x W^T + b (bf16, saved), a = gelu(z) (bf16)
 int linear_gelu(const bf16* x, const bf16* W, const float* b, bf16* z, bf16* a, int M, int N, int K, void* st) {
   mmae_gemm_epilogue ep = ep_zero();
   ep.bias = b;
-  ep.act = 1;
-  ep.preact_bf16 = z;
-  ep.ld_preact = N;
-  ep.out_bf16 = a;
+  if (g_fuse_gelu) {
+    ep.act = 1;
+    ep.preact_bf16 = z;
+    ep.ld_preact = N;
+    ep.out_bf16 = a;
+    ep.ld_out_bf16 = N;
+    return mmae_gemm_bf16(x, K, 0, W, K, 0, M, N, K, 1, &ep, st);
+  }
+  ep.out_bf16 = z;
   ep.ld_out_bf16 = N;
-  return mmae_gemm_bf16(x, K, 0, W, K, 0, M, N, K, 1, &ep, st);
+  int rc = mmae_gemm_bf16(x, K, 0, W, K, 0, M, N, K, 1, &ep, st);
+  if (rc != MMAE_OK) return rc;
+  return mmae_gelu_bf16(z, a, int64_t(M) * N, 0, st);
 }
 // dx[M, Kin] = dy[M, Nout] W[Nout, Kin]  (bf16 out; optional * gelu'(z))
 int dgrad_bf16(const bf16* dy, int64_t lddy, const bf16* W, const bf16* dgelu_z, bf16* dx, int M, int Nout, int Kin,
                void* st) {
   mmae_gemm_epilogue ep = ep_zero();
-  ep.dgelu_z = dgelu_z;
+  const bool fused = dgelu_z != nullptr && g_fuse_gelu;
+  ep.dgelu_z = fused ? dgelu_z : nullptr;
   ep.ld_dgelu_z = Kin;
   ep.out_bf16 = dx;
   ep.ld_out_bf16 = Kin;
-  return mmae_gemm_bf16(dy, lddy, 0, W, Kin, 1, M, Kin, Nout, 1, &ep, st);
+  int rc = mmae_gemm_bf16(dy, lddy, 0, W, Kin, 1, M, Kin, Nout, 1, &ep, st);
+  if (rc != MMAE_OK || dgelu_z == nullptr || fused) return rc;
+  return mmae_gelu_bf16(dgelu_z, dx, int64_t(M) * Kin, 1, st);
 }
 // dW[Nout, Kin] += dy[M, Nout]^T x[M, Kin]
 int wgrad(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, float* dW, int M, int Nout, int Kin, void* st) {
@@ -542,5 +560,10 @@ extern "C" int mmae_embed_backward(const mmae_embed_layout* Lp, const mmae_embed
                                 L.num_classes[t], g->class_emb[t], cst));
     }
   }
+  return MMAE_OK;
+}
+
+extern "C" int mmae_set_fuse_gelu(int enable) {
+  mmae::g_fuse_gelu = enable;
   return MMAE_OK;
 }
