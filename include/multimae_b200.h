@@ -95,6 +95,8 @@ int mmae_gelu_bf16(const void* z, void* io, int64_t n, int backward, void* strea
 /* 1: the module-level entry points fuse GELU / GELU' into the GEMM epilogue; 0 (default): streaming kernel after the
  * GEMM (measured faster: the epilogue is instruction-issue bound).  Env MMAE_FUSE_GELU sets the initial value. */
 int mmae_set_fuse_gelu(int enable);
+/* out[i] = x[i] + float(y_bf16[i]); n must be a multiple of 8 */
+int mmae_add_bf16_f32(const float* x, const void* y_bf16, float* out, int64_t n, void* stream);
 /* dst[N,M] = src[M,N]^T (bf16) */
 int mmae_transpose_bf16(const void* src, int64_t ld_src, void* dst, int64_t ld_dst, int M, int N, void* stream);
 
@@ -107,6 +109,11 @@ int mmae_transpose_bf16(const void* src, int64_t ld_src, void* dst, int64_t ld_d
 int mmae_layernorm_forward(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
                            int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd, int M, int D,
                            float eps, void* stream);
+/* x_sum = x + addend_bf16 (fp32, written when non-NULL) followed by LayerNorm(x_sum) -> y_bf16: the residual add
+ * `x = x + branch(...)` (multimae/multimae_utils.py:230-231) fused in front of the next norm. */
+int mmae_add_layernorm_forward(const float* x, int64_t ldx, const void* addend_bf16, int64_t ldadd, float* x_sum,
+                               int64_t ldsum, const float* gamma, const float* beta, void* y_bf16, int64_t ldy,
+                               float* mean, float* rstd, int M, int D, float eps, void* stream);
 int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
                             const float* mean, const float* rstd, const float* gamma, const float* dx_resid,
                             int64_t ldr, float* dx, int64_t lddx, float* dgamma, float* dbeta, int M, int D,
@@ -119,7 +126,8 @@ int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t lddy, const 
  * [b*N, (b+1)*N).  head_dim in {32, 64}.  lse[B,H,Nq] = log-sum-exp of the scaled scores (saved for backward).
  * backward: delta_ws is a [B,H,Nq] fp32 scratch; dq/dk/dv are written (not accumulated).
  * ---------------------------------------------------------------------------------------------- */
-/* 1 (default): tcgen05 kernels where supported (Nq, Nk <= 128, head_dim 64); 0: warp-MMA kernels everywhere */
+/* bit mask: 1 = fused single-tile tcgen05 kernels (Nq, Nk <= 128, head_dim 64), 2 = general tcgen05 forward (<= 256 keys,
+ * head_dim 32/64), 4 = general tcgen05 backward; 0 = warp-MMA kernels everywhere.  Default 3 (env MMAE_ATTN_TC). */
 int mmae_attention_set_tc(int enable);
 int mmae_attention_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                            void* o, int64_t ldo, float* lse, int B, int H, int Nq, int Nk, int head_dim,
@@ -280,6 +288,8 @@ int mmae_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
 /* image <-> token layout helpers ('b (nh nw) (c ph pw) <-> b c (nh ph) (nw pw)') */
 int mmae_unpatchify(const float* tokens, int64_t ld_tok, float* image, int B, int C, int nh, int nw, int P,
                     void* stream);
+int mmae_unpatchify_bf16(const void* tokens_bf16, int64_t ld_tok, float* image, int B, int C, int nh, int nw, int P,
+                         void* stream);
 int mmae_patchify_bf16(const float* image, void* tokens_bf16, int64_t ld_tok, int B, int C, int nh, int nw, int P,
                        void* stream);
 

@@ -440,10 +440,12 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 using namespace mmae;
 
-// 1 = tcgen05 kernels for shapes they support (default), 0 = mma.sync kernels everywhere (A/B measurements)
+// bit 0: fused single-tile tcgen05 kernels (encoder shape) ; bit 1: general tcgen05 forward (query tiles, <= 256 keys,
+// head_dim 32/64) ; bit 2: general tcgen05 backward (measured slower than the warp-MMA backward at N = 196: off).
+// 0 = warp-MMA kernels everywhere.  Default 3.
 static int g_attn_tc = []() {
   const char* e = getenv("MMAE_ATTN_TC");
-  return e ? atoi(e) : 1;
+  return e ? atoi(e) : 3;
 }();
 extern "C" int mmae_attention_set_tc(int enable) {
   g_attn_tc = enable;
@@ -460,9 +462,9 @@ extern "C" int mmae_attention_forward(const void* q, int64_t ldq, const void* k,
              MMAE_ERR_ARG, "mmae_attention_forward: 16-byte alignment / ld %% 8 required");
   dim3 grid(ceil_div(Nq, ATT_ROWS), H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (g_attn_tc && attn_tc_supported(Nq, Nk, head_dim))
+  if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim))
     return attn_tc_forward(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, scale, st);
-  if (g_attn_tc >= 2 && attn_tc_fwd_gen_supported(H, Nq, Nk, head_dim))
+  if ((g_attn_tc & 2) && attn_tc_fwd_gen_supported(H, Nq, Nk, head_dim))
     return attn_tc_forward_gen(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, head_dim, scale, st);
   const bf16 *qp = (const bf16*)q, *kp = (const bf16*)k, *vp = (const bf16*)v;
   if (head_dim == 64)
@@ -490,14 +492,14 @@ extern "C" int mmae_attention_backward(const void* q, int64_t ldq, const void* k
   const bf16 *qp = (const bf16*)q, *kp = (const bf16*)k, *vp = (const bf16*)v, *op = (const bf16*)o,
              *dop = (const bf16*)d_o;
   dim3 gq(ceil_div(Nq, ATT_ROWS), H, B), gk(ceil_div(Nk, ATT_ROWS), H, B);
-  if (g_attn_tc && attn_tc_supported(Nq, Nk, head_dim)) {
+  if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim)) {
     attn_delta_kernel<64><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
     count_launch();
     MMAE_LAUNCH_OK();
     return attn_tc_backward(q, ldq, k, ldk, v, ldv, d_o, lddo, lse, delta_ws, dq, lddq, dk, lddk, dv, lddv, B, H, Nq, Nk,
                             scale, st);
   }
-  if (g_attn_tc >= 2 && attn_tc_bwd_gen_supported(H, Nq, Nk, head_dim)) {
+  if ((g_attn_tc & 4) && attn_tc_bwd_gen_supported(H, Nq, Nk, head_dim)) {
     if (head_dim == 64)
       attn_delta_kernel<64><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
     else

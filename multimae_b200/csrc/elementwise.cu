@@ -99,6 +99,20 @@ __global__ void __launch_bounds__(256) gelu_stream_kernel(const bf16* __restrict
   }
 }
 
+// out[i] = x[i] + float(y_bf16[i])   (residual add of a bf16 branch output onto the fp32 stream)
+__global__ void __launch_bounds__(256) add_bf16_f32_kernel(const float* __restrict__ x, const bf16* __restrict__ y,
+                                                           float* __restrict__ out, int64_t n) {
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x * 8;
+  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x + i + 4));
+    const uint4 yv = __ldg(reinterpret_cast<const uint4*>(y + i));
+    const float2 y0 = unpack_bf16x2(yv.x), y1 = unpack_bf16x2(yv.y), y2 = unpack_bf16x2(yv.z), y3 = unpack_bf16x2(yv.w);
+    *reinterpret_cast<float4*>(out + i) = make_float4(a.x + y0.x, a.y + y0.y, a.z + y1.x, a.w + y1.y);
+    *reinterpret_cast<float4*>(out + i + 4) = make_float4(b.x + y2.x, b.y + y2.y, b.z + y3.x, b.w + y3.y);
+  }
+}
+
 // 64x64 bf16 tile transpose through padded shared memory; block 256 threads
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restrict__ src, int64_t ld_src,
                                                              bf16* __restrict__ dst, int64_t ld_dst, int M, int N) {
@@ -198,6 +212,19 @@ extern "C" int mmae_gelu_bf16(const void* z, void* io, int64_t n, int backward, 
     gelu_stream_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(io), n);
   else
     gelu_stream_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(io), n);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+extern "C" int mmae_add_bf16_f32(const float* x, const void* y_bf16, float* out, int64_t n, void* stream) {
+  MMAE_CHECK(x && y_bf16 && out && n >= 0 && n % 8 == 0, MMAE_ERR_ARG, "mmae_add_bf16_f32: bad args (n %% 8)");
+  if (n == 0) return MMAE_OK;
+  int64_t blocks = (n / 8 + 255) / 256;
+  const int64_t cap = int64_t(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  add_bf16_f32_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<const bf16*>(y_bf16), out, n);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

@@ -279,7 +279,13 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(TokT* __restrict__ tok,
     float* ip = img + ((int64_t(b) * C + c) * H + ph * P + py) * W + pw * P + px;
     TokT* tp = tok + (int64_t(b) * nh * nw + ph * nw + pw) * ld_tok + gcol;
     if constexpr (TO_IMAGE) {
-      *reinterpret_cast<float4*>(ip) = __ldg(reinterpret_cast<const float4*>(tp));
+      if constexpr (sizeof(TokT) == 4) {
+        *reinterpret_cast<float4*>(ip) = __ldg(reinterpret_cast<const float4*>(tp));
+      } else {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(tp));
+        const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y);
+        *reinterpret_cast<float4*>(ip) = make_float4(a.x, a.y, b2.x, b2.y);
+      }
     } else {
       const float4 v = __ldg(reinterpret_cast<const float4*>(ip));
       uint2 o;
@@ -386,6 +392,17 @@ extern "C" int mmae_unpatchify(const float* tokens, int64_t ld_tok, float* image
   MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_unpatchify: P and ld must be multiples of 4");
   unpatchify_kernel<true, const float><<<B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       tokens, ld_tok, image, B, C, nh, nw, P);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+extern "C" int mmae_unpatchify_bf16(const void* tokens_bf16, int64_t ld_tok, float* image, int B, int C, int nh, int nw,
+                                    int P, void* stream) {
+  MMAE_CHECK(tokens_bf16 && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG, "mmae_unpatchify_bf16: bad args");
+  MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_unpatchify_bf16: P and ld must be multiples of 4");
+  unpatchify_kernel<true, const bf16><<<B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(tokens_bf16), ld_tok, image, B, C, nh, nw, P);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

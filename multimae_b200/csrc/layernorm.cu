@@ -14,6 +14,8 @@ constexpr int LN_WARPS = 8;
 // D = NVEC * 128 (each lane owns NVEC float4, strided by 32 lanes)
 template <int NVEC>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __restrict__ x, int64_t ldx,
+                                                               const bf16* __restrict__ addend, int64_t ldadd,
+                                                               float* __restrict__ x_sum, int64_t ldsum,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, bf16* __restrict__ y_bf16,
                                                                int64_t ldy, float* __restrict__ y_f32, int64_t ldyf,
@@ -28,7 +30,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NVEC; ++i) {
-    v[i] = __ldg(reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4));
+    const int c = (i * 32 + lane) * 4;
+    v[i] = __ldg(reinterpret_cast<const float4*>(xr + c));
+    if (addend != nullptr) {   // residual add fused in front of the normalisation: x <- x + bf16 branch output
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(addend + int64_t(row) * ldadd + c));
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      v[i].x += a.x; v[i].y += a.y; v[i].z += b.x; v[i].w += b.y;
+      if (x_sum != nullptr) *reinterpret_cast<float4*>(x_sum + int64_t(row) * ldsum + c) = v[i];
+    }
     s += v[i].x + v[i].y + v[i].z + v[i].w;
   }
   const float mean = warp_sum(s) * (1.0f / D);
@@ -159,9 +168,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __res
 
 using namespace mmae;
 
-extern "C" int mmae_layernorm_forward(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
-                                      int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd, int M, int D,
-                                      float eps, void* stream) {
+static int ln_forward_impl(const float* x, int64_t ldx, const bf16* addend, int64_t ldadd, float* x_sum, int64_t ldsum,
+                           const float* gamma, const float* beta, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldyf,
+                           float* mean, float* rstd, int M, int D, float eps, void* stream) {
   MMAE_CHECK(x && gamma && beta && (y_bf16 || y_f32) && M > 0, MMAE_ERR_ARG, "mmae_layernorm_forward: bad args");
   MMAE_CHECK(D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && ldyf % 4 == 0, MMAE_ERR_UNSUPPORTED,
              "mmae_layernorm_forward: D=%d must be a multiple of 128 and <= 1024", D);
@@ -170,7 +179,8 @@ extern "C" int mmae_layernorm_forward(const float* x, int64_t ldx, const float* 
   bf16* yb = reinterpret_cast<bf16*>(y_bf16);
 #define LN_CASE(NV)                                                                                            \
   case NV:                                                                                                     \
-    ln_fwd_kernel<NV><<<grid, block, 0, st>>>(x, ldx, gamma, beta, yb, ldy, y_f32, ldyf, mean, rstd, M, eps); \
+    ln_fwd_kernel<NV><<<grid, block, 0, st>>>(x, ldx, addend, ldadd, x_sum, ldsum, gamma, beta, yb, ldy, y_f32, ldyf, \
+                                              mean, rstd, M, eps);                                            \
     break;
   switch (D / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
@@ -180,6 +190,22 @@ extern "C" int mmae_layernorm_forward(const float* x, int64_t ldx, const float* 
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
+}
+
+extern "C" int mmae_layernorm_forward(const float* x, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
+                                      int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd, int M, int D,
+                                      float eps, void* stream) {
+  return ln_forward_impl(x, ldx, nullptr, 0, nullptr, 0, gamma, beta, y_bf16, ldy, y_f32, ldyf, mean, rstd, M, D, eps, stream);
+}
+
+// x_sum = x + addend (fp32, written when non-NULL), then LayerNorm of x_sum: the residual add of
+// `x = x + attn(...)` (multimae/multimae_utils.py:230) fused in front of the next norm (:231)
+extern "C" int mmae_add_layernorm_forward(const float* x, int64_t ldx, const void* addend_bf16, int64_t ldadd, float* x_sum,
+                                          int64_t ldsum, const float* gamma, const float* beta, void* y_bf16, int64_t ldy,
+                                          float* mean, float* rstd, int M, int D, float eps, void* stream) {
+  MMAE_CHECK(addend_bf16 && ldadd % 4 == 0 && (!x_sum || ldsum % 4 == 0), MMAE_ERR_ARG, "mmae_add_layernorm_forward: bad args");
+  return ln_forward_impl(x, ldx, reinterpret_cast<const bf16*>(addend_bf16), ldadd, x_sum, ldsum, gamma, beta, y_bf16, ldy,
+                         nullptr, 0, mean, rstd, M, D, eps, stream);
 }
 
 extern "C" int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,

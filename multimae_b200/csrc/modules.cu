@@ -273,8 +273,7 @@ extern "C" int64_t mmae_block_workspace_bytes(int B, int N, int D, int H, int hi
 
 extern "C" int mmae_block_forward(const float* x_in, float* x_out, int B, int N, int D, int H, int hidden, float eps,
                                   const mmae_block_params* p, void* saved, void* ws, void* st) {
-  (void)ws;
-  MMAE_CHECK(x_in && x_out && p && saved && B > 0 && N > 0 && H > 0 && D % H == 0, MMAE_ERR_ARG,
+  MMAE_CHECK(x_in && x_out && p && saved && ws && B > 0 && N > 0 && H > 0 && D % H == 0, MMAE_ERR_ARG,
              "mmae_block_forward: bad args");
   const int M = B * N, dh = D / H;
   BlockSaved s = block_saved(saved, B, N, D, H, hidden);
@@ -282,16 +281,22 @@ extern "C" int mmae_block_forward(const float* x_in, float* x_out, int B, int N,
   RUN(mmae_cast_f32_to_bf16(p->proj_w, s.wproj, int64_t(D) * D, st));
   RUN(mmae_cast_f32_to_bf16(p->fc1_w, s.w1, int64_t(hidden) * D, st));
   RUN(mmae_cast_f32_to_bf16(p->fc2_w, s.w2, int64_t(D) * hidden, st));
+  // Residual adds are NOT done in the GEMM epilogues: a row-per-lane fp32 read-modify-write there costs one L1 wavefront
+  // per 16 bytes (measured 262 TF/s for the proj GEMM vs ~900 for a bf16 store).  The branch output is stored as bf16
+  // (what the reference's autocast Linear produces) and the add is fused into the next streaming kernel.
+  BlockWs w = block_ws(ws, B, N, D, H, hidden);
+  bf16* y = w.g;   // [M, D] bf16 scratch (forward only)
   // x = x + attn(norm1(x))                                       multimae_utils.py:230
   RUN(mmae_layernorm_forward(x_in, D, p->norm1_w, p->norm1_b, s.h1, D, nullptr, 0, s.mean1, s.rstd1, M, D, eps, st));
   RUN(linear_bf16(s.h1, s.wqkv, p->qkv_b, s.qkv, M, 3 * D, D, st));
   RUN(mmae_attention_forward(s.qkv, 3 * D, s.qkv + D, 3 * D, s.qkv + 2 * D, 3 * D, s.o, D, s.lse, B, H, N, N, dh,
                              1.0f / sqrtf((float)dh), st));
-  RUN(linear_f32(s.o, s.wproj, p->proj_b, x_in, s.x_mid, M, D, D, st));
-  // x = x + mlp(norm2(x))                                        multimae_utils.py:231
-  RUN(mmae_layernorm_forward(s.x_mid, D, p->norm2_w, p->norm2_b, s.h2, D, nullptr, 0, s.mean2, s.rstd2, M, D, eps, st));
+  RUN(linear_bf16(s.o, s.wproj, p->proj_b, y, M, D, D, st));
+  // x = x + mlp(norm2(x))                                        multimae_utils.py:231  (add fused in front of norm2)
+  RUN(mmae_add_layernorm_forward(x_in, D, y, D, s.x_mid, D, p->norm2_w, p->norm2_b, s.h2, D, s.mean2, s.rstd2, M, D, eps, st));
   RUN(linear_gelu(s.h2, s.w1, p->fc1_b, s.z, s.a, M, hidden, D, st));
-  RUN(linear_f32(s.a, s.w2, p->fc2_b, s.x_mid, x_out, M, D, hidden, st));
+  RUN(linear_bf16(s.a, s.w2, p->fc2_b, y, M, D, hidden, st));
+  RUN(mmae_add_bf16_f32(s.x_mid, y, x_out, int64_t(M) * D, st));
   return MMAE_OK;
 }
 
@@ -373,7 +378,8 @@ extern "C" int mmae_dechead_forward(const float* enc, int De, const mmae_decoder
   RUN(mmae_layernorm_forward(s.x0, Dd, p->out_norm_w, p->out_norm_b, s.h, Dd, nullptr, 0, s.omean, s.orstd, Mq, Dd, eps,
                              st));
   RUN(linear_gelu(s.h, s.w1, p->fc1_b, s.z, s.a, Mq, hidden, Dd, st));
-  RUN(linear_f32(s.a, s.w2, p->fc2_b, s.x0, x_out, Mq, Dd, hidden, st));
+  RUN(linear_bf16(s.a, s.w2, p->fc2_b, w.g, Mq, Dd, hidden, st));          // bf16 branch output, add outside the epilogue
+  RUN(mmae_add_bf16_f32(s.x0, w.g, x_out, int64_t(Mq) * Dd, st));
   return MMAE_OK;
 }
 
@@ -445,7 +451,7 @@ TailSaved tail_saved(void* base, int B, int nh, int nw, int Dd, int C, int P) {
   return s;
 }
 struct TailWs {
-  float* y;
+  bf16* y;
   bf16* dy;
   size_t bytes;
 };
@@ -453,7 +459,7 @@ TailWs tail_ws(void* base, int B, int nh, int nw, int Dd, int C, int P) {
   (void)Dd;
   Carver c(base);
   TailWs w;
-  w.y = c.take<float>(size_t(B) * nh * nw * C * P * P);
+  w.y = c.take<bf16>(size_t(B) * nh * nw * C * P * P);
   w.dy = c.take<bf16>(size_t(B) * nh * nw * C * P * P);
   w.bytes = align_up(c.off, 256);
   return w;
@@ -475,8 +481,8 @@ extern "C" int mmae_dectail_forward(const float* x, int B, int nh, int nw, int D
   TailWs w = tail_ws(ws, B, nh, nw, Dd, C, P);
   RUN(mmae_cast_f32_to_bf16(x, s.x_b, int64_t(M) * Dd, st));
   RUN(mmae_cast_f32_to_bf16(out_w, s.w_b, int64_t(Nout) * Dd, st));
-  RUN(linear_f32(s.x_b, s.w_b, out_b, nullptr, w.y, M, Nout, Dd, st));       // output_adapters.py:274
-  RUN(mmae_unpatchify(w.y, Nout, pred, B, C, nh, nw, P, st));               // output_adapters.py:277-280
+  RUN(linear_bf16(s.x_b, s.w_b, out_b, w.y, M, Nout, Dd, st));              // output_adapters.py:274 (half precision
+  RUN(mmae_unpatchify_bf16(w.y, Nout, pred, B, C, nh, nw, P, st));          //  like the autocast Linear); :277-280
   return MMAE_OK;
 }
 

@@ -95,10 +95,11 @@ class BlockFunction(torch.autograd.Function):
         x = x.contiguous().float()
         lib = L.lib()
         saved = torch.empty(lib.mmae_block_saved_bytes(B, N, D, H, hidden), dtype=torch.uint8, device=x.device)
+        ws = Workspace.get(lib.mmae_block_workspace_bytes(B, N, D, H, hidden), x.device)
         out = torch.empty_like(x)
         prm = L.BlockParams(*[p.data_ptr() for p in params])
         L.check(lib.mmae_block_forward(x.data_ptr(), out.data_ptr(), B, N, D, H, hidden, eps, ctypes.byref(prm),
-                                       saved.data_ptr(), None, L.current_stream()), "mmae_block_forward")
+                                       saved.data_ptr(), ws.data_ptr(), L.current_stream()), "mmae_block_forward")
         ctx.meta = meta
         ctx.params = params
         ctx.save_for_backward(x, saved)

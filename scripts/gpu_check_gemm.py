@@ -178,7 +178,7 @@ def attn_case(B, H, Nq, Nk, dh, self_attn):
     report("attn bwd dv " + tag, relerr(dv, vf.grad.transpose(1, 2).reshape(B * Nk, D)), 1e-2)
 
 
-for tc in (0, 1, 2):
+for tc in (0, 1, 3, 7):
     LIB.lib().mmae_attention_set_tc(tc)
     print("== attention tcgen05 path", tc, flush=True)
     for args in [(3, 12, 99, 99, 64, True), (2, 8, 196, 99, 32, False), (2, 8, 196, 196, 32, True),
@@ -240,7 +240,7 @@ o = torch.empty(B_ * N_, D_, device=dev, dtype=torch.bfloat16)
 fl = 4.0 * B_ * H_ * N_ * N_ * dh_
 do = rand_bf16(B_ * N_, D_)
 dqkv = torch.empty_like(qkv)
-for tc in (0, 1, 2):
+for tc in (0, 1, 3, 7):
     LIB.lib().mmae_attention_set_tc(tc)
     ms = time_it(lambda: KN.attention_fwd(q, k, v, B_, H_, N_, N_, dh_, 0.125, out=o))
     print("time attn fwd enc (tc=%d): %.3f ms (%.1f TF/s useful)" % (tc, ms, fl / ms / 1e9), flush=True)

@@ -27,7 +27,7 @@ def KN():
     from multimae_b200 import kernels
     yield kernels
     L.lib().mmae_gemm_set_variant(-1)
-    L.lib().mmae_attention_set_tc(1)
+    L.lib().mmae_attention_set_tc(3)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
@@ -129,7 +129,7 @@ ATTN_CASES = [(3, 12, 99, 99, 64, True), (2, 8, 196, 99, 32, False), (2, 8, 196,
               (1, 2, 100, 33, 64, False)]
 
 
-@pytest.mark.parametrize("tc", [0, 1, 2])
+@pytest.mark.parametrize("tc", [0, 1, 3, 7])
 @pytest.mark.parametrize("case", ATTN_CASES)
 def test_attention_forward_backward(dev, KN, tc, case):
     from multimae_b200 import _lib as L
