@@ -132,17 +132,20 @@ def run_ours(args, rank, world, local_rank):
     resident = [{k: v.to(device) for k, v in hb.items()} for hb in host]
     lib = L.lib()
 
+    from multimae_b200.train_step import TrainStep
+    stepper = TrainStep(model, loss_fns, opt, scaler, num_encoded_tokens=98, alphas=1.0, loss_sources={"norm_rgb": "rgb"})
+    mode = "eager"
+    if args.graph and world == 1:
+        try:
+            stepper.capture(resident[0], warmup=3)
+            mode = "cuda-graph (whole step = one graph launch)"
+        except Exception as e:  # noqa: BLE001
+            stepper.graph = None
+            model.external_shares = None
+            mode = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:120]
+
     def train_step(x):
-        preds, masks = model(x, num_encoded_tokens=98, alphas=1.0, sample_tasks_uniformly=False,
-                             fp32_output_adapters=[])
-        task_losses = {}
-        for task in preds:
-            src = "rgb" if task == "norm_rgb" else task
-            task_losses[task] = loss_fns[task](preds[task].float(), x[src], mask=masks.get(src))
-        loss = sum(task_losses.values())
-        opt.zero_grad()
-        grad_norm = scaler(loss, opt, clip_grad=None, skip_grad=None, parameters=None)
-        return loss, grad_norm
+        return stepper(x)
 
     def barrier():
         if world > 1:
@@ -208,7 +211,11 @@ def run_ours(args, rank, world, local_rank):
     # ------------------------------------------------------------------ roofline of the dominant kernel (tcgen05 GEMM)
     peak_tf, peak_gbs, peak_src = peaks()
     lib.mmae_profile_gemm(1)
-    train_step(resident[0])
+    l0 = lib.mmae_launch_count()
+    stepper._step(resident[0])                             # eager: per-launch events cannot be replayed from a graph
+    launches_per_step = lib.mmae_launch_count() - l0
+    if stepper.graph is not None:
+        launches = launches_per_step * args.steps          # a replayed graph re-issues the captured launches
     torch.cuda.synchronize()
     lib.mmae_profile_gemm(0)
     fl, ms_g, n_g = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
@@ -244,7 +251,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "global_batch": args.batch * world, "per_gpu_batch": args.batch,
                    "parallelism": "dp%d" % world,
                    "l2": "two alternating input batches (212 MB) and a >9 GB per-step activation working set exceed the 126 MB L2",
-                   "loss_scaling": "none (bf16)", "final_loss": round(final_loss, 4)},
+                   "loss_scaling": "none (bf16)", "final_loss": round(final_loss, 4), "launch_mode": mode},
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
@@ -341,6 +348,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (BASELINE: 128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (single GPU)")
     ap.add_argument("--gemm-shapes", default=None, help="write a per-shape GEMM time table of one profiled step here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -281,9 +281,11 @@ int mmae_masked_loss_backward(int kind, int norm_pix, float label_smoothing, con
  * ---------------------------------------------------------------------------------------------- */
 int mmae_grad_unscale_norm(float* grads, int64_t n, const float* inv_scale_dev, float inv_scale, float post_scale,
                            float* out2, float* norm_out, void* stream);
+/* dyn_lr_step_dev (optional): device float[2] = {learning rate, step count}; when non-NULL it overrides the host
+ * `lr` / `step` arguments so that a CUDA-graph replay picks up the current schedule values. */
 int mmae_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, const float* found_inf_dev,
-                    void* stream);
+                    const float* dyn_lr_step_dev, void* stream);
 
 /* image <-> token layout helpers ('b (nh nw) (c ph pw) <-> b c (nh ph) (nw pw)') */
 int mmae_unpatchify(const float* tokens, int64_t ld_tok, float* image, int B, int C, int nh, int nw, int P,

@@ -53,8 +53,14 @@ __global__ void sqrt_kernel(const float* __restrict__ in, float* __restrict__ no
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
                                                     float eps, float wd, float bc1, float bc2_sqrt,
-                                                    const float* __restrict__ found_inf) {
+                                                    const float* __restrict__ found_inf, const float* __restrict__ dyn) {
   if (found_inf != nullptr && found_inf[0] != 0.f) return;
+  if (dyn != nullptr) {   // learning rate and step count live on the device (CUDA-graph replay): dyn = {lr, step}
+    lr = dyn[0];
+    const float step = dyn[1];
+    bc1 = 1.0f - powf(beta1, step);
+    bc2_sqrt = sqrtf(1.0f - powf(beta2, step));
+  }
   const int64_t stride = int64_t(gridDim.x) * blockDim.x * 4;
   for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     if (i + 4 <= n) {
@@ -116,7 +122,7 @@ extern "C" int mmae_grad_unscale_norm(float* grads, int64_t n, const float* inv_
 
 extern "C" int mmae_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                                float beta1, float beta2, float eps, float weight_decay, int step,
-                               const float* found_inf_dev, void* stream) {
+                               const float* found_inf_dev, const float* dyn_lr_step_dev, void* stream) {
   MMAE_CHECK(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, MMAE_ERR_ARG, "mmae_adamw_step: bad args");
   if (n == 0) return MMAE_OK;
   const float bc1 = 1.0f - powf(beta1, (float)step);
@@ -126,7 +132,7 @@ extern "C" int mmae_adamw_step(float* params, const float* grads, float* exp_avg
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   adamw_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, found_inf_dev);
+      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, found_inf_dev, dyn_lr_step_dev);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

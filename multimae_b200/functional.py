@@ -417,11 +417,11 @@ def grad_unscale_norm(flat, inv_scale=1.0, post_scale=1.0, inv_scale_tensor=None
     return norm, out2
 
 
-def adamw_step(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, found_inf=None):
+def adamw_step(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay, step, found_inf=None, dyn=None):
     L.check(L.lib().mmae_adamw_step(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                     params.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
-                                    float(weight_decay), int(step), L.ptr(found_inf), L.current_stream()),
-            "mmae_adamw_step")
+                                    float(weight_decay), max(int(step), 1), L.ptr(found_inf), L.ptr(dyn),
+                                    L.current_stream()), "mmae_adamw_step")
 
 
 _ = math

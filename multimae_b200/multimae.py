@@ -112,6 +112,14 @@ class MultiMAE(nn.Module):
         self._arena = None
         self._grad_callback = None
         self._warned_fp32 = False
+        self.external_shares = None
+
+    def draw_task_shares(self, B, n_tasks, alphas=1.0, sample_tasks_uniformly=False):
+        """Host-side Dirichlet draw of generate_random_masks (multimae/multimae.py:182-187) as a separate step."""
+        alphas = [alphas] * n_tasks if isinstance(alphas, float) else alphas
+        if sample_tasks_uniformly:
+            return Dirichlet(self.sample_alphas(B, n_tasks, alphas=alphas)).sample()
+        return Dirichlet(torch.Tensor(alphas)).sample((B,))
 
     # ------------------------------------------------------------------------------------------------------------
     # initialisation, same scheme as multimae/multimae.py:100-125
@@ -197,7 +205,11 @@ class MultiMAE(nn.Module):
         first = list(input_tokens.values())[0]
         B, device = first.shape[0], first.device
         alphas = [alphas] * len(input_tokens) if isinstance(alphas, float) else alphas
-        if sample_tasks_uniformly:
+        if self.external_shares is not None:
+            # CUDA-graph mode (train_step.GraphedTrainStep): the host-side Dirichlet draw is made outside the captured
+            # region and copied into this static device buffer before every replay
+            shares = self.external_shares
+        elif sample_tasks_uniformly:
             shares = Dirichlet(self.sample_alphas(B, len(input_tokens), alphas=alphas)).sample()
         else:
             shares = Dirichlet(torch.Tensor(alphas)).sample((B,))

@@ -26,14 +26,26 @@ class FlatAdamW(torch.optim.Optimizer):
                 p.data = view
         self.exp_avg = torch.zeros_like(self.flat_params)
         self.exp_avg_sq = torch.zeros_like(self.flat_params)
-        self._step = 0
+        # {learning rate, step count} on the device: the update kernel reads them there, so a captured CUDA graph replays
+        # with the current schedule value and an advancing bias correction
+        self._dyn = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(1)
+        self.sync_hyperparams()
+
+    def sync_hyperparams(self):
+        """Push the current param_group learning rate to the device scalar (call before a graph replay)."""
+        g = self.param_groups[0]
+        self._lr_host[0] = g["lr"] * g.get("lr_scale", 1.0)
+        self._dyn[0:1].copy_(self._lr_host, non_blocking=True)
 
     @torch.no_grad()
     def fused_step(self, found_inf=None):
         g = self.param_groups[0]
-        self._step += 1
+        if not (self._dyn.is_cuda and torch.cuda.is_current_stream_capturing()):
+            self.sync_hyperparams()
+        self._dyn[1:2].add_(1.0)            # device-side step counter (captured and replayed with the graph)
         Fn.adamw_step(self.flat_params, self.mmae_arena.flat, self.exp_avg, self.exp_avg_sq, g["lr"] * g.get("lr_scale", 1.0),
-                      g["betas"], g["eps"], g["weight_decay"], self._step, found_inf)
+                      g["betas"], g["eps"], g["weight_decay"], 1, found_inf, dyn=self._dyn)
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -1,0 +1,69 @@
+"""One pre-training step (run_pretraining_multimae.py:494-537) as a reusable object, optionally replayed as ONE CUDA graph.
+
+All shapes of the step are static (the ragged Dirichlet sampling still yields exactly `num_encoded_tokens` per sample),
+no kernel of the path synchronises with the host, and every buffer the C ABI sees is owned by torch's allocator, so the
+whole forward + losses + backward + gradient all-reduce hooks + unscale/norm + AdamW sequence (~900 launches) can be
+captured once and replayed: the host then costs one graph launch per step instead of ~900 kernel launches and ~70
+autograd-function dispatches.  The only host work left per step is the Dirichlet draw (copied into a static buffer)."""
+import torch
+
+
+class TrainStep:
+    def __init__(self, model, loss_fns, optimizer, scaler, num_encoded_tokens=98, alphas=1.0, sample_tasks_uniformly=False,
+                 loss_sources=None):
+        self.model, self.loss_fns, self.opt, self.scaler = model, loss_fns, optimizer, scaler
+        self.num_encoded_tokens, self.alphas, self.uniform = num_encoded_tokens, alphas, sample_tasks_uniformly
+        self.loss_sources = loss_sources or {}          # output key -> input key holding its target / mask
+        self.graph = None
+        self.static_x = None
+        self.static_out = None
+
+    # the eager step: exactly the body of train_one_epoch between the H2D copy and the optimizer step
+    def _step(self, x):
+        preds, masks = self.model(x, num_encoded_tokens=self.num_encoded_tokens, alphas=self.alphas,
+                                  sample_tasks_uniformly=self.uniform)
+        task_losses = {}
+        for task in preds:
+            src = self.loss_sources.get(task, task)
+            task_losses[task] = self.loss_fns[task](preds[task].float(), x[src], mask=masks.get(src))
+        loss = sum(task_losses.values())
+        self.opt.zero_grad()
+        grad_norm = self.scaler(loss, self.opt, clip_grad=None, skip_grad=None, parameters=None)
+        return loss.detach(), grad_norm
+
+    def __call__(self, x):
+        if self.graph is None:
+            return self._step(x)
+        n_tasks = len([d for d in x if d in self.model.input_adapters])
+        B = next(iter(x.values())).shape[0]
+        shares = self.model.draw_task_shares(B, n_tasks, self.alphas, self.uniform)
+        self._shares_host.copy_(shares)
+        self.model.external_shares.copy_(self._shares_host, non_blocking=True)
+        for k, v in x.items():
+            self.static_x[k].copy_(v, non_blocking=True)
+        if hasattr(self.opt, "sync_hyperparams"):
+            self.opt.sync_hyperparams()
+        self.graph.replay()
+        return self.static_out
+
+    def capture(self, example_x, warmup=3):
+        """Warm up eagerly (lazy kernel attributes, workspaces, arena) then capture the step into a CUDA graph."""
+        dev = next(iter(example_x.values())).device
+        n_tasks = len([d for d in example_x if d in self.model.input_adapters])
+        B = next(iter(example_x.values())).shape[0]
+        self.static_x = {k: v.clone() for k, v in example_x.items()}
+        self._shares_host = torch.empty((B, n_tasks), dtype=torch.float32).pin_memory()
+        self._shares_host.copy_(self.model.draw_task_shares(B, n_tasks, self.alphas, self.uniform))
+        self.model.external_shares = self._shares_host.to(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._step(self.static_x)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.static_out = self._step(self.static_x)
+        self.graph = graph
+        return self
