@@ -92,6 +92,8 @@ int mmae_colsum_bf16(const void* src_bf16, int64_t ld_src, float* colsum, int M,
 /* exact-erf GELU over a bf16 stream (nn.GELU, multimae/multimae_utils.py:139,150): backward = 0: io[i] = gelu(z[i]);
  * backward = 1: io[i] *= gelu'(z[i]) in place.  n must be a multiple of 8. */
 int mmae_gelu_bf16(const void* z, void* io, int64_t n, int backward, void* stream);
+/* dz[m,n] *= gelu'(z[m,n]) in place and colsum[n] += sum_m dz[m,n] (fc1 bias gradient) in one pass */
+int mmae_dgelu_colsum_bf16(const void* z, void* dz, int64_t ld, float* colsum, int M, int N, void* stream);
 /* 1: the module-level entry points fuse GELU / GELU' into the GEMM epilogue; 0 (default): streaming kernel after the
  * GEMM (measured faster: the epilogue is instruction-issue bound).  Env MMAE_FUSE_GELU sets the initial value. */
 int mmae_set_fuse_gelu(int enable);
@@ -118,6 +120,12 @@ int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t lddy, const 
                             const float* mean, const float* rstd, const float* gamma, const float* dx_resid,
                             int64_t ldr, float* dx, int64_t lddx, float* dgamma, float* dbeta, int M, int D,
                             void* stream);
+
+/* as mmae_layernorm_backward, additionally writing bf16(dx) and accumulating dx_colsum[d] += sum_rows dx[:,d] */
+int mmae_layernorm_backward_ex(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
+                               const float* mean, const float* rstd, const float* gamma, const float* dx_resid,
+                               int64_t ldr, float* dx, int64_t lddx, float* dgamma, float* dbeta, void* dx_bf16,
+                               int64_t lddxb, float* dx_colsum, int M, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused multi-head attention (scores stay on chip).  Attention / CrossAttention:

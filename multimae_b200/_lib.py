@@ -118,6 +118,7 @@ SIGNATURES = {
     "mmae_cast_colsum_f32": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_int, c_int, c_void_p]),
     "mmae_colsum_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_void_p]),
     "mmae_gelu_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "mmae_dgelu_colsum_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_int, c_int, c_void_p]),
     "mmae_set_fuse_gelu": (c_int, [c_int]),
     "mmae_add_bf16_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "mmae_transpose_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p]),
@@ -127,6 +128,9 @@ SIGNATURES = {
                                            c_i64, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "mmae_layernorm_backward": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mmae_layernorm_backward_ex": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
+                                           c_int, c_int, c_void_p]),
     "mmae_attention_set_tc": (c_int, [c_int]),
     "mmae_attention_forward": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p,
                                        c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),

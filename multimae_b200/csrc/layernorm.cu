@@ -85,15 +85,17 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __res
                                                                const float* __restrict__ dx_resid, int64_t ldr,
                                                                float* __restrict__ dx, int64_t lddx,
                                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                               int M) {
+                                                               bf16* __restrict__ dx_bf16, int64_t lddxb,
+                                                               float* __restrict__ dx_colsum, int M) {
   constexpr int D = NVEC * 128;
   __shared__ float4 red[LN_WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 dg[NVEC], db[NVEC], gm[NVEC];
+  float4 dg[NVEC], db[NVEC], gm[NVEC], cs[NVEC];
 #pragma unroll
   for (int i = 0; i < NVEC; ++i) {
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
   }
   const int r_end = min((blockIdx.x + 1) * LNB_ROWS, M);
@@ -134,17 +136,24 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __res
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       *reinterpret_cast<float4*>(dx + int64_t(row) * lddx + c) = o;
+      if (dx_bf16 != nullptr) {   // bf16 copy of dx (next GEMM operand) and its column sums (next bias gradient)
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(dx_bf16 + int64_t(row) * lddxb + c) = pk;
+        cs[i].x += o.x; cs[i].y += o.y; cs[i].z += o.z; cs[i].w += o.w;
+      }
     }
   }
   // column reductions across the block's warps
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
-    float* dst = pass == 0 ? dgamma : dbeta;
+  for (int pass = 0; pass < 3; ++pass) {
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dx_colsum);
     if (dst == nullptr) continue;
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
       __syncthreads();
-      red[warp][lane] = pass == 0 ? dg[i] : db[i];
+      red[warp][lane] = pass == 0 ? dg[i] : (pass == 1 ? db[i] : cs[i]);
       __syncthreads();
       if (warp == 0) {
         float4 a = red[0][lane];
@@ -208,10 +217,10 @@ extern "C" int mmae_add_layernorm_forward(const float* x, int64_t ldx, const voi
                          nullptr, 0, mean, rstd, M, D, eps, stream);
 }
 
-extern "C" int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
-                                       const float* mean, const float* rstd, const float* gamma, const float* dx_resid,
-                                       int64_t ldr, float* dx, int64_t lddx, float* dgamma, float* dbeta, int M, int D,
-                                       void* stream) {
+static int ln_backward_impl(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx, const float* mean,
+                            const float* rstd, const float* gamma, const float* dx_resid, int64_t ldr, float* dx,
+                            int64_t lddx, float* dgamma, float* dbeta, bf16* dx_bf16, int64_t lddxb, float* dx_colsum, int M,
+                            int D, void* stream) {
   MMAE_CHECK(dy && x && mean && rstd && gamma && dx && M > 0, MMAE_ERR_ARG, "mmae_layernorm_backward: bad args");
   MMAE_CHECK(D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && ldr % 4 == 0,
              MMAE_ERR_UNSUPPORTED, "mmae_layernorm_backward: D=%d must be a multiple of 128 and <= 1024", D);
@@ -221,10 +230,10 @@ extern "C" int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t l
   case NV:                                                                                                        \
     if (dy_is_bf16)                                                                                               \
       ln_bwd_kernel<NV, true><<<grid, block, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx,     \
-                                                      lddx, dgamma, dbeta, M);                                   \
+                                                      lddx, dgamma, dbeta, dx_bf16, lddxb, dx_colsum, M);        \
     else                                                                                                          \
       ln_bwd_kernel<NV, false><<<grid, block, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx,    \
-                                                       lddx, dgamma, dbeta, M);                                  \
+                                                       lddx, dgamma, dbeta, dx_bf16, lddxb, dx_colsum, M);       \
     break;
   switch (D / 128) {
     LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
@@ -234,4 +243,22 @@ extern "C" int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t l
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
+}
+
+extern "C" int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
+                                       const float* mean, const float* rstd, const float* gamma, const float* dx_resid,
+                                       int64_t ldr, float* dx, int64_t lddx, float* dgamma, float* dbeta, int M, int D,
+                                       void* stream) {
+  return ln_backward_impl(dy, dy_is_bf16, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx, lddx, dgamma, dbeta, nullptr, 0,
+                          nullptr, M, D, stream);
+}
+
+// same, additionally emitting bf16(dx) and colsum += sum_rows(dx): the operand and bias gradient of the next Linear backward
+extern "C" int mmae_layernorm_backward_ex(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,
+                                          const float* mean, const float* rstd, const float* gamma, const float* dx_resid,
+                                          int64_t ldr, float* dx, int64_t lddx, float* dgamma, float* dbeta, void* dx_bf16,
+                                          int64_t lddxb, float* dx_colsum, int M, int D, void* stream) {
+  MMAE_CHECK(!dx_bf16 || lddxb % 4 == 0, MMAE_ERR_ARG, "mmae_layernorm_backward_ex: bad bf16 leading dimension");
+  return ln_backward_impl(dy, dy_is_bf16, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx, lddx, dgamma, dbeta,
+                          reinterpret_cast<bf16*>(dx_bf16), lddxb, dx_colsum, M, D, stream);
 }

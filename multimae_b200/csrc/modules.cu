@@ -93,6 +93,18 @@ int dgrad_bf16(const bf16* dy, int64_t lddy, const bf16* W, const bf16* dgelu_z,
   if (rc != MMAE_OK || dgelu_z == nullptr || fused) return rc;
   return mmae_gelu_bf16(dgelu_z, dx, int64_t(M) * Kin, 1, st);
 }
+// dz = (dy W) * gelu'(z)  and  db1 += colsum(dz)   (fc2 dgrad + GELU backward + fc1 bias gradient)
+int dgrad_dgelu_colsum(const bf16* dy, int64_t lddy, const bf16* W, const bf16* z, bf16* dz, float* db, int M, int Nout,
+                       int Kin, void* st) {
+  if (g_fuse_gelu) {
+    int rc = dgrad_bf16(dy, lddy, W, z, dz, M, Nout, Kin, st);
+    if (rc != MMAE_OK) return rc;
+    return mmae_colsum_bf16(dz, Kin, db, M, Kin, st);
+  }
+  int rc = dgrad_bf16(dy, lddy, W, nullptr, dz, M, Nout, Kin, st);
+  if (rc != MMAE_OK) return rc;
+  return mmae_dgelu_colsum_bf16(z, dz, Kin, db, M, Kin, st);
+}
 // dW[Nout, Kin] += dy[M, Nout]^T x[M, Kin]
 int wgrad(const bf16* dy, int64_t lddy, const bf16* x, int64_t ldx, float* dW, int M, int Nout, int Kin, void* st) {
   mmae_gemm_epilogue ep = ep_zero();
@@ -309,15 +321,14 @@ extern "C" int mmae_block_backward(const float* x_in, const float* dx_out, float
   BlockWs w = block_ws(ws, B, N, D, H, hidden);
   // ---- MLP branch
   RUN(mmae_cast_colsum_f32(dx_out, D, w.g, D, g->fc2_b, M, D, st));
-  RUN(dgrad_bf16(w.g, D, s.w2, s.z, w.big, M, D, hidden, st));               // dz = (g W2) * gelu'(z)
+  RUN(dgrad_dgelu_colsum(w.g, D, s.w2, s.z, w.big, g->fc1_b, M, D, hidden, st));   // dz = (g W2) * gelu'(z); db1
   RUN(wgrad(w.g, D, s.a, hidden, g->fc2_w, M, D, hidden, st));
-  RUN(mmae_colsum_bf16(w.big, hidden, g->fc1_b, M, hidden, st));
   RUN(wgrad(w.big, hidden, s.h2, D, g->fc1_w, M, hidden, D, st));
   RUN(dgrad_bf16(w.big, hidden, s.w1, nullptr, w.dh, M, hidden, D, st));
-  RUN(mmae_layernorm_backward(w.dh, 1, D, s.x_mid, D, s.mean2, s.rstd2, p->norm2_w, dx_out, D, w.dx_mid, D, g->norm2_w,
-                              g->norm2_b, M, D, st));
+  // LN2 backward also emits bf16(dx_mid) and its column sums = operand and bias gradient of the proj backward
+  RUN(mmae_layernorm_backward_ex(w.dh, 1, D, s.x_mid, D, s.mean2, s.rstd2, p->norm2_w, dx_out, D, w.dx_mid, D, g->norm2_w,
+                                 g->norm2_b, w.g, D, g->proj_b, M, D, st));
   // ---- attention branch
-  RUN(mmae_cast_colsum_f32(w.dx_mid, D, w.g, D, g->proj_b, M, D, st));
   RUN(wgrad(w.g, D, s.o, D, g->proj_w, M, D, D, st));
   RUN(dgrad_bf16(w.g, D, s.wproj, nullptr, w.d_o, M, D, D, st));
   bf16* dqkv = w.big;
@@ -396,15 +407,13 @@ extern "C" int mmae_dechead_backward(const float* enc, int De, const mmae_decode
   cudaStream_t cst = reinterpret_cast<cudaStream_t>(st);
   // ---- MLP
   RUN(mmae_cast_colsum_f32(dx_out, Dd, w.g, Dd, g->fc2_b, Mq, Dd, st));
-  RUN(dgrad_bf16(w.g, Dd, s.w2, s.z, w.dz, Mq, Dd, hidden, st));
+  RUN(dgrad_dgelu_colsum(w.g, Dd, s.w2, s.z, w.dz, g->fc1_b, Mq, Dd, hidden, st));
   RUN(wgrad(w.g, Dd, s.a, hidden, g->fc2_w, Mq, Dd, hidden, st));
-  RUN(mmae_colsum_bf16(w.dz, hidden, g->fc1_b, Mq, hidden, st));
   RUN(wgrad(w.dz, hidden, s.h, Dd, g->fc1_w, Mq, hidden, Dd, st));
   RUN(dgrad_bf16(w.dz, hidden, s.w1, nullptr, w.dh, Mq, hidden, Dd, st));
-  RUN(mmae_layernorm_backward(w.dh, 1, Dd, s.x0, Dd, s.omean, s.orstd, p->out_norm_w, dx_out, Dd, w.dx0, Dd,
-                              g->out_norm_w, g->out_norm_b, Mq, Dd, st));
+  RUN(mmae_layernorm_backward_ex(w.dh, 1, Dd, s.x0, Dd, s.omean, s.orstd, p->out_norm_w, dx_out, Dd, w.dx0, Dd,
+                                 g->out_norm_w, g->out_norm_b, w.g, Dd, g->proj_b, Mq, Dd, st));
   // ---- cross attention (no residual around it)
-  RUN(mmae_cast_colsum_f32(w.dx0, Dd, w.g, Dd, g->proj_b, Mq, Dd, st));
   RUN(wgrad(w.g, Dd, s.o, Dd, g->proj_w, Mq, Dd, Dd, st));
   RUN(dgrad_bf16(w.g, Dd, s.wproj, nullptr, w.d_o, Mq, Dd, Dd, st));
   RUN(mmae_attention_backward(s.q, Dd, s.kv, 2 * Dd, s.kv + Dd, 2 * Dd, s.o, Dd, w.d_o, Dd, s.lse, w.delta, w.dq, Dd,

@@ -231,6 +231,21 @@ for (M, N, K_, a_mn, b_mn, split) in [(12672, 2304, 768, 0, 0, 1), (12672, 768, 
           (M, N, K_, a_mn, b_mn, split, "  ".join(res), ms_ref, fl / ms_ref / 1e9), flush=True)
 
 
+# epilogue cost: same GEMM with / without bias, bf16 vs fp32 output
+LIB.lib().mmae_gemm_set_variant(-1)
+for (M, N, K_) in [(12672, 3072, 768), (12672, 2304, 768), (25088, 1024, 256)]:
+    A = rand_bf16(M, K_)
+    B = rand_bf16(N, K_)
+    bias = torch.randn(N, device=dev)
+    ob = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    of = torch.empty(M, N, device=dev)
+    fl = 2.0 * M * N * K_
+    t0 = time_it(lambda: KN.gemm(A, B, out_bf16=ob))
+    t1 = time_it(lambda: KN.gemm(A, B, bias=bias, out_bf16=ob))
+    t2 = time_it(lambda: KN.gemm(A, B, bias=bias, out_f32=of))
+    print("epilogue M=%d N=%d K=%d: plain bf16 %.3f ms (%.0f TF/s) | +bias %.3f ms (%.0f) | +bias fp32-out %.3f ms (%.0f)" %
+          (M, N, K_, t0, fl / t0 / 1e9, t1, fl / t1 / 1e9, t2, fl / t2 / 1e9), flush=True)
+
 # attention timing at the encoder shape
 B_, H_, N_, dh_ = 128, 12, 99, 64
 qkv = rand_bf16(B_ * N_, 3 * H_ * dh_)
@@ -248,6 +263,7 @@ for tc in (0, 1, 3, 7):
     ms = time_it(lambda: KN.attention_bwd(q, k, v, o2, do, lse, dqkv[:, :D_], dqkv[:, D_:2 * D_], dqkv[:, 2 * D_:], B_, H_, N_, N_, dh_, 0.125))
     print("time attn bwd enc (tc=%d): %.3f ms (%.1f TF/s useful)" % (tc, ms, 2.5 * fl / ms / 1e9), flush=True)
 # decoder attention shapes (warp-MMA kernels)
+LIB.lib().mmae_attention_set_tc(3)
 for (Nq_, Nk_, self_) in [(196, 196, True), (196, 99, False)]:
     Dd_, Hd_ = 256, 8
     if self_:
