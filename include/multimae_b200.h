@@ -74,6 +74,9 @@ typedef struct mmae_gemm_epilogue {
 /* Kernel variant selection for measurements: -1 = heuristic (default), 0 = one-tile-per-CTA 128x128,
  * 1 = persistent 128x128 with double-buffered TMEM, 2 = persistent 128x256, 3 = persistent 128x192.  Env MMAE_GEMM_VARIANT sets the initial value. */
 int mmae_gemm_set_variant(int variant);
+/* 1 (default): bf16-only epilogues of the persistent kernels leave through shared memory + TMA tile stores;
+ * 0: per-lane global stores (kept for A/B measurements and for epilogues with extra operands).  Env MMAE_GEMM_TMA_STORE. */
+int mmae_gemm_set_tma_store(int enable);
 
 int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                    int M, int N, int K, int split_k, const mmae_gemm_epilogue* ep, void* stream);

@@ -32,6 +32,7 @@ struct GemmParams {
   int M, N, K;
   int num_kb;        // total k-blocks (ceil(K / BK))
   int kb_per_split;  // k-blocks handled by one split
+  int tma_store;     // persistent kernel: bf16 output leaves through shared memory + TMA tile stores
   mmae_gemm_epilogue ep;
 };
 
@@ -41,7 +42,8 @@ struct GemmSmem {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
+  static constexpr int TOTAL = BIAS_OFFSET + BN * 4 + 1024;  // + barriers + bias tile + alignment slack
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -51,10 +53,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 
 
 // Fused epilogue for 32 consecutive accumulator columns of one output row (held by one thread).
+// `sbias`: the 32 bias values of this chunk staged in shared memory (or nullptr).  Reading the bias with per-group
+// global loads inside this loop cost 30-40 % of the kernel (measured: 962 -> 673 TF/s at 12672x3072x768).
 __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&r)[32], int row, bool row_ok, int nb, const GemmParams& p,
-                                                 bool first_split, bool atomic_out) {
+                                                 bool first_split, bool atomic_out, const float* sbias) {
   const mmae_gemm_epilogue& ep = p.ep;
-  const float* bias = first_split ? ep.bias : nullptr;
+  const float* bias = sbias;
   const float* resid = first_split ? ep.residual : nullptr;
   const bf16* zptr = reinterpret_cast<const bf16*>(ep.dgelu_z);
   bf16* preact = reinterpret_cast<bf16*>(ep.preact_bf16);
@@ -68,8 +72,8 @@ __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&r)[32], int ro
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * ep.alpha;
     if (bias) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n + 4));
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + g * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + g * 8 + 4);
       v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
       v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     }
@@ -216,6 +220,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
     }
   } else if (nkb > 0) {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
+    float* sbias = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+    const bool use_bias = p.ep.bias != nullptr && blockIdx.z == 0;
+    if (use_bias) {
+      for (int c = (warp - 2) * 32 + lane; c < BN; c += 128) sbias[c] = n0 + c < p.N ? __ldg(p.ep.bias + n0 + c) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -231,7 +241,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), r);
       tc_wait_ld();
-      epilogue_chunk32(r, row, row_ok, nb, p, first_split, atomic_out);
+      epilogue_chunk32(r, row, row_ok, nb, p, first_split, atomic_out, use_bias ? sbias + c * 32 : nullptr);
     }
   }
 
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch_gemm1(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int split_k,
+int launch_gemm1(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&, const GemmParams& p, int split_k,
                  cudaStream_t stream) {
   constexpr int STAGES = 3;
   using L = GemmSmem<BN, STAGES>;
@@ -261,6 +271,49 @@ int launch_gemm1(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParam
 }
 
 
+// TMA-store epilogue for 32 accumulator columns: alpha, bias, optional GELU, bf16 pack, then one 64-byte row per lane
+// into this warp's 32x32 staging tile (SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3), which
+// makes the warp's st.shared.v4 conflict-free) and one bulk tensor store per warp.  Per-lane global stores touch 32
+// different 128-byte lines per instruction, i.e. ~4096 L1 tag cycles per 128x256 tile - more than the MMA time of a
+// K <= 512 tile; the TMA unit writes full rows instead and clips the M / N edges itself.
+__device__ __forceinline__ void epilogue_chunk32_tma(const uint32_t (&r)[32], const GemmParams& p, const float* sbias,
+                                                     uint8_t* stage, int lane, const CUtensorMap* tmC, int col, int row0) {
+  const mmae_gemm_epilogue& ep = p.ep;
+  uint32_t packed[16];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]) * ep.alpha;
+    if (sbias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(sbias + g * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(sbias + g * 8 + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (ep.act == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) packed[g * 4 + i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  }
+  // the previous store of this warp must have finished reading the staging tile
+  if (lane == 0) bulk_wait_read_all();
+  __syncwarp();
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    *reinterpret_cast<uint4*>(stage + lane * 64 + ((g ^ sw) << 4)) =
+        make_uint4(packed[g * 4], packed[g * 4 + 1], packed[g * 4 + 2], packed[g * 4 + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmC, stage, col, row0);
+    bulk_commit_group();
+  }
+}
+
 // =====================================================================================================================
 // v2: persistent CTAs (one per SM), double-buffered TMEM accumulators: the epilogue of work item i overlaps the
 // TMA/MMA mainloop of item i+1.  BN = 256 halves the shared-memory operand bandwidth per MMA relative to BN = 128
@@ -276,8 +329,11 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;       // one 32x32 bf16 staging tile (2 KB) per epilogue warp
+  static constexpr int BAR_OFFSET = STORE_OFFSET + EPI_WARPS * 2048;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 512;             // 2 x BN floats (double-buffered per work item)
+  static constexpr int TOTAL = BIAS_OFFSET + 2 * BN * 4 + 1024;
+  static_assert(TOTAL <= 232448, "persistent GEMM exceeds the 227 KB shared-memory limit");
   static constexpr uint32_t TMEM_COLS = BN > 128 ? 512 : 256;  // two accumulators, power-of-two allocation
 };
 
@@ -288,7 +344,7 @@ struct Gemm2Sched {
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
     gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                const GemmParams p, const Gemm2Sched sc) {
+                                const __grid_constant__ CUtensorMap tmC, const GemmParams p, const Gemm2Sched sc) {
   using C = Gemm2Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -307,6 +363,7 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
     if (elect_one()) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
+      if (p.tma_store) tma_prefetch_desc(&tmC);
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -422,6 +479,15 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
       decode(item, m0, n0, kb_begin, nkb, z);
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      // stage this tile's bias in shared memory while the MMAs run; buffer (it & 1) was last read two items ago and
+      // every epilogue warp has passed the previous item's barrier since
+      float* sbias = reinterpret_cast<float*>(smem + C::BIAS_OFFSET) + buf * BN;
+      const bool use_bias = p.ep.bias != nullptr && z == 0;
+      if (p.ep.bias != nullptr) {
+        if (use_bias)
+          for (int c = e * 32 + lane; c < BN; c += C::EPI_WARPS * 32) sbias[c] = n0 + c < p.N ? __ldg(p.ep.bias + n0 + c) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(C::EPI_WARPS * 32) : "memory");
+      }
       mbar_wait(&tmem_full_bar[buf], acc_phase);
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
@@ -437,12 +503,17 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN + col0 + c * 32), r);
         tc_wait_ld();
-        epilogue_chunk32(r, row, row_ok, nb, p, first_split, atomic_out);
+        if (p.tma_store)
+          epilogue_chunk32_tma(r, p, use_bias ? sbias + col0 + c * 32 : nullptr, smem + C::STORE_OFFSET + e * 2048, lane,
+                               &tmC, nb, m0 + q * 32);
+        else
+          epilogue_chunk32(r, row, row_ok, nb, p, first_split, atomic_out, use_bias ? sbias + col0 + c * 32 : nullptr);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
+    if (p.tma_store && lane == 0) bulk_wait_all();   // stores must have drained before the CTA's shared memory goes away
   }
 
   tc_fence_before();
@@ -451,7 +522,8 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int split_k, cudaStream_t stream) {
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int split_k,
+                 cudaStream_t stream) {
   using C = Gemm2Cfg<BN>;
   auto kern = gemm_bf16_persistent_kernel<BN, A_MN, B_MN>;
   static bool configured = false;
@@ -466,7 +538,7 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParam
   sc.total = sc.tiles_m * sc.tiles_n * split_k;
   const int grid = std::min(sc.total, sm_count());
   const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K, (A_MN ? 1 : 0) | (B_MN ? 2 : 0) | (split_k << 8));
-  kern<<<grid, C::THREADS, C::TOTAL, stream>>>(tmA, tmB, p, sc);
+  kern<<<grid, C::THREADS, C::TOTAL, stream>>>(tmA, tmB, tmC, p, sc);
   if (prof) gemm_profile_end(stream);
   count_launch();
   MMAE_LAUNCH_OK();
@@ -482,6 +554,17 @@ static int g_gemm_variant = []() {
   const char* e = getenv("MMAE_GEMM_VARIANT");
   return e ? atoi(e) : -1;
 }();
+
+// MMAE_GEMM_TMA_STORE=0 (or mmae_gemm_set_variant(v | 0x100)) falls back to per-lane global stores (A/B measurements)
+static int g_gemm_tma_store = []() {
+  const char* e = getenv("MMAE_GEMM_TMA_STORE");
+  return e ? atoi(e) : 1;
+}();
+
+extern "C" int mmae_gemm_set_tma_store(int enable) {
+  g_gemm_tma_store = enable != 0;
+  return MMAE_OK;
+}
 
 extern "C" int mmae_gemm_set_variant(int variant) {
   g_gemm_variant = variant;
@@ -562,13 +645,21 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   p.num_kb = num_kb;
   p.kb_per_split = kb_per_split;
   p.ep = *ep;
+  // bf16-only linear / GELU epilogues of the persistent kernels leave through TMA tile stores
+  p.tma_store = (g_gemm_tma_store && variant != 0 && ep->out_bf16 && !ep->out_f32 && !ep->preact_bf16 && !ep->dgelu_z &&
+                 !ep->residual && split_k == 1 && !ep->accumulate) ? 1 : 0;
+  CUtensorMap tmC = tmA;
+  if (p.tma_store) {
+    rc = make_tmap_2d_bf16_store(&tmC, ep->out_bf16, (uint64_t)M, (uint64_t)N, (uint64_t)ep->ld_out_bf16);
+    if (rc) return rc;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define MMAE_DISPATCH(FN, ...)                                                                   \
   do {                                                                                           \
-    if (!a_mn_major && !b_mn_major) return FN<__VA_ARGS__, false, false>(tmA, tmB, p, split_k, st); \
-    if (!a_mn_major && b_mn_major) return FN<__VA_ARGS__, false, true>(tmA, tmB, p, split_k, st);   \
-    if (a_mn_major && !b_mn_major) return FN<__VA_ARGS__, true, false>(tmA, tmB, p, split_k, st);   \
-    return FN<__VA_ARGS__, true, true>(tmA, tmB, p, split_k, st);                                  \
+    if (!a_mn_major && !b_mn_major) return FN<__VA_ARGS__, false, false>(tmA, tmB, tmC, p, split_k, st); \
+    if (!a_mn_major && b_mn_major) return FN<__VA_ARGS__, false, true>(tmA, tmB, tmC, p, split_k, st);   \
+    if (a_mn_major && !b_mn_major) return FN<__VA_ARGS__, true, false>(tmA, tmB, tmC, p, split_k, st);   \
+    return FN<__VA_ARGS__, true, true>(tmA, tmB, tmC, p, split_k, st);                                  \
   } while (0)
   if (variant == 2) MMAE_DISPATCH(launch_gemm2, 256);
   if (variant == 3) MMAE_DISPATCH(launch_gemm2, 192);

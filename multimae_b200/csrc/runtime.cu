@@ -107,6 +107,25 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return MMAE_OK;
 }
 
+// Output-tile map for the GEMM epilogue's TMA stores: box = 32 rows x 32 bf16 columns (64-byte rows, SWIZZLE_64B).
+int make_tmap_2d_bf16_store(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+  encode_tiled_fn fn = get_encode_fn();
+  if (!fn) return MMAE_ERR_CUDA;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(store) failed: %d (rows=%llu cols=%llu ld=%llu base=%p)", (int)r,
+                   (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, base);
+    return MMAE_ERR_CUDA;
+  }
+  return MMAE_OK;
+}
+
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1,
                       uint64_t s2, uint32_t b0, uint32_t b1, uint32_t b2) {
   encode_tiled_fn fn = get_encode_fn();

@@ -233,18 +233,24 @@ for (M, N, K_, a_mn, b_mn, split) in [(12672, 2304, 768, 0, 0, 1), (12672, 768, 
 
 # epilogue cost: same GEMM with / without bias, bf16 vs fp32 output
 LIB.lib().mmae_gemm_set_variant(-1)
-for (M, N, K_) in [(12672, 3072, 768), (12672, 2304, 768), (25088, 1024, 256)]:
+for (M, N, K_) in [(12672, 3072, 768), (12672, 2304, 768), (12672, 768, 768), (25088, 1024, 256), (25088, 256, 256),
+                   (25088, 768, 256), (25088, 256, 1024)]:
     A = rand_bf16(M, K_)
     B = rand_bf16(N, K_)
     bias = torch.randn(N, device=dev)
     ob = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     of = torch.empty(M, N, device=dev)
     fl = 2.0 * M * N * K_
-    t0 = time_it(lambda: KN.gemm(A, B, out_bf16=ob))
-    t1 = time_it(lambda: KN.gemm(A, B, bias=bias, out_bf16=ob))
-    t2 = time_it(lambda: KN.gemm(A, B, bias=bias, out_f32=of))
-    print("epilogue M=%d N=%d K=%d: plain bf16 %.3f ms (%.0f TF/s) | +bias %.3f ms (%.0f) | +bias fp32-out %.3f ms (%.0f)" %
-          (M, N, K_, t0, fl / t0 / 1e9, t1, fl / t1 / 1e9, t2, fl / t2 / 1e9), flush=True)
+    for tma in (1, 0):
+        LIB.lib().mmae_gemm_set_tma_store(tma)
+        t0 = time_it(lambda: KN.gemm(A, B, out_bf16=ob))
+        t1 = time_it(lambda: KN.gemm(A, B, bias=bias, out_bf16=ob))
+        t2 = time_it(lambda: KN.gemm(A, B, bias=bias, out_f32=of))
+        t3 = time_it(lambda: torch.nn.functional.linear(A, B, bias.to(torch.bfloat16)))
+        print("epilogue tma_store=%d M=%d N=%d K=%d: plain bf16 %.3f ms (%.0f TF/s) | +bias %.3f ms (%.0f) | +bias fp32-out "
+              "%.3f ms (%.0f) | cublas+bias %.3f ms (%.0f)" %
+              (tma, M, N, K_, t0, fl / t0 / 1e9, t1, fl / t1 / 1e9, t2, fl / t2 / 1e9, t3, fl / t3 / 1e9), flush=True)
+LIB.lib().mmae_gemm_set_tma_store(1)
 
 # attention timing at the encoder shape
 B_, H_, N_, dh_ = 128, 12, 99, 64

@@ -27,6 +27,7 @@ def KN():
     from multimae_b200 import kernels
     yield kernels
     L.lib().mmae_gemm_set_variant(-1)
+    L.lib().mmae_gemm_set_tma_store(1)
     L.lib().mmae_attention_set_tc(3)
 
 
@@ -84,6 +85,31 @@ def test_gemm_fused_epilogues(dev, KN, variant):
     out = torch.ones(M, N, device=dev)
     KN.gemm(A, B, out_f32=out, accumulate=True, alpha=0.5)
     assert rel_l2(out, 1 + 0.5 * acc) < 3e-5
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (200, 136, 200), (396, 2128, 256), (1000, 776, 512), (2560, 2304, 768),
+                                   (25088, 256, 256)])
+def test_gemm_tma_store_epilogue(dev, KN, variant, shape):
+    """bf16 outputs through shared memory + TMA tile stores: ragged M / N edges, a strided output view, bias and GELU;
+    bit-identical to the per-lane store path and untouched bytes outside the [M, N] view."""
+    from multimae_b200 import _lib as L
+    L.lib().mmae_gemm_set_variant(variant)
+    M, N, K = shape
+    A, B = _bf16(dev, M, K), _bf16(dev, N, K)
+    bias = torch.randn(N, device=dev)
+    acc = A.float() @ B.float().t()
+    for kw, ref in (({}, acc), ({"bias": bias}, acc + bias), ({"bias": bias, "act": 1}, torch.nn.functional.gelu(acc + bias)),
+                    ({"alpha": 0.25}, 0.25 * acc)):
+        outs = []
+        for tma in (1, 0):
+            L.lib().mmae_gemm_set_tma_store(tma)
+            buf = torch.full((M + 3, N + 16), 7.0, device=dev, dtype=torch.bfloat16)
+            KN.gemm(A, B, out_bf16=buf[:M, :N], **kw)
+            assert bool((buf[M:] == 7).all()) and bool((buf[:, N:] == 7).all()), (variant, shape, kw.keys(), tma)
+            outs.append(buf[:M, :N].clone())
+        assert rel_l2(outs[0], ref) < 4e-3, (variant, shape, list(kw), rel_l2(outs[0], ref))
+        assert torch.equal(outs[0], outs[1]), (variant, shape, list(kw))
 
 
 def test_gemm_rejects_bad_arguments(dev, KN):
