@@ -56,6 +56,9 @@ int64_t mmae_profile_gemm_dump(char* buf_host, int64_t capacity);
  * split_k > 1 (or accumulate != 0) accumulates into out_f32 with fp32 atomics; the destination must have
  * been zeroed (or hold the value to accumulate onto); bias/residual are applied by split 0 only; act,
  * dgelu_z, preact_bf16 and out_bf16 are not allowed with split_k > 1.
+ * split_k <= 0: automatic - split count and tile width are chosen together so that one wave of ~SM-count work items
+ * covers the problem (fp32-only linear epilogues; anything else runs unsplit).  The accumulation then uses TMA
+ * reduce-add tiles (cp.reduce.async.bulk.tensor) instead of per-lane atomics.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct mmae_gemm_epilogue {
   float alpha;
@@ -284,6 +287,14 @@ int mmae_masked_loss_forward(int kind, int norm_pix, float label_smoothing, cons
 int mmae_masked_loss_backward(int kind, int norm_pix, float label_smoothing, const float* pred, const void* target,
                               const int64_t* mask, int B, int C, int H, int W, int scale, const float* ws,
                               const float* grad_out, float* dpred, void* stream);
+
+/* bf16 weight mirror.  Registers a bf16 twin (same element count and layout) of a flat fp32 parameter buffer; pass
+ * mirror_bf16 = NULL to unregister.  While registered: (1) the block / decoder / tail orchestrators take the bf16 GEMM
+ * operand of any weight that lies inside `params_f32` (at an offset that is a multiple of 8 elements) from the twin
+ * instead of casting it per call, (2) mmae_adamw_step on `params_f32` also writes the updated values to the twin.  The
+ * caller keeps the twin in sync after any other modification of the parameters (mmae_cast_f32_to_bf16 over the buffer).
+ * Replaces the per-Linear autocast weight casts of the reference (torch.cuda.amp.autocast, run_pretraining_multimae.py:452). */
+int mmae_weight_mirror_register(const float* params_f32, void* mirror_bf16, int64_t n);
 
 /* ------------------------------------------------------------------------------------------------
  * Flat-buffer gradient post-processing and AdamW (utils/native_scaler.py:34-36, 49-62; torch.optim.AdamW as built

@@ -172,6 +172,7 @@ SIGNATURES = {
     "mmae_masked_loss_backward": (c_int, [c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                           c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmae_grad_unscale_norm": (c_int, [c_void_p, c_i64, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "mmae_weight_mirror_register": (c_int, [c_void_p, c_void_p, c_i64]),
     "mmae_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_float, c_float, c_float, c_float,
                                 c_float, c_int, c_void_p, c_void_p, c_void_p]),
     "mmae_unpatchify": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -108,8 +108,11 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 // the erf tail and the Gaussian density of the derivative.
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf_unnorm) {
   const float ax = fabsf(x) * 0.70710678118654752440f;          // |x| / sqrt(2)
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  const float e = exp2f(-0.72134752044448170368f * x * x);      // exp(-x^2 / 2)
+  // one MUFU.RCP + one MUFU.EX2 per element (the IEEE __frcp_rn / exp2f sequences cost ~3x the instructions, and the
+  // streaming GELU kernels sit within 30 % of the FP32-issue limit at HBM speed)
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170368f * x * x));   // exp(-x^2 / 2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
@@ -128,6 +131,24 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   float cdf, e;
   gelu_parts(x, cdf, e);
   return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
+// 16-byte streaming load: read once, do not keep in L1 (activations streamed by the element-wise kernels)
+__device__ __forceinline__ uint4 ld_stream_16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// same for a buffer the kernel also writes (in-place updates): no .nc
+__device__ __forceinline__ uint4 ld_stream_16_rw(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -185,6 +206,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
 // 2D tile store shared -> global (bulk async group completion); out-of-bounds parts of the box are clipped by the TMA unit
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// same, but the tile is ADDED to global memory (element type from the tensor map): split-K / gradient accumulation
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
                :
                : "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
@@ -320,7 +348,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_cols, uint32_t box_rows);
 // 3D bf16 tensor [d2, d1, d0] (d0 innermost) with element strides s1, s2; 128B swizzle
-int make_tmap_2d_bf16_store(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld);
+int make_tmap_2d_store(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld);
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1,
                       uint64_t s2, uint32_t b0, uint32_t b1, uint32_t b2);
 

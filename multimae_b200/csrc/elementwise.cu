@@ -74,28 +74,41 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const void* __restrict
 // instructions/element of erf-GELU overrun; a full-occupancy streaming kernel does not.
 template <bool BACKWARD>
 __global__ void __launch_bounds__(256) gelu_stream_kernel(const bf16* __restrict__ z, bf16* __restrict__ io, int64_t n) {
+  constexpr int U = 2;   // independent 16-byte loads in flight per thread and stream
   const int64_t stride = int64_t(gridDim.x) * blockDim.x * 8;
-  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
-    const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + i));
-    const uint32_t* zu = reinterpret_cast<const uint32_t*>(&zv);
-    uint4 ov;
-    uint32_t* ou = reinterpret_cast<uint32_t*>(&ov);
-    if constexpr (BACKWARD) {
-      const uint4 dv = *reinterpret_cast<const uint4*>(io + i);
-      const uint32_t* du = reinterpret_cast<const uint32_t*>(&dv);
+  for (int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i0 < n; i0 += stride * U) {
+    uint4 zv[U], dv[U];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 a = unpack_bf16x2(zu[k]), d = unpack_bf16x2(du[k]);
-        ou[k] = pack_bf16x2(d.x * dgelu_erf(a.x), d.y * dgelu_erf(a.y));
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 a = unpack_bf16x2(zu[k]);
-        ou[k] = pack_bf16x2(gelu_erf(a.x), gelu_erf(a.y));
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < n) {
+        zv[u] = ld_stream_16(z + i);
+        if constexpr (BACKWARD) dv[u] = ld_stream_16_rw(io + i);
       }
     }
-    *reinterpret_cast<uint4*>(io + i) = ov;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= n) break;
+      const uint32_t* zu = reinterpret_cast<const uint32_t*>(&zv[u]);
+      uint4 ov;
+      uint32_t* ou = reinterpret_cast<uint32_t*>(&ov);
+      if constexpr (BACKWARD) {
+        const uint32_t* du = reinterpret_cast<const uint32_t*>(&dv[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = unpack_bf16x2(zu[k]), d = unpack_bf16x2(du[k]);
+          ou[k] = pack_bf16x2(d.x * dgelu_erf(a.x), d.y * dgelu_erf(a.y));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = unpack_bf16x2(zu[k]);
+          ou[k] = pack_bf16x2(gelu_erf(a.x), gelu_erf(a.y));
+        }
+      }
+      *reinterpret_cast<uint4*>(io + i) = ov;
+    }
   }
 }
 
@@ -110,23 +123,37 @@ __global__ void __launch_bounds__(256) dgelu_colsum_kernel(const bf16* __restric
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (col < N) {
-    for (int r = r0 + threadIdx.y; r < min(r0 + CS_ROWS, M); r += 8) {
-      const uint4 zv = __ldg(reinterpret_cast<const uint4*>(z + int64_t(r) * ld + col));
-      const uint4 dv = *reinterpret_cast<const uint4*>(dz + int64_t(r) * ld + col);
-      const uint32_t* zu = reinterpret_cast<const uint32_t*>(&zv);
-      const uint32_t* du = reinterpret_cast<const uint32_t*>(&dv);
-      uint4 ov;
-      uint32_t* ou = reinterpret_cast<uint32_t*>(&ov);
+    const int r_end = min(r0 + CS_ROWS, M);
+    constexpr int U = 4;   // rows in flight per thread (loads issued before any of the in-place stores)
+    for (int rb = r0 + threadIdx.y; rb < r_end; rb += 8 * U) {
+      uint4 zv[U], dv[U];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 a = unpack_bf16x2(zu[k]), d = unpack_bf16x2(du[k]);
-        const float o0 = d.x * dgelu_erf(a.x), o1 = d.y * dgelu_erf(a.y);
-        ou[k] = pack_bf16x2(o0, o1);
-        const float2 rb = unpack_bf16x2(ou[k]);      // sum what is stored (bf16-rounded), as a separate pass would
-        acc[2 * k] += rb.x;
-        acc[2 * k + 1] += rb.y;
+      for (int u = 0; u < U; ++u) {
+        const int r = rb + 8 * u;
+        if (r < r_end) {
+          zv[u] = ld_stream_16(z + int64_t(r) * ld + col);
+          dv[u] = ld_stream_16_rw(dz + int64_t(r) * ld + col);
+        }
       }
-      *reinterpret_cast<uint4*>(dz + int64_t(r) * ld + col) = ov;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = rb + 8 * u;
+        if (r >= r_end) break;
+        const uint32_t* zu = reinterpret_cast<const uint32_t*>(&zv[u]);
+        const uint32_t* du = reinterpret_cast<const uint32_t*>(&dv[u]);
+        uint4 ov;
+        uint32_t* ou = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = unpack_bf16x2(zu[k]), d = unpack_bf16x2(du[k]);
+          const float o0 = d.x * dgelu_erf(a.x), o1 = d.y * dgelu_erf(a.y);
+          ou[k] = pack_bf16x2(o0, o1);
+          const float2 rbk = unpack_bf16x2(ou[k]);      // sum what is stored (bf16-rounded), as a separate pass would
+          acc[2 * k] += rbk.x;
+          acc[2 * k + 1] += rbk.y;
+        }
+        *reinterpret_cast<uint4*>(dz + int64_t(r) * ld + col) = ov;
+      }
     }
   }
 #pragma unroll

@@ -32,7 +32,7 @@ struct GemmParams {
   int M, N, K;
   int num_kb;        // total k-blocks (ceil(K / BK))
   int kb_per_split;  // k-blocks handled by one split
-  int tma_store;     // persistent kernel: bf16 output leaves through shared memory + TMA tile stores
+  int tma_store;     // persistent kernel, output through shared memory + TMA: 1 = bf16 store, 2 = fp32 store, 3 = fp32 add
   mmae_gemm_epilogue ep;
 };
 
@@ -314,6 +314,41 @@ __device__ __forceinline__ void epilogue_chunk32_tma(const uint32_t (&r)[32], co
   }
 }
 
+// fp32 flavour: two 32x16 boxes (64-byte rows) per 32-column chunk, stored or ADDED (cp.reduce ... .add: split-K partial
+// sums and gradient accumulation without per-lane red.global instructions).
+__device__ __forceinline__ void epilogue_chunk32_tma_f32(const uint32_t (&r)[32], const GemmParams& p, const float* sbias,
+                                                         uint8_t* stage, int lane, const CUtensorMap* tmC, int col, int row0,
+                                                         bool add) {
+  const mmae_gemm_epilogue& ep = p.ep;
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (col + h * 16 >= p.N) break;   // warp-uniform
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[h * 16 + i]) * ep.alpha;
+    if (sbias) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float4 b = *reinterpret_cast<const float4*>(sbias + h * 16 + g * 4);
+        v[g * 4] += b.x; v[g * 4 + 1] += b.y; v[g * 4 + 2] += b.z; v[g * 4 + 3] += b.w;
+      }
+    }
+    if (lane == 0) bulk_wait_read_all();
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      *reinterpret_cast<float4*>(stage + lane * 64 + ((g ^ sw) << 4)) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (add) tma_reduce_add_2d(tmC, stage, col + h * 16, row0);
+      else tma_store_2d(tmC, stage, col + h * 16, row0);
+      bulk_commit_group();
+    }
+  }
+}
+
 // =====================================================================================================================
 // v2: persistent CTAs (one per SM), double-buffered TMEM accumulators: the epilogue of work item i overlaps the
 // TMA/MMA mainloop of item i+1.  BN = 256 halves the shared-memory operand bandwidth per MMA relative to BN = 128
@@ -503,9 +538,12 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN + col0 + c * 32), r);
         tc_wait_ld();
-        if (p.tma_store)
+        if (p.tma_store == 1)
           epilogue_chunk32_tma(r, p, use_bias ? sbias + col0 + c * 32 : nullptr, smem + C::STORE_OFFSET + e * 2048, lane,
                                &tmC, nb, m0 + q * 32);
+        else if (p.tma_store != 0)
+          epilogue_chunk32_tma_f32(r, p, use_bias ? sbias + col0 + c * 32 : nullptr, smem + C::STORE_OFFSET + e * 2048, lane,
+                                   &tmC, nb, m0 + q * 32, p.tma_store == 3);
         else
           epilogue_chunk32(r, row, row_ok, nb, p, first_split, atomic_out, use_bias ? sbias + col0 + c * 32 : nullptr);
       }
@@ -581,8 +619,38 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   MMAE_CHECK((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
              MMAE_ERR_ARG, "mmae_gemm_bf16: operands must be 16-byte aligned");
   MMAE_CHECK(ep->out_f32 || ep->out_bf16, MMAE_ERR_ARG, "mmae_gemm_bf16: no output");
-  if (split_k < 1) split_k = 1;
   const int num_kb = ceil_div(K, BK);
+  int variant = g_gemm_variant;
+  if (split_k <= 0 && !(ep->out_f32 && !ep->out_bf16 && !ep->preact_bf16 && !ep->dgelu_z && ep->act == 0)) split_k = 1;
+  if (split_k <= 0) {
+    // auto split-K (weight gradients: small M x N, long K).  Joint choice of tile width and split count: one wave of
+    // ~SM-count work items; an item costs ~BN * (k-blocks + 6), the 6 standing for the fp32 reduce-add epilogue.
+    // Measured (B200, K = 25088): 256x256 -> BN 128 x 37 splits 11.8 us vs BN 256 x 66 splits 22 us.
+    const int sms = sm_count();
+    const int tm = ceil_div(M, BM);
+    const int cand_bn[3] = {128, 192, 256};
+    const int cand_var[3] = {1, 3, 2};
+    long best_cost = -1;
+    int best_split = 1, best_var = 1;
+    for (int i = 0; i < 3; ++i) {
+      if (variant > 0 && cand_var[i] != variant) continue;
+      if (cand_bn[i] > 128 && N < cand_bn[i]) continue;
+      const int tiles = tm * ceil_div(N, cand_bn[i]);
+      int s_ = std::max(1, sms / tiles);
+      s_ = std::min(s_, std::max(1, num_kb / 4));
+      const int kbps = ceil_div(num_kb, s_);
+      s_ = ceil_div(num_kb, kbps);
+      const long rounds = (long(tiles) * s_ + sms - 1) / sms;
+      const long cost = rounds * cand_bn[i] * (kbps + 6);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_split = s_;
+        best_var = cand_var[i];
+      }
+    }
+    split_k = best_split;
+    if (variant < 0) variant = best_var;
+  }
   if (split_k > num_kb) split_k = num_kb;
   const int kb_per_split = ceil_div(num_kb, split_k);
   split_k = ceil_div(num_kb, kb_per_split);  // no empty splits
@@ -600,7 +668,6 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
 
   // kernel variant: 0 = v1 (one tile per CTA, BN=128), 1 = persistent BN=128, 2 = persistent BN=256.
   // MMAE_GEMM_VARIANT overrides the heuristic (for A/B measurements).
-  int variant = g_gemm_variant;
   if (variant < 0) {
     // tile-quantisation model: persistent CTAs process ceil(tiles / SMs) rounds; a round costs ~(BN + c) where c
     // stands for the per-tile fixed work (pipeline fill, epilogue tail).  Pick the cheapest of BN = 128 / 192 / 256.
@@ -646,12 +713,19 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   p.kb_per_split = kb_per_split;
   p.ep = *ep;
   // bf16-only linear / GELU epilogues of the persistent kernels leave through TMA tile stores
-  p.tma_store = (g_gemm_tma_store && variant != 0 && ep->out_bf16 && !ep->out_f32 && !ep->preact_bf16 && !ep->dgelu_z &&
-                 !ep->residual && split_k == 1 && !ep->accumulate) ? 1 : 0;
+  // and so do fp32-only linear epilogues: plain store, or reduce-add for split-K / accumulate
+  p.tma_store = 0;
   CUtensorMap tmC = tmA;
-  if (p.tma_store) {
-    rc = make_tmap_2d_bf16_store(&tmC, ep->out_bf16, (uint64_t)M, (uint64_t)N, (uint64_t)ep->ld_out_bf16);
-    if (rc) return rc;
+  if (g_gemm_tma_store && variant != 0 && !ep->preact_bf16 && !ep->dgelu_z && !ep->residual) {
+    if (ep->out_bf16 && !ep->out_f32 && split_k == 1 && !ep->accumulate) {
+      p.tma_store = 1;
+      rc = make_tmap_2d_store(&tmC, ep->out_bf16, 2, (uint64_t)M, (uint64_t)N, (uint64_t)ep->ld_out_bf16);
+      if (rc) return rc;
+    } else if (ep->out_f32 && !ep->out_bf16 && ep->act == 0 && ep->ld_out_f32 % 4 == 0) {
+      p.tma_store = (split_k > 1 || ep->accumulate) ? 3 : 2;
+      rc = make_tmap_2d_store(&tmC, ep->out_f32, 4, (uint64_t)M, (uint64_t)N, (uint64_t)ep->ld_out_f32);
+      if (rc) return rc;
+    }
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define MMAE_DISPATCH(FN, ...)                                                                   \

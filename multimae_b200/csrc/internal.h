@@ -16,6 +16,9 @@ struct TaskEmbGradPtrs {
 
 void count_launch();
 
+// bf16 weight mirror registry (runtime.cu): the bf16 twin of a registered fp32 parameter buffer, or nullptr
+const bf16* mirror_lookup(const float* w);
+
 int launch_embed_gather(const mmae_embed_layout& L, const mmae_embed_inputs& in, const int64_t* ids_keep, int B, int T,
                         bf16* A, int* row_task, int* row_patch, cudaStream_t st);
 int launch_embed_assemble(const float* Cmat, const mmae_embed_params& prm, const int* row_task, const int* row_patch,

@@ -74,7 +74,46 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
 
 // Backward.  dx_out = dx_resid (optional) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * gamma.
 // dgamma/dbeta: per-lane register partials over the block's rows -> smem reduce over warps -> fp32 atomics.
-constexpr int LNB_ROWS = 64;  // rows per block
+//
+// Persistent: the grid is one wave (blocks = SMs x resident blocks), warps stride over the rows, so there is no partial
+// last wave (12672 rows in 64-row blocks were 198 blocks on 148 SMs: a third of the time ran at 1/3 occupancy) and the
+// column-sum atomics drop to one set per resident block.  The next row's x / dy loads are issued before the current
+// row's reductions (the per-lane column accumulators cap residency at 8 warps per SM for D = 768, so a warp has to
+// carry its own memory-level parallelism).
+template <int NVEC, bool DY_BF16>
+struct LnRow {
+  float4 x[NVEC];
+  float4 d[DY_BF16 ? (NVEC + 1) / 2 : NVEC];   // bf16 dy stays packed: 8 bytes per float4 slot
+};
+
+template <int NVEC, bool DY_BF16>
+__device__ __forceinline__ void ln_row_load(LnRow<NVEC, DY_BF16>& r, const void* dy_, int64_t lddy, const float* x,
+                                            int64_t ldx, int row, int lane) {
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    r.x[i] = __ldg(reinterpret_cast<const float4*>(x + int64_t(row) * ldx + c));
+    if constexpr (DY_BF16) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + int64_t(row) * lddy + c));
+      float* slot = reinterpret_cast<float*>(&r.d[i >> 1]) + (i & 1) * 2;
+      slot[0] = __uint_as_float(u.x);
+      slot[1] = __uint_as_float(u.y);
+    } else {
+      r.d[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + int64_t(row) * lddy + c));
+    }
+  }
+}
+
+template <int NVEC, bool DY_BF16>
+__device__ __forceinline__ float4 ln_row_dy(const LnRow<NVEC, DY_BF16>& r, int i) {
+  if constexpr (DY_BF16) {
+    const float* slot = reinterpret_cast<const float*>(&r.d[i >> 1]) + (i & 1) * 2;
+    const float2 a = unpack_bf16x2(__float_as_uint(slot[0])), b = unpack_bf16x2(__float_as_uint(slot[1]));
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    return r.d[i];
+  }
+}
 
 template <int NVEC, bool DY_BF16>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __restrict__ dy_, int64_t lddy,
@@ -89,48 +128,59 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __res
                                                                float* __restrict__ dx_colsum, int M) {
   constexpr int D = NVEC * 128;
   __shared__ float4 red[LN_WARPS][32];
+  __shared__ float4 sgamma[NVEC * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 dg[NVEC], db[NVEC], gm[NVEC], cs[NVEC];
+  for (int i = threadIdx.x; i < NVEC * 32; i += LN_WARPS * 32) sgamma[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+  __syncthreads();
+  float4 dg[NVEC], db[NVEC], cs[NVEC];
 #pragma unroll
   for (int i = 0; i < NVEC; ++i) {
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4));
   }
-  const int r_end = min((blockIdx.x + 1) * LNB_ROWS, M);
-  for (int row = blockIdx.x * LNB_ROWS + warp; row < r_end; row += LN_WARPS) {
-    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
-    float4 xh[NVEC], g[NVEC];
+  const int row_stride = gridDim.x * LN_WARPS;
+  int row = blockIdx.x * LN_WARPS + warp;
+  LnRow<NVEC, DY_BF16> cur, nxt;
+  float mean = 0.f, rstd = 0.f, mean_n = 0.f, rstd_n = 0.f;
+  if (row < M) {
+    ln_row_load(cur, dy_, lddy, x, ldx, row, lane);
+    mean = __ldg(mean_in + row);
+    rstd = __ldg(rstd_in + row);
+  }
+  for (; row < M; row += row_stride) {
+    const int row_n = row + row_stride;
+    if (row_n < M) {   // next row's loads fly while this row is reduced and written
+      ln_row_load(nxt, dy_, lddy, x, ldx, row_n, lane);
+      mean_n = __ldg(mean_in + row_n);
+      rstd_n = __ldg(rstd_in + row_n);
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + int64_t(row) * ldx + c));
-      float4 d;
-      if constexpr (DY_BF16) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + int64_t(row) * lddy + c));
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-        d = make_float4(a.x, a.y, b.x, b.y);
-      } else {
-        d = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + int64_t(row) * lddy + c));
-      }
-      xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-      g[i] = make_float4(d.x * gm[i].x, d.y * gm[i].y, d.z * gm[i].z, d.w * gm[i].w);
-      s1 += g[i].x + g[i].y + g[i].z + g[i].w;
-      s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
-      dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+      const float4 d = ln_row_dy(cur, i);
+      const float4 gm = sgamma[i * 32 + lane];
+      const float4 xh = make_float4((cur.x[i].x - mean) * rstd, (cur.x[i].y - mean) * rstd, (cur.x[i].z - mean) * rstd,
+                                    (cur.x[i].w - mean) * rstd);
+      const float4 g = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+      s1 += g.x + g.y + g.z + g.w;
+      s2 += g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+      dg[i].x += d.x * xh.x; dg[i].y += d.y * xh.y; dg[i].z += d.z * xh.z; dg[i].w += d.w * xh.w;
       db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
     }
     const float c1 = warp_sum(s1) * (1.0f / D), c2 = warp_sum(s2) * (1.0f / D);
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
       const int c = (i * 32 + lane) * 4;
+      const float4 d = ln_row_dy(cur, i);
+      const float4 gm = sgamma[i * 32 + lane];
+      const float4 xh = make_float4((cur.x[i].x - mean) * rstd, (cur.x[i].y - mean) * rstd, (cur.x[i].z - mean) * rstd,
+                                    (cur.x[i].w - mean) * rstd);
       float4 o;
-      o.x = rstd * (g[i].x - c1 - xh[i].x * c2);
-      o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
-      o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
-      o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
+      o.x = rstd * (d.x * gm.x - c1 - xh.x * c2);
+      o.y = rstd * (d.y * gm.y - c1 - xh.y * c2);
+      o.z = rstd * (d.z * gm.z - c1 - xh.z * c2);
+      o.w = rstd * (d.w * gm.w - c1 - xh.w * c2);
       if (dx_resid) {
         const float4 r = __ldg(reinterpret_cast<const float4*>(dx_resid + int64_t(row) * ldr + c));
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -144,6 +194,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __res
         cs[i].x += o.x; cs[i].y += o.y; cs[i].z += o.z; cs[i].w += o.w;
       }
     }
+    cur = nxt;
+    mean = mean_n;
+    rstd = rstd_n;
   }
   // column reductions across the block's warps
 #pragma unroll
@@ -224,7 +277,9 @@ static int ln_backward_impl(const void* dy, int dy_is_bf16, int64_t lddy, const 
   MMAE_CHECK(dy && x && mean && rstd && gamma && dx && M > 0, MMAE_ERR_ARG, "mmae_layernorm_backward: bad args");
   MMAE_CHECK(D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && ldr % 4 == 0,
              MMAE_ERR_UNSUPPORTED, "mmae_layernorm_backward: D=%d must be a multiple of 128 and <= 1024", D);
-  dim3 grid(ceil_div(M, LNB_ROWS)), block(LN_WARPS * 32);
+  // one wave: resident blocks per SM follow from the register footprint of the per-lane column accumulators
+  const int per_sm = D <= 256 ? 3 : (D <= 384 ? 2 : 1);
+  dim3 grid(std::min(ceil_div(M, LN_WARPS), sm_count() * per_sm)), block(LN_WARPS * 32);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define LNB_CASE(NV)                                                                                              \
   case NV:                                                                                                        \

@@ -22,12 +22,17 @@ struct Carver {
   }
 };
 
-int pick_split(int M, int N, int K) {
-  const int tiles = ceil_div(M, 128) * ceil_div(N, 128);
-  int s = (2 * sm_count()) / std::max(tiles, 1);
-  const int kb = ceil_div(K, 64);
-  s = std::min(s, std::max(1, kb / 4));
-  return std::max(s, 1);
+// split-K count of the weight-gradient GEMMs: 0 = chosen by mmae_gemm_bf16 together with the tile width
+int pick_split(int, int, int) { return 0; }
+
+// bf16 operand of a weight: the registered mirror of the fp32 parameter buffer (no cast, refreshed by the optimizer
+// kernel), else the per-call saved slot (cast now in forward; already cast in backward).
+int weight_operand(const float* w, bf16** slot, int64_t n, bool cast_now, void* st) {
+  if (const bf16* m = mirror_lookup(w)) {
+    *slot = const_cast<bf16*>(m);
+    return MMAE_OK;
+  }
+  return cast_now ? mmae_cast_f32_to_bf16(w, *slot, n, st) : MMAE_OK;
 }
 
 mmae_gemm_epilogue ep_zero() {
@@ -289,10 +294,10 @@ extern "C" int mmae_block_forward(const float* x_in, float* x_out, int B, int N,
              "mmae_block_forward: bad args");
   const int M = B * N, dh = D / H;
   BlockSaved s = block_saved(saved, B, N, D, H, hidden);
-  RUN(mmae_cast_f32_to_bf16(p->qkv_w, s.wqkv, int64_t(3) * D * D, st));
-  RUN(mmae_cast_f32_to_bf16(p->proj_w, s.wproj, int64_t(D) * D, st));
-  RUN(mmae_cast_f32_to_bf16(p->fc1_w, s.w1, int64_t(hidden) * D, st));
-  RUN(mmae_cast_f32_to_bf16(p->fc2_w, s.w2, int64_t(D) * hidden, st));
+  RUN(weight_operand(p->qkv_w, &s.wqkv, int64_t(3) * D * D, true, st));
+  RUN(weight_operand(p->proj_w, &s.wproj, int64_t(D) * D, true, st));
+  RUN(weight_operand(p->fc1_w, &s.w1, int64_t(hidden) * D, true, st));
+  RUN(weight_operand(p->fc2_w, &s.w2, int64_t(D) * hidden, true, st));
   // Residual adds are NOT done in the GEMM epilogues: a row-per-lane fp32 read-modify-write there costs one L1 wavefront
   // per 16 bytes (measured 262 TF/s for the proj GEMM vs ~900 for a bf16 store).  The branch output is stored as bf16
   // (what the reference's autocast Linear produces) and the add is fused into the next streaming kernel.
@@ -318,6 +323,10 @@ extern "C" int mmae_block_backward(const float* x_in, const float* dx_out, float
   MMAE_CHECK(x_in && dx_out && dx_in && p && g && saved && ws, MMAE_ERR_ARG, "mmae_block_backward: bad args");
   const int M = B * N, dh = D / H;
   BlockSaved s = block_saved(const_cast<void*>(saved), B, N, D, H, hidden);
+  RUN(weight_operand(p->qkv_w, &s.wqkv, 0, false, st));
+  RUN(weight_operand(p->proj_w, &s.wproj, 0, false, st));
+  RUN(weight_operand(p->fc1_w, &s.w1, 0, false, st));
+  RUN(weight_operand(p->fc2_w, &s.w2, 0, false, st));
   BlockWs w = block_ws(ws, B, N, D, H, hidden);
   // ---- MLP branch
   RUN(mmae_cast_colsum_f32(dx_out, D, w.g, D, g->fc2_b, M, D, st));
@@ -363,12 +372,12 @@ extern "C" int mmae_dechead_forward(const float* enc, int De, const mmae_decoder
   HeadWs w = head_ws(ws, ix, De, H, hidden);
   cudaStream_t cst = reinterpret_cast<cudaStream_t>(st);
   RUN(mmae_cast_f32_to_bf16(enc, s.enc_b, int64_t(Mc) * De, st));
-  RUN(mmae_cast_f32_to_bf16(p->proj_context_w, s.wpc, int64_t(Dd) * De, st));
-  RUN(mmae_cast_f32_to_bf16(p->q_w, s.wq, int64_t(Dd) * Dd, st));
-  RUN(mmae_cast_f32_to_bf16(p->kv_w, s.wkv, int64_t(2) * Dd * Dd, st));
-  RUN(mmae_cast_f32_to_bf16(p->proj_w, s.wproj, int64_t(Dd) * Dd, st));
-  RUN(mmae_cast_f32_to_bf16(p->fc1_w, s.w1, int64_t(hidden) * Dd, st));
-  RUN(mmae_cast_f32_to_bf16(p->fc2_w, s.w2, int64_t(Dd) * hidden, st));
+  RUN(weight_operand(p->proj_context_w, &s.wpc, int64_t(Dd) * De, true, st));
+  RUN(weight_operand(p->q_w, &s.wq, int64_t(Dd) * Dd, true, st));
+  RUN(weight_operand(p->kv_w, &s.wkv, int64_t(2) * Dd * Dd, true, st));
+  RUN(weight_operand(p->proj_w, &s.wproj, int64_t(Dd) * Dd, true, st));
+  RUN(weight_operand(p->fc1_w, &s.w1, int64_t(hidden) * Dd, true, st));
+  RUN(weight_operand(p->fc2_w, &s.w2, int64_t(Dd) * hidden, true, st));
   // proj_context                                                   output_adapters.py:258
   RUN(linear_f32(s.enc_b, s.wpc, p->proj_context_b, nullptr, w.ctx, Mc, Dd, De, st));
   // queries / context                                              output_adapters.py:183-234
@@ -403,6 +412,12 @@ extern "C" int mmae_dechead_backward(const float* enc, int De, const mmae_decode
   const int Dd = ix.dim, B = ix.batch, P = ix.num_queries, Nc = ix.num_visible + ix.num_global;
   const int Mq = B * P, Mc = B * Nc, dh = Dd / H;
   HeadSaved s = head_saved(const_cast<void*>(saved), ix, De, H, hidden);
+  RUN(weight_operand(p->proj_context_w, &s.wpc, 0, false, st));
+  RUN(weight_operand(p->q_w, &s.wq, 0, false, st));
+  RUN(weight_operand(p->kv_w, &s.wkv, 0, false, st));
+  RUN(weight_operand(p->proj_w, &s.wproj, 0, false, st));
+  RUN(weight_operand(p->fc1_w, &s.w1, 0, false, st));
+  RUN(weight_operand(p->fc2_w, &s.w2, 0, false, st));
   HeadWs w = head_ws(ws, ix, De, H, hidden);
   cudaStream_t cst = reinterpret_cast<cudaStream_t>(st);
   // ---- MLP
@@ -489,7 +504,7 @@ extern "C" int mmae_dectail_forward(const float* x, int B, int nh, int nw, int D
   TailSaved s = tail_saved(saved, B, nh, nw, Dd, C, P);
   TailWs w = tail_ws(ws, B, nh, nw, Dd, C, P);
   RUN(mmae_cast_f32_to_bf16(x, s.x_b, int64_t(M) * Dd, st));
-  RUN(mmae_cast_f32_to_bf16(out_w, s.w_b, int64_t(Nout) * Dd, st));
+  RUN(weight_operand(out_w, &s.w_b, int64_t(Nout) * Dd, true, st));
   RUN(linear_bf16(s.x_b, s.w_b, out_b, w.y, M, Nout, Dd, st));              // output_adapters.py:274 (half precision
   RUN(mmae_unpatchify_bf16(w.y, Nout, pred, B, C, nh, nw, P, st));          //  like the autocast Linear); :277-280
   return MMAE_OK;
@@ -497,10 +512,10 @@ extern "C" int mmae_dectail_forward(const float* x, int B, int nh, int nw, int D
 
 extern "C" int mmae_dectail_backward(const float* dpred, int B, int nh, int nw, int Dd, int C, int P, const float* out_w,
                                      float* d_out_w, float* d_out_b, float* dx, const void* saved, void* ws, void* st) {
-  (void)out_w;
-  MMAE_CHECK(dpred && d_out_w && d_out_b && dx && saved && ws, MMAE_ERR_ARG, "mmae_dectail_backward: bad args");
+  MMAE_CHECK(dpred && out_w && d_out_w && d_out_b && dx && saved && ws, MMAE_ERR_ARG, "mmae_dectail_backward: bad args");
   const int M = B * nh * nw, Nout = C * P * P;
   TailSaved s = tail_saved(const_cast<void*>(saved), B, nh, nw, Dd, C, P);
+  RUN(weight_operand(out_w, &s.w_b, 0, false, st));
   TailWs w = tail_ws(ws, B, nh, nw, Dd, C, P);
   RUN(mmae_patchify_bf16(dpred, w.dy, Nout, B, C, nh, nw, P, st));
   RUN(mmae_colsum_bf16(w.dy, Nout, d_out_b, M, Nout, st));

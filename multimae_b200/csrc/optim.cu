@@ -6,6 +6,7 @@
 // mmae_adamw_step is torch.optim.AdamW's update (utils/optim_factory.py:155-174 builds it) over flat buffers.
 #include "common.cuh"
 #include "../../include/multimae_b200.h"
+#include "internal.h"
 
 namespace mmae {
 void count_launch();
@@ -53,7 +54,8 @@ __global__ void sqrt_kernel(const float* __restrict__ in, float* __restrict__ no
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
                                                     float eps, float wd, float bc1, float bc2_sqrt,
-                                                    const float* __restrict__ found_inf, const float* __restrict__ dyn) {
+                                                    const float* __restrict__ found_inf, const float* __restrict__ dyn,
+                                                    bf16* __restrict__ mirror) {
   if (found_inf != nullptr && found_inf[0] != 0.f) return;
   if (dyn != nullptr) {   // learning rate and step count live on the device (CUDA-graph replay): dyn = {lr, step}
     lr = dyn[0];
@@ -80,12 +82,19 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
       *reinterpret_cast<float4*>(p + i) = pp;
       *reinterpret_cast<float4*>(m + i) = mm;
       *reinterpret_cast<float4*>(v + i) = vv;
+      if (mirror != nullptr) {   // bf16 twin of the parameters: the GEMM weight operands of the next step
+        uint2 pk;
+        pk.x = pack_bf16x2(pp.x, pp.y);
+        pk.y = pack_bf16x2(pp.z, pp.w);
+        *reinterpret_cast<uint2*>(mirror + i) = pk;
+      }
     } else {
       for (int64_t j = i; j < n; ++j) {
         float P = p[j], M = m[j], V = v[j];
         const float G = g[j];
         MMAE_ADAM1(P, G, M, V)
         p[j] = P; m[j] = M; v[j] = V;
+        if (mirror != nullptr) mirror[j] = __float2bfloat16_rn(P);
       }
     }
   }
@@ -132,7 +141,8 @@ extern "C" int mmae_adamw_step(float* params, const float* grads, float* exp_avg
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   adamw_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, found_inf_dev, dyn_lr_step_dev);
+      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, found_inf_dev, dyn_lr_step_dev,
+      const_cast<bf16*>(mirror_lookup(params)));
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

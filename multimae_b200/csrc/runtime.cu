@@ -107,15 +107,17 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
   return MMAE_OK;
 }
 
-// Output-tile map for the GEMM epilogue's TMA stores: box = 32 rows x 32 bf16 columns (64-byte rows, SWIZZLE_64B).
-int make_tmap_2d_bf16_store(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+// Output-tile map for the GEMM epilogue's TMA stores / reductions: box = 32 rows x 64 bytes (32 bf16 or 16 fp32 columns),
+// SWIZZLE_64B.  `ld` in elements.
+int make_tmap_2d_store(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld) {
   encode_tiled_fn fn = get_encode_fn();
   if (!fn) return MMAE_ERR_CUDA;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {32, 32};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(64 / elem_bytes), 32};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -145,6 +147,56 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 }
 
 }  // namespace mmae
+
+// ---------------------------------------------------------------------------------------------------------------------
+// bf16 weight mirror: a flat fp32 parameter buffer (FlatAdamW's) may register a bf16 twin of the same length.  The module
+// orchestrators then take GEMM weight operands straight from the twin instead of casting ~117 tensors per step, and
+// mmae_adamw_step refreshes the twin in the same pass that updates the fp32 master copy.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace mmae {
+namespace {
+struct MirrorEntry {
+  const float* f32;
+  bf16* b16;
+  int64_t n;
+};
+constexpr int MAX_MIRRORS = 8;
+MirrorEntry g_mirror[MAX_MIRRORS];
+int g_num_mirrors = 0;
+}  // namespace
+
+const bf16* mirror_lookup(const float* w) {
+  for (int i = 0; i < g_num_mirrors; ++i) {
+    const MirrorEntry& e = g_mirror[i];
+    if (w >= e.f32 && w < e.f32 + e.n) {
+      const int64_t off = w - e.f32;
+      if (off % 8 != 0) return nullptr;   // TMA needs a 16-byte aligned bf16 base
+      return e.b16 + off;
+    }
+  }
+  return nullptr;
+}
+}  // namespace mmae
+
+extern "C" int mmae_weight_mirror_register(const float* params_f32, void* mirror_bf16, int64_t n) {
+  using namespace mmae;
+  MMAE_CHECK(params_f32 != nullptr, MMAE_ERR_ARG, "mmae_weight_mirror_register: null parameter buffer");
+  int at = -1;
+  for (int i = 0; i < g_num_mirrors; ++i)
+    if (g_mirror[i].f32 == params_f32) at = i;
+  if (mirror_bf16 == nullptr || n <= 0) {   // unregister
+    if (at >= 0) g_mirror[at] = g_mirror[--g_num_mirrors];
+    return MMAE_OK;
+  }
+  MMAE_CHECK((reinterpret_cast<uintptr_t>(params_f32) & 31) == 0 && (reinterpret_cast<uintptr_t>(mirror_bf16) & 15) == 0,
+             MMAE_ERR_ARG, "mmae_weight_mirror_register: buffers must be 32-byte (fp32) / 16-byte (bf16) aligned");
+  if (at < 0) {
+    MMAE_CHECK(g_num_mirrors < MAX_MIRRORS, MMAE_ERR_UNSUPPORTED, "mmae_weight_mirror_register: too many mirrors");
+    at = g_num_mirrors++;
+  }
+  g_mirror[at] = {params_f32, reinterpret_cast<bf16*>(mirror_bf16), n};
+  return MMAE_OK;
+}
 
 extern "C" int mmae_abi_version(void) { return MMAE_ABI_VERSION; }
 extern "C" const char* mmae_last_error(void) { return mmae::g_err; }

@@ -8,6 +8,7 @@ the model (zeroed once per forward), and the per-parameter views are what backwa
 (data-parallel trainer), what `p.grad` permanently aliases so the arena can be all-reduced in place.
 """
 import ctypes
+import weakref
 import math
 
 import torch
@@ -35,14 +36,14 @@ class Workspace:
 
 
 class GradArena:
-    """Flat fp32 gradient storage for a list of (name, parameter); views are 16-byte aligned."""
+    """Flat fp32 gradient storage for a list of (name, parameter); views are 32-byte aligned."""
 
     def __init__(self, named_params, device):
         self.offsets = {}
         off = 0
         for name, p in named_params:
             self.offsets[name] = (off, p.numel(), tuple(p.shape))
-            off += (p.numel() + 3) // 4 * 4
+            off += (p.numel() + 7) // 8 * 8      # 32-byte slots: the bf16 twin of a slot stays 16-byte aligned (TMA)
         self.numel = off
         self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=device)
         self.views = {name: self.flat[o:o + n].view(shape) for name, (o, n, shape) in self.offsets.items()}
@@ -53,6 +54,22 @@ class GradArena:
 
     def view(self, name):
         return self.views[name]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# bf16 weight mirrors (FlatAdamW registers one): every fused module checks that the registered twins are current before
+# it launches, so a parameter change made through torch (load_state_dict, broadcast, manual init) is picked up
+# ---------------------------------------------------------------------------------------------------------------------
+_MIRRORS = weakref.WeakSet()
+
+
+def register_mirror(owner):
+    _MIRRORS.add(owner)
+
+
+def _fresh_mirrors():
+    for m in _MIRRORS:
+        m.ensure_mirror_fresh()
 
 
 def _grad_ptr(arena, name):
@@ -90,6 +107,7 @@ class BlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, meta, *params):
         _require_cuda(x, "Block")
+        _fresh_mirrors()
         B, N, D = x.shape
         H, hidden, eps = meta["heads"], meta["hidden"], meta["eps"]
         x = x.contiguous().float()
@@ -243,6 +261,7 @@ class DecoderHeadFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, meta, ids_keep, ids_restore, *params):
+        _fresh_mirrors()
         _require_cuda(enc, "SpatialOutputAdapter")
         lib = L.lib()
         enc = enc.contiguous().float()
@@ -308,6 +327,7 @@ class DecoderTailFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, meta, weight, bias):
+        _fresh_mirrors()
         _require_cuda(x, "SpatialOutputAdapter")
         lib = L.lib()
         x = x.contiguous().float()

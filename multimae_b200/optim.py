@@ -4,6 +4,7 @@ non-finite step is skipped on the device.  Same update rule / hyper-parameter se
 reference builds it (utils/optim_factory.py:155-174; betas (0.9, 0.95), weight_decay 0.05 on every parameter)."""
 import torch
 
+from . import _lib as L
 from . import functional as Fn
 
 
@@ -24,6 +25,15 @@ class FlatAdamW(torch.optim.Optimizer):
                 view = self.flat_params[o:o + numel].view(shape)
                 view.copy_(p.data.to(dev))
                 p.data = view
+        # bf16 twin of the parameters: the GEMM weight operands are read from it (no per-step casts of ~117 tensors); the
+        # update kernel keeps it current, ensure_mirror_fresh() catches every other modification through torch
+        self.flat_bf16 = None
+        self._mirror_version = None
+        if dev.type == "cuda":
+            self.flat_bf16 = torch.empty(self.flat_params.numel(), dtype=torch.bfloat16, device=dev)
+            L.check(L.lib().mmae_weight_mirror_register(self.flat_params.data_ptr(), self.flat_bf16.data_ptr(),
+                                                        self.flat_params.numel()), "mmae_weight_mirror_register")
+            Fn.register_mirror(self)
         self.exp_avg = torch.zeros_like(self.flat_params)
         self.exp_avg_sq = torch.zeros_like(self.flat_params)
         # {learning rate, step count} on the device: the update kernel reads them there, so a captured CUDA graph replays
@@ -31,6 +41,26 @@ class FlatAdamW(torch.optim.Optimizer):
         self._dyn = torch.zeros(2, dtype=torch.float32, device=dev)
         self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(1)
         self.sync_hyperparams()
+
+    def ensure_mirror_fresh(self):
+        """Re-cast the whole flat buffer (one kernel) if the parameters were modified through torch since the twin was
+        last written.  The update kernel itself writes the twin and does not touch the version counter."""
+        if self.flat_bf16 is None or self._mirror_version == self.flat_params._version:
+            return
+        L.check(L.lib().mmae_cast_f32_to_bf16(self.flat_params.data_ptr(), self.flat_bf16.data_ptr(),
+                                              self.flat_params.numel(), L.current_stream()), "mmae_cast_f32_to_bf16")
+        self._mirror_version = self.flat_params._version
+
+    def release_mirror(self):
+        if getattr(self, "flat_bf16", None) is not None:
+            try:
+                L.lib().mmae_weight_mirror_register(self.flat_params.data_ptr(), None, 0)
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
+            self.flat_bf16 = None
+
+    def __del__(self):
+        self.release_mirror()
 
     def sync_hyperparams(self):
         """Push the current param_group learning rate to the device scalar (call before a graph replay)."""

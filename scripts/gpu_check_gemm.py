@@ -252,6 +252,28 @@ for (M, N, K_) in [(12672, 3072, 768), (12672, 2304, 768), (12672, 768, 768), (2
               (tma, M, N, K_, t0, fl / t0 / 1e9, t1, fl / t1 / 1e9, t2, fl / t2 / 1e9, t3, fl / t3 / 1e9), flush=True)
 LIB.lib().mmae_gemm_set_tma_store(1)
 
+# split-K weight-gradient shapes (fp32 accumulate): TMA reduce-add vs per-lane red.global, over split counts and tiles
+for (M, N, K_) in [(256, 256, 25088), (256, 1024, 25088), (1024, 256, 25088), (768, 256, 25088), (768, 768, 12672),
+                   (768, 3072, 12672), (3072, 768, 12672), (2304, 768, 12672)]:
+    A = rand_bf16(K_, M)
+    B = rand_bf16(K_, N)
+    of = torch.zeros(M, N, device=dev)
+    fl = 2.0 * M * N * K_
+    res = []
+    for variant in (1, 3, 2):
+        LIB.lib().mmae_gemm_set_variant(variant)
+        bn = {1: 128, 2: 256, 3: 192}[variant]
+        tiles = -(-M // 128) * -(-N // bn)
+        for mult in (1, 2):
+            split = max(1, (148 * mult) // tiles)
+            for tma in (1, 0):
+                LIB.lib().mmae_gemm_set_tma_store(tma)
+                t = time_it(lambda: KN.gemm(A, B, a_mn=True, b_mn=True, out_f32=of, accumulate=True, split_k=split))
+                res.append("bn%d s%d tma%d %.1f us (%.0f)" % (bn, split, tma, t * 1e3, fl / t / 1e9))
+    print("wgrad M=%d N=%d K=%d: %s" % (M, N, K_, " | ".join(res)), flush=True)
+LIB.lib().mmae_gemm_set_variant(-1)
+LIB.lib().mmae_gemm_set_tma_store(1)
+
 # attention timing at the encoder shape
 B_, H_, N_, dh_ = 128, 12, 99, 64
 qkv = rand_bf16(B_ * N_, 3 * H_ * dh_)

@@ -110,6 +110,19 @@ def test_gemm_tma_store_epilogue(dev, KN, variant, shape):
             outs.append(buf[:M, :N].clone())
         assert rel_l2(outs[0], ref) < 4e-3, (variant, shape, list(kw), rel_l2(outs[0], ref))
         assert torch.equal(outs[0], outs[1]), (variant, shape, list(kw))
+    # fp32 outputs: plain tile stores, and reduce-add tiles for accumulate / split-K (margins stay untouched)
+    for kw, ref in (({"bias": bias}, acc + bias), ({"accumulate": True, "alpha": 0.5}, 1 + 0.5 * acc),
+                    ({"accumulate": True, "split_k": 3, "bias": bias}, 1 + acc + bias)):
+        outs = []
+        for tma in (1, 0):
+            L.lib().mmae_gemm_set_tma_store(tma)
+            buf = torch.full((M + 3, N + 8), 1.0, device=dev)
+            KN.gemm(A, B, out_f32=buf[:M, :N], **kw)
+            assert bool((buf[M:] == 1).all()) and bool((buf[:, N:] == 1).all()), (variant, shape, list(kw), tma)
+            assert rel_l2(buf[:M, :N], ref) < 3e-5, (variant, shape, list(kw), tma, rel_l2(buf[:M, :N], ref))
+            outs.append(buf[:M, :N].clone())
+        if "split_k" not in kw:
+            assert torch.equal(outs[0], outs[1]), (variant, shape, list(kw))
 
 
 def test_gemm_rejects_bad_arguments(dev, KN):

@@ -296,3 +296,46 @@ def test_cuda_graph_step_matches_eager(dev, golden_dir):
     assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(l_eager, l_graph)), (l_eager, l_graph)
     assert l_eager[-1] < l_eager[0]
     assert rel_l2(p_graph, p_eager) < 1e-3
+
+
+def test_bf16_weight_mirror_tracks_parameters(dev, golden_dir):
+    """FlatAdamW registers a bf16 twin of the flat parameter buffer: the update kernel keeps it equal to bf16(params), a
+    change made through torch is picked up before the next launch, and a step that reads its weights from the twin gives
+    the same loss as one that casts them per call (twin unregistered)."""
+    from multimae_b200 import _lib as L
+    from multimae_b200.native_scaler import NativeScalerWithGradNormCount
+    from multimae_b200.optim import FlatAdamW
+    from multimae_b200.train_step import TrainStep
+    fx = _load(golden_dir, "cuda_small.pt")
+    c = fx["config"]
+    x = {k: v.to(dev) for k, v in fx["inputs"].items()}
+    triple = ({k: v.to(dev) for k, v in fx["task_masks"].items()}, fx["ids_keep"].to(dev), fx["ids_restore"].to(dev))
+
+    def run(with_mirror):
+        model = _build_model(c)
+        formula_fill_(list(model.named_parameters()))
+        model = model.to(dev).train()
+        model.generate_random_masks = lambda *a, **k: triple
+        opt = FlatAdamW(model, lr=1e-3)
+        if not with_mirror:
+            opt.release_mirror()
+        scaler = NativeScalerWithGradNormCount(enabled=False).attach_arena(model.grad_arena())
+        step = TrainStep(model, _loss_modules(), opt, scaler, num_encoded_tokens=12, loss_sources={"norm_rgb": "rgb"})
+        losses = [float(step(x)[0]) for _ in range(3)]
+        if with_mirror:
+            torch.cuda.synchronize()
+            assert torch.equal(opt.flat_bf16, opt.flat_params.to(torch.bfloat16))      # written by the update kernel
+            with torch.no_grad():
+                next(model.parameters()).mul_(1.5)                                     # bumps the version counter
+            assert opt._mirror_version != opt.flat_params._version
+            step(x)
+            torch.cuda.synchronize()
+            assert torch.equal(opt.flat_bf16, opt.flat_params.to(torch.bfloat16))
+        return losses
+
+    launches0 = L.lib().mmae_launch_count()
+    l_mirror = run(True)
+    l_cast = run(False)
+    assert L.lib().mmae_launch_count() > launches0
+    assert abs(l_mirror[0] - l_cast[0]) <= 1e-6 * abs(l_cast[0]), (l_mirror, l_cast)   # same bf16 operand bits
+    assert all(abs(a - b) <= 1e-3 * abs(a) for a, b in zip(l_mirror, l_cast)), (l_mirror, l_cast)   # atomics reorder
