@@ -1,6 +1,7 @@
 // HBM-bound cast / column-sum / transpose kernels (vectorised, coalesced; no data reuse -> no tensor cores).
 #include "common.cuh"
 #include "../../include/multimae_b200.h"
+#include "internal.h"
 
 namespace mmae {
 void count_launch();
@@ -23,19 +24,19 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __rest
 }
 
 // Tile: ROWS_PER_BLOCK rows x 128 columns; block (32, 8).  Each thread owns 4 consecutive columns.
-constexpr int CS_ROWS = 64;
 
 template <bool SRC_BF16>
 __global__ void __launch_bounds__(256) cast_colsum_kernel(const void* __restrict__ src_, int64_t ld_src,
                                                           bf16* __restrict__ dst, int64_t ld_dst,
-                                                          float* __restrict__ colsum, int M, int N) {
+                                                          float* __restrict__ colsum, float* __restrict__ partial, int M, int N,
+                                                          int rows_per_block) {
   __shared__ float4 red[8][32];
   const int col = blockIdx.x * 128 + threadIdx.x * 4;
-  const int r0 = blockIdx.y * CS_ROWS;
+  const int r0 = blockIdx.y * rows_per_block;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < N) {
 #pragma unroll 4
-    for (int r = r0 + threadIdx.y; r < min(r0 + CS_ROWS, M); r += 8) {
+    for (int r = r0 + threadIdx.y; r < min(r0 + rows_per_block, M); r += 8) {
       float4 v;
       if constexpr (SRC_BF16) {
         const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(src_) + int64_t(r) * ld_src + col));
@@ -62,10 +63,92 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const void* __restrict
       const float4 o = red[y][threadIdx.x];
       acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
     }
-    atomicAdd(colsum + col + 0, acc.x);
-    atomicAdd(colsum + col + 1, acc.y);
-    atomicAdd(colsum + col + 2, acc.z);
-    atomicAdd(colsum + col + 3, acc.w);
+    // one partial row per row-block (added by colred_finalize), or the only block adds directly
+    if (gridDim.y == 1) {
+      float4 c = *reinterpret_cast<float4*>(colsum + col);
+      c.x += acc.x; c.y += acc.y; c.z += acc.z; c.w += acc.w;
+      *reinterpret_cast<float4*>(colsum + col) = c;
+    } else {
+      *reinterpret_cast<float4*>(partial + int64_t(blockIdx.y) * N + col) = acc;
+    }
+  }
+}
+
+// dst[c] += sum_y partial[y, c]: block (32, 8) per 32 columns, y strided over the 8 thread rows
+__global__ void __launch_bounds__(256) colred_finalize_kernel(const float* __restrict__ partial, int Y, int ld, int C, int seg,
+                                                              float* __restrict__ d0, float* __restrict__ d1,
+                                                              float* __restrict__ d2) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < C) {
+    int y = threadIdx.y;
+    for (; y + 24 < Y; y += 32) {
+      const float a0 = partial[int64_t(y) * ld + c], a1 = partial[int64_t(y + 8) * ld + c];
+      const float a2 = partial[int64_t(y + 16) * ld + c], a3 = partial[int64_t(y + 24) * ld + c];
+      acc += (a0 + a1) + (a2 + a3);
+    }
+    for (; y < Y; y += 8) acc += partial[int64_t(y) * ld + c];
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) acc += red[y][threadIdx.x];
+    const int k = c / seg;
+    float* d = k == 0 ? d0 : (k == 1 ? d1 : d2);
+    if (d != nullptr) d[c - k * seg] += acc;
+  }
+}
+
+// colsum[n] += sum_m src[m, n] for a bf16 matrix: 8 columns (16 bytes) per thread, 4 rows in flight, block (32, 8)
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ src, int64_t ld, float* __restrict__ colsum,
+                                                          float* __restrict__ partial, int M, int N, int rows_per_block) {
+  __shared__ float red[8][32][9];
+  const int col = blockIdx.x * 256 + threadIdx.x * 8;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r_end = min(r0 + rows_per_block, M);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (col < N) {
+    constexpr int U = 4;
+    for (int rb = r0 + threadIdx.y; rb < r_end; rb += 8 * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (rb + 8 * u < r_end) v[u] = ld_stream_16(src + int64_t(rb + 8 * u) * ld + col);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (rb + 8 * u >= r_end) break;
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(&v[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = unpack_bf16x2(w[k]);
+          acc[2 * k] += a.x;
+          acc[2 * k + 1] += a.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.y][threadIdx.x][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    float t[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      t[k] = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t[k] += red[y][threadIdx.x][k];
+    }
+    float* dst = gridDim.y == 1 ? colsum + col : partial + int64_t(blockIdx.y) * N + col;
+    if (gridDim.y == 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] += dst[k];
+    }
+    *reinterpret_cast<float4*>(dst) = make_float4(t[0], t[1], t[2], t[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(t[4], t[5], t[6], t[7]);
   }
 }
 
@@ -115,15 +198,16 @@ __global__ void __launch_bounds__(256) gelu_stream_kernel(const bf16* __restrict
 // dz[m,n] *= gelu'(z[m,n]) in place AND colsum[n] += sum_m dz[m,n] (the fc1 bias gradient): one pass instead of a GELU'
 // pass plus a column-sum pass.  Block (32, 8): 8 rows x 256 columns per iteration, 64 rows per block.
 __global__ void __launch_bounds__(256) dgelu_colsum_kernel(const bf16* __restrict__ z, bf16* __restrict__ dz, int64_t ld,
-                                                           float* __restrict__ colsum, int M, int N) {
+                                                           float* __restrict__ colsum, float* __restrict__ partial, int M, int N,
+                                                           int rows_per_block) {
   __shared__ float red[8][32][9];
   const int col = blockIdx.x * 256 + threadIdx.x * 8;
-  const int r0 = blockIdx.y * CS_ROWS;
+  const int r0 = blockIdx.y * rows_per_block;
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
   if (col < N) {
-    const int r_end = min(r0 + CS_ROWS, M);
+    const int r_end = min(r0 + rows_per_block, M);
     constexpr int U = 4;   // rows in flight per thread (loads issued before any of the in-place stores)
     for (int rb = r0 + threadIdx.y; rb < r_end; rb += 8 * U) {
       uint4 zv[U], dv[U];
@@ -160,13 +244,20 @@ __global__ void __launch_bounds__(256) dgelu_colsum_kernel(const bf16* __restric
   for (int k = 0; k < 8; ++k) red[threadIdx.y][threadIdx.x][k] = acc[k];
   __syncthreads();
   if (threadIdx.y == 0 && col < N) {
+    float t[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float t = 0.f;
+      t[k] = 0.f;
 #pragma unroll
-      for (int y = 0; y < 8; ++y) t += red[y][threadIdx.x][k];
-      atomicAdd(colsum + col + k, t);
+      for (int y = 0; y < 8; ++y) t[k] += red[y][threadIdx.x][k];
     }
+    float* dst = gridDim.y == 1 ? colsum + col : partial + int64_t(blockIdx.y) * N + col;
+    if (gridDim.y == 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] += dst[k];
+    }
+    *reinterpret_cast<float4*>(dst) = make_float4(t[0], t[1], t[2], t[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(t[4], t[5], t[6], t[7]);
   }
 }
 
@@ -219,6 +310,57 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restr
 
 using namespace mmae;
 
+// Row blocking of the column-sum kernels: about `blocks_per_sm` resident blocks per SM in ONE wave.  Each block ends with
+// one fp32 atomic per column, so fewer, longer blocks also mean fewer same-address atomics (64-row blocks meant 392
+// atomics per column on a 25088-row matrix, which cost more than reading it).  MMAE_TUNE_CS overrides blocks_per_sm.
+static int colsum_rows_per_block(int M, int col_blocks, int blocks_per_sm) {
+  static const int tune = []() {
+    const char* e = getenv("MMAE_TUNE_CS");
+    return e ? atoi(e) : 0;
+  }();
+  if (tune > 0) blocks_per_sm = tune;
+  const int target = std::max(1, sm_count() * blocks_per_sm / std::max(col_blocks, 1));
+  int rpb = ceil_div(M, target);
+  rpb = std::max(32, (rpb + 7) / 8 * 8);
+  return rpb;
+}
+
+namespace mmae {
+float* colred_scratch(size_t floats, cudaStream_t st) {
+  static float* buf = nullptr;
+  static size_t cap = 0;
+  if (floats <= cap) return buf;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cs);
+  if (cs != cudaStreamCaptureStatusNone) {
+    set_last_error("column-reduction scratch must grow to %zu floats during stream capture: run the step once eagerly first",
+                   floats);
+    return nullptr;
+  }
+  // growing frees the old buffer: drain the device first (rare: first call, or a larger problem than any before)
+  cudaDeviceSynchronize();
+  if (buf) cudaFree(buf);
+  const size_t want = std::max(floats, size_t(4) << 20);   // 16 MB covers every shape of the MultiMAE-B step
+  if (cudaMalloc(&buf, want * sizeof(float)) != cudaSuccess) {
+    buf = nullptr;
+    cap = 0;
+    set_last_error("cudaMalloc of the column-reduction scratch (%zu bytes) failed", want * sizeof(float));
+    return nullptr;
+  }
+  cap = want;
+  return buf;
+}
+
+int colred_finalize(const float* partial, int Y, int ld, int seg, float* dst0, float* dst1, float* dst2, cudaStream_t st) {
+  const int nseg = dst2 ? 3 : (dst1 ? 2 : 1);
+  dim3 grid(ceil_div(seg * nseg, 32)), block(32, 8);
+  colred_finalize_kernel<<<grid, block, 0, st>>>(partial, Y, ld, seg * nseg, seg, dst0, dst1, dst2);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+}  // namespace mmae
+
 extern "C" int mmae_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
   MMAE_CHECK(src && dst_bf16 && n >= 0, MMAE_ERR_ARG, "mmae_cast_f32_to_bf16: bad args");
   if (n == 0) return MMAE_OK;
@@ -240,22 +382,42 @@ extern "C" int mmae_cast_colsum_f32(const float* src, int64_t ld_src, void* dst_
                                     int M, int N, void* stream) {
   MMAE_CHECK(src && M > 0 && N > 0 && N % 4 == 0 && ld_src % 4 == 0 && (!dst_bf16 || ld_dst % 4 == 0), MMAE_ERR_ARG,
              "mmae_cast_colsum_f32: bad args (N, ld must be multiples of 4)");
-  dim3 grid(ceil_div(N, 128), ceil_div(M, CS_ROWS)), block(32, 8);
-  cast_colsum_kernel<false><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, ld_src, reinterpret_cast<bf16*>(dst_bf16), ld_dst, colsum, M, N);
+  cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
+  const int rpb = colsum_rows_per_block(M, ceil_div(N, 128), 4);
+  dim3 grid(ceil_div(N, 128), ceil_div(M, rpb)), block(32, 8);
+  float* partial = nullptr;
+  if (colsum && grid.y > 1) {
+    partial = colred_scratch(size_t(grid.y) * N, cst);
+    if (!partial) return MMAE_ERR_CUDA;
+  }
+  cast_colsum_kernel<false><<<grid, block, 0, cst>>>(src, ld_src, reinterpret_cast<bf16*>(dst_bf16), ld_dst, colsum, partial,
+                                                     M, N, rpb);
   count_launch();
   MMAE_LAUNCH_OK();
+  if (partial) return colred_finalize(partial, grid.y, N, N, colsum, nullptr, nullptr, cst);
   return MMAE_OK;
 }
 
 extern "C" int mmae_colsum_bf16(const void* src_bf16, int64_t ld_src, float* colsum, int M, int N, void* stream) {
   MMAE_CHECK(src_bf16 && colsum && M > 0 && N > 0 && N % 4 == 0 && ld_src % 4 == 0, MMAE_ERR_ARG,
              "mmae_colsum_bf16: bad args");
-  dim3 grid(ceil_div(N, 128), ceil_div(M, CS_ROWS)), block(32, 8);
-  cast_colsum_kernel<true><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src_bf16, ld_src, nullptr, 0,
-                                                                                      colsum, M, N);
+  cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
+  const bool wide = N % 8 == 0 && ld_src % 8 == 0 && (reinterpret_cast<uintptr_t>(src_bf16) & 15) == 0;
+  const int cols = wide ? 256 : 128;
+  const int rpb = colsum_rows_per_block(M, ceil_div(N, cols), 4);
+  dim3 grid(ceil_div(N, cols), ceil_div(M, rpb)), block(32, 8);
+  float* partial = nullptr;
+  if (grid.y > 1) {
+    partial = colred_scratch(size_t(grid.y) * N, cst);
+    if (!partial) return MMAE_ERR_CUDA;
+  }
+  if (wide)
+    colsum_bf16_kernel<<<grid, block, 0, cst>>>(reinterpret_cast<const bf16*>(src_bf16), ld_src, colsum, partial, M, N, rpb);
+  else
+    cast_colsum_kernel<true><<<grid, block, 0, cst>>>(src_bf16, ld_src, nullptr, 0, colsum, partial, M, N, rpb);
   count_launch();
   MMAE_LAUNCH_OK();
+  if (partial) return colred_finalize(partial, grid.y, N, N, colsum, nullptr, nullptr, cst);
   return MMAE_OK;
 }
 
@@ -303,10 +465,18 @@ extern "C" int mmae_add_bf16_f32(const float* x, const void* y_bf16, float* out,
 
 extern "C" int mmae_dgelu_colsum_bf16(const void* z, void* dz, int64_t ld, float* colsum, int M, int N, void* stream) {
   MMAE_CHECK(z && dz && colsum && M > 0 && N > 0 && N % 8 == 0 && ld % 8 == 0, MMAE_ERR_ARG, "mmae_dgelu_colsum_bf16: bad args");
-  dim3 grid(ceil_div(N, 256), ceil_div(M, CS_ROWS)), block(32, 8);
-  dgelu_colsum_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(dz), ld, colsum, M, N);
+  cudaStream_t cst = reinterpret_cast<cudaStream_t>(stream);
+  const int rpb = colsum_rows_per_block(M, ceil_div(N, 256), 3);
+  dim3 grid(ceil_div(N, 256), ceil_div(M, rpb)), block(32, 8);
+  float* partial = nullptr;
+  if (grid.y > 1) {
+    partial = colred_scratch(size_t(grid.y) * N, cst);
+    if (!partial) return MMAE_ERR_CUDA;
+  }
+  dgelu_colsum_kernel<<<grid, block, 0, cst>>>(reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(dz), ld, colsum,
+                                               partial, M, N, rpb);
   count_launch();
   MMAE_LAUNCH_OK();
+  if (partial) return colred_finalize(partial, grid.y, N, N, colsum, nullptr, nullptr, cst);
   return MMAE_OK;
 }

@@ -16,6 +16,14 @@ struct TaskEmbGradPtrs {
 
 void count_launch();
 
+// Column-partial reduction (elementwise.cu).  Kernels that reduce over rows write one partial row per block into the
+// library's scratch buffer and colred_finalize adds the column totals to up to three destinations of `seg` columns each
+// (dst[k] covers partial columns [k*seg, (k+1)*seg) of rows `ld` floats apart; trailing null destinations are skipped).  No atomics: Y x C scalar atomics on a
+// few cache lines serialise in one or two L2 slices (measured: 592 blocks x 256 columns = 45 us for a 13 MB column sum),
+// and the result is deterministic.
+float* colred_scratch(size_t floats, cudaStream_t st);   // nullptr + last error if it cannot be provided
+int colred_finalize(const float* partial, int Y, int ld, int seg, float* dst0, float* dst1, float* dst2, cudaStream_t st);
+
 // bf16 weight mirror registry (runtime.cu): the bf16 twin of a registered fp32 parameter buffer, or nullptr
 const bf16* mirror_lookup(const float* w);
 

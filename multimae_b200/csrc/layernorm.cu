@@ -4,6 +4,7 @@
 // HBM-bound: fwd reads 4 B/elem, writes 2 B/elem (bf16 operand for the next GEMM) + 8 B/row of statistics.
 #include "common.cuh"
 #include "../../include/multimae_b200.h"
+#include "internal.h"
 
 namespace mmae {
 void count_launch();
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
 }
 
 // Backward.  dx_out = dx_resid (optional) + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * gamma.
-// dgamma/dbeta: per-lane register partials over the block's rows -> smem reduce over warps -> fp32 atomics.
+// dgamma/dbeta: per-lane register partials over the block's rows -> smem reduce over warps -> one partial row per block.
 //
 // Persistent: the grid is one wave (blocks = SMs x resident blocks), warps stride over the rows, so there is no partial
 // last wave (12672 rows in 64-row blocks were 198 blocks on 148 SMs: a third of the time ran at 1/3 occupancy) and the
@@ -123,9 +124,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __res
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ dx_resid, int64_t ldr,
                                                                float* __restrict__ dx, int64_t lddx,
-                                                               float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                               bf16* __restrict__ dx_bf16, int64_t lddxb,
-                                                               float* __restrict__ dx_colsum, int M) {
+                                                               float* __restrict__ partial, bool want_colsum,
+                                                               bf16* __restrict__ dx_bf16, int64_t lddxb, int M) {
   constexpr int D = NVEC * 128;
   __shared__ float4 red[LN_WARPS][32];
   __shared__ float4 sgamma[NVEC * 32];
@@ -198,11 +198,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __res
     mean = mean_n;
     rstd = rstd_n;
   }
-  // column reductions across the block's warps
+  // column reductions across the block's warps -> this block's row of partial sums [dgamma | dbeta | colsum(dx)], added up
+  // by colred_finalize (no atomics: blocks x 3D scalar atomics on a few cache lines cost more than the streaming pass)
 #pragma unroll
   for (int pass = 0; pass < 3; ++pass) {
-    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dx_colsum);
-    if (dst == nullptr) continue;
+    if (pass == 2 && !want_colsum) continue;
+    float* dst = partial + (int64_t(blockIdx.x) * 3 + pass) * D;
 #pragma unroll
     for (int i = 0; i < NVEC; ++i) {
       __syncthreads();
@@ -216,10 +217,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __res
           a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
         }
         const int c = (i * 32 + lane) * 4;
-        atomicAdd(dst + c + 0, a.x);
-        atomicAdd(dst + c + 1, a.y);
-        atomicAdd(dst + c + 2, a.z);
-        atomicAdd(dst + c + 3, a.w);
+        *reinterpret_cast<float4*>(dst + c) = a;
       }
     }
   }
@@ -278,17 +276,25 @@ static int ln_backward_impl(const void* dy, int dy_is_bf16, int64_t lddy, const 
   MMAE_CHECK(D % 128 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0 && ldr % 4 == 0,
              MMAE_ERR_UNSUPPORTED, "mmae_layernorm_backward: D=%d must be a multiple of 128 and <= 1024", D);
   // one wave: resident blocks per SM follow from the register footprint of the per-lane column accumulators
-  const int per_sm = D <= 256 ? 3 : (D <= 384 ? 2 : 1);
+  static const int tune = []() {
+    const char* e = getenv("MMAE_TUNE_LNB");
+    return e ? atoi(e) : 0;
+  }();
+  int per_sm = D <= 256 ? 3 : (D <= 384 ? 2 : 1);
+  if (tune > 0) per_sm = std::min(per_sm, tune);
   dim3 grid(std::min(ceil_div(M, LN_WARPS), sm_count() * per_sm)), block(LN_WARPS * 32);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMAE_CHECK(dgamma && dbeta, MMAE_ERR_ARG, "mmae_layernorm_backward: dgamma / dbeta are required");
+  float* partial = colred_scratch(size_t(grid.x) * 3 * D, st);
+  if (!partial) return MMAE_ERR_CUDA;
 #define LNB_CASE(NV)                                                                                              \
   case NV:                                                                                                        \
     if (dy_is_bf16)                                                                                               \
       ln_bwd_kernel<NV, true><<<grid, block, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx,     \
-                                                      lddx, dgamma, dbeta, dx_bf16, lddxb, dx_colsum, M);        \
+                                                      lddx, partial, dx_colsum != nullptr, dx_bf16, lddxb, M);   \
     else                                                                                                          \
       ln_bwd_kernel<NV, false><<<grid, block, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx,    \
-                                                       lddx, dgamma, dbeta, dx_bf16, lddxb, dx_colsum, M);       \
+                                                       lddx, partial, dx_colsum != nullptr, dx_bf16, lddxb, M);  \
     break;
   switch (D / 128) {
     LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
@@ -297,7 +303,8 @@ static int ln_backward_impl(const void* dy, int dy_is_bf16, int64_t lddy, const 
 #undef LNB_CASE
   count_launch();
   MMAE_LAUNCH_OK();
-  return MMAE_OK;
+  // partial row = [dgamma | dbeta | colsum]; without a colsum destination only the first two segments are summed
+  return colred_finalize(partial, grid.x, 3 * D, D, dgamma, dbeta, dx_colsum, st);
 }
 
 extern "C" int mmae_layernorm_backward(const void* dy, int dy_is_bf16, int64_t lddy, const float* x, int64_t ldx,

@@ -20,19 +20,30 @@ __global__ void __launch_bounds__(256) unscale_norm_kernel(float* __restrict__ g
   float acc = 0.f;
   bool bad = false;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x * 4;
-  for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
-    if (i + 4 <= n) {
-      float4 v = *reinterpret_cast<float4*>(g + i);
-      v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
-      if (inv != 1.0f) *reinterpret_cast<float4*>(g + i) = v;
-      acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-      bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
-    } else {
-      for (int64_t j = i; j < n; ++j) {
-        const float v = g[j] * inv;
-        if (inv != 1.0f) g[j] = v;
-        acc += v * v;
-        bad |= !isfinite(v);
+  constexpr int U = 4;   // independent 16-byte loads in flight per thread
+  for (int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += stride * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i + 4 <= n) v[u] = *reinterpret_cast<const float4*>(g + i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i + 4 <= n) {
+        float4 w = v[u];
+        w.x *= inv; w.y *= inv; w.z *= inv; w.w *= inv;
+        if (inv != 1.0f) *reinterpret_cast<float4*>(g + i) = w;
+        acc += w.x * w.x + w.y * w.y + w.z * w.z + w.w * w.w;
+        bad |= !(isfinite(w.x) && isfinite(w.y) && isfinite(w.z) && isfinite(w.w));
+      } else if (i < n) {
+        for (int64_t j = i; j < n; ++j) {
+          const float w = g[j] * inv;
+          if (inv != 1.0f) g[j] = w;
+          acc += w * w;
+          bad |= !isfinite(w);
+        }
       }
     }
   }

@@ -57,8 +57,9 @@ class GradArena:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# bf16 weight mirrors (FlatAdamW registers one): every fused module checks that the registered twins are current before
-# it launches, so a parameter change made through torch (load_state_dict, broadcast, manual init) is picked up
+# bf16 weight mirrors (FlatAdamW registers one): the model checks at the start of every forward that the registered
+# twins are current, so a parameter change made through torch (load_state_dict, manual init) is picked up; writes that
+# bypass the version counters (`.data`) call invalidate_mirrors()
 # ---------------------------------------------------------------------------------------------------------------------
 _MIRRORS = weakref.WeakSet()
 
@@ -67,9 +68,14 @@ def register_mirror(owner):
     _MIRRORS.add(owner)
 
 
-def _fresh_mirrors():
+def fresh_mirrors():
     for m in _MIRRORS:
         m.ensure_mirror_fresh()
+
+
+def invalidate_mirrors():
+    for m in _MIRRORS:
+        m.invalidate_mirror()
 
 
 def _grad_ptr(arena, name):
@@ -107,7 +113,6 @@ class BlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, meta, *params):
         _require_cuda(x, "Block")
-        _fresh_mirrors()
         B, N, D = x.shape
         H, hidden, eps = meta["heads"], meta["hidden"], meta["eps"]
         x = x.contiguous().float()
@@ -261,7 +266,6 @@ class DecoderHeadFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, meta, ids_keep, ids_restore, *params):
-        _fresh_mirrors()
         _require_cuda(enc, "SpatialOutputAdapter")
         lib = L.lib()
         enc = enc.contiguous().float()
@@ -327,7 +331,6 @@ class DecoderTailFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, meta, weight, bias):
-        _fresh_mirrors()
         _require_cuda(x, "SpatialOutputAdapter")
         lib = L.lib()
         x = x.contiguous().float()

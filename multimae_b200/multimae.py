@@ -278,6 +278,7 @@ class MultiMAE(nn.Module):
                 task_masks: Dict[str, torch.Tensor] = None, num_encoded_tokens: int = 128,
                 alphas: Union[float, List[float]] = 1.0, sample_tasks_uniformly: bool = False,
                 fp32_output_adapters: List[str] = []):
+        Fn.fresh_mirrors()                                    # bf16 weight twins follow any torch-side parameter change
         x, adapters, placeholders, B, H, W, dev = self._prepare(x)
         input_info = self.generate_input_info(input_task_tokens=placeholders, image_size=(H, W))
         total = input_info["num_task_tokens"]
@@ -348,6 +349,7 @@ class MultiViT(MultiMAE):
         return seq, input_info
 
     def forward(self, x, return_all_layers=False, **kwargs):
+        Fn.fresh_mirrors()
         tokens, input_info = self.process_input(x)
         if not return_all_layers:
             encoder_tokens = self.encoder(tokens)

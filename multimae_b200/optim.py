@@ -29,6 +29,8 @@ class FlatAdamW(torch.optim.Optimizer):
         # update kernel keeps it current, ensure_mirror_fresh() catches every other modification through torch
         self.flat_bf16 = None
         self._mirror_version = None
+        self._invalidations = 0
+        self._flat_views = params
         if dev.type == "cuda":
             self.flat_bf16 = torch.empty(self.flat_params.numel(), dtype=torch.bfloat16, device=dev)
             L.check(L.lib().mmae_weight_mirror_register(self.flat_params.data_ptr(), self.flat_bf16.data_ptr(),
@@ -42,14 +44,26 @@ class FlatAdamW(torch.optim.Optimizer):
         self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(1)
         self.sync_hyperparams()
 
+    def _params_version(self):
+        # in-place torch ops on a Parameter (copy_, load_state_dict, init) bump its counter; our kernels do not
+        return self._invalidations + sum(p._version for p in self._flat_views)
+
+    def invalidate_mirror(self):
+        """Call after modifying parameters in a way autograd's version counters do not see (writes through `.data`)."""
+        self._invalidations += 1
+
     def ensure_mirror_fresh(self):
         """Re-cast the whole flat buffer (one kernel) if the parameters were modified through torch since the twin was
-        last written.  The update kernel itself writes the twin and does not touch the version counter."""
-        if self.flat_bf16 is None or self._mirror_version == self.flat_params._version:
+        last written.  The update kernel itself writes the twin and does not touch the version counters.  Called by the
+        model at the start of every forward."""
+        if self.flat_bf16 is None:
+            return
+        ver = self._params_version()
+        if self._mirror_version == ver:
             return
         L.check(L.lib().mmae_cast_f32_to_bf16(self.flat_params.data_ptr(), self.flat_bf16.data_ptr(),
                                               self.flat_params.numel(), L.current_stream()), "mmae_cast_f32_to_bf16")
-        self._mirror_version = self.flat_params._version
+        self._mirror_version = ver
 
     def release_mirror(self):
         if getattr(self, "flat_bf16", None) is not None:

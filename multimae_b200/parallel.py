@@ -9,6 +9,8 @@ Replaces DistributedDataParallel's bucket copy-in/copy-out + unused-parameter bo
 import torch
 import torch.distributed as dist
 
+from . import functional as Fn
+
 
 class FlatGradReducer:
     def __init__(self, arena, param_names_in_registration_order, process_group=None, bucket_bytes=48 << 20):
@@ -83,3 +85,4 @@ def broadcast_parameters(model, src=0, process_group=None):
         with torch.no_grad():
             for p in model.parameters():
                 dist.broadcast(p.data, src=src, group=process_group)
+    Fn.invalidate_mirrors()                                   # `.data` writes are invisible to the version counters

@@ -327,7 +327,7 @@ def test_bf16_weight_mirror_tracks_parameters(dev, golden_dir):
             assert torch.equal(opt.flat_bf16, opt.flat_params.to(torch.bfloat16))      # written by the update kernel
             with torch.no_grad():
                 next(model.parameters()).mul_(1.5)                                     # bumps the version counter
-            assert opt._mirror_version != opt.flat_params._version
+            assert opt._mirror_version != opt._params_version()
             step(x)
             torch.cuda.synchronize()
             assert torch.equal(opt.flat_bf16, opt.flat_params.to(torch.bfloat16))
