@@ -80,6 +80,10 @@ int mmae_gemm_set_variant(int variant);
 /* 1 (default): bf16-only epilogues of the persistent kernels leave through shared memory + TMA tile stores;
  * 0: per-lane global stores (kept for A/B measurements and for epilogues with extra operands).  Env MMAE_GEMM_TMA_STORE. */
 int mmae_gemm_set_tma_store(int enable);
+/* 1 (default): kernels are launched with programmatic stream serialization and start with griddepcontrol
+ * (launch_dependents + wait), so the next kernel's blocks are scheduled while the previous one drains; 0: plain
+ * stream order.  Env MMAE_PDL. */
+int mmae_set_pdl(int enable);
 
 int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                    int M, int N, int K, int split_k, const mmae_gemm_epilogue* ep, void* stream);

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
                                                                bf16* __restrict__ O, int64_t ldo,
                                                                float* __restrict__ lse, int Nq, int Nk, int H,
                                                                float scale) {
+  pdl_prologue();
   constexpr int LDS = DH + 8, LDT = ATT_CHUNK + 8;
   __shared__ __align__(16) bf16 sQ[ATT_ROWS * LDS];
   __shared__ __align__(16) bf16 sK[ATT_CHUNK * LDS];
@@ -210,6 +211,7 @@ template <int DH>
 __global__ void __launch_bounds__(128) attn_delta_kernel(const bf16* __restrict__ O, int64_t ldo,
                                                          const bf16* __restrict__ dO, int64_t lddo,
                                                          float* __restrict__ delta, int Nq, int H) {
+  pdl_prologue();
   const int row = blockIdx.x;  // b * Nq + q
   const int b = row / Nq, q = row % Nq;
   constexpr int TPH = DH / 8;  // threads per head
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
                                                                   const float* __restrict__ delta,
                                                                   bf16* __restrict__ dQ, int64_t lddq, int Nq, int Nk,
                                                                   int H, float scale) {
+  pdl_prologue();
   constexpr int LDS = DH + 8, LDT = ATT_CHUNK + 8;
   __shared__ __align__(16) bf16 sA[ATT_ROWS * LDS];   // Q tile, then dO tile (staging for the A fragments)
   __shared__ __align__(16) bf16 sK[ATT_CHUNK * LDS];
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
                                                                    bf16* __restrict__ dK, int64_t lddk,
                                                                    bf16* __restrict__ dV, int64_t lddv, int Nq, int Nk,
                                                                    int H, float scale) {
+  pdl_prologue();
   constexpr int LDS = DH + 8, LDT = ATT_CHUNK + 8;
   __shared__ __align__(16) bf16 sQ[ATT_CHUNK * LDS];
   __shared__ __align__(16) bf16 sdO[ATT_CHUNK * LDS];
@@ -468,9 +472,9 @@ extern "C" int mmae_attention_forward(const void* q, int64_t ldq, const void* k,
     return attn_tc_forward_gen(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, head_dim, scale, st);
   const bf16 *qp = (const bf16*)q, *kp = (const bf16*)k, *vp = (const bf16*)v;
   if (head_dim == 64)
-    attn_fwd_kernel<64><<<grid, ATT_THREADS, 0, st>>>(qp, ldq, kp, ldk, vp, ldv, (bf16*)o, ldo, lse, Nq, Nk, H, scale);
+    launch_k(attn_fwd_kernel<64>, grid, ATT_THREADS, 0, st, qp, ldq, kp, ldk, vp, ldv, (bf16*)o, ldo, lse, Nq, Nk, H, scale);
   else
-    attn_fwd_kernel<32><<<grid, ATT_THREADS, 0, st>>>(qp, ldq, kp, ldk, vp, ldv, (bf16*)o, ldo, lse, Nq, Nk, H, scale);
+    launch_k(attn_fwd_kernel<32>, grid, ATT_THREADS, 0, st, qp, ldq, kp, ldk, vp, ldv, (bf16*)o, ldo, lse, Nq, Nk, H, scale);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -493,7 +497,7 @@ extern "C" int mmae_attention_backward(const void* q, int64_t ldq, const void* k
              *dop = (const bf16*)d_o;
   dim3 gq(ceil_div(Nq, ATT_ROWS), H, B), gk(ceil_div(Nk, ATT_ROWS), H, B);
   if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim)) {
-    attn_delta_kernel<64><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
+    launch_k(attn_delta_kernel<64>, B * Nq, 128, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H);
     count_launch();
     MMAE_LAUNCH_OK();
     return attn_tc_backward(q, ldq, k, ldk, v, ldv, d_o, lddo, lse, delta_ws, dq, lddq, dk, lddk, dv, lddv, B, H, Nq, Nk,
@@ -501,25 +505,25 @@ extern "C" int mmae_attention_backward(const void* q, int64_t ldq, const void* k
   }
   if ((g_attn_tc & 4) && attn_tc_bwd_gen_supported(H, Nq, Nk, head_dim)) {
     if (head_dim == 64)
-      attn_delta_kernel<64><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
+      launch_k(attn_delta_kernel<64>, B * Nq, 128, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H);
     else
-      attn_delta_kernel<32><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
+      launch_k(attn_delta_kernel<32>, B * Nq, 128, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H);
     count_launch();
     MMAE_LAUNCH_OK();
     return attn_tc_backward_gen(q, ldq, k, ldk, v, ldv, d_o, lddo, lse, delta_ws, dq, lddq, dk, lddk, dv, lddv, B, H, Nq,
                                 Nk, head_dim, scale, st);
   }
   if (head_dim == 64) {
-    attn_delta_kernel<64><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
-    attn_bwd_dq_kernel<64><<<gq, ATT_THREADS, 0, st>>>(qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dq,
+    launch_k(attn_delta_kernel<64>, B * Nq, 128, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H);
+    launch_k(attn_bwd_dq_kernel<64>, gq, ATT_THREADS, 0, st, qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dq,
                                                        lddq, Nq, Nk, H, scale);
-    attn_bwd_dkv_kernel<64><<<gk, ATT_THREADS, 0, st>>>(qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dk,
+    launch_k(attn_bwd_dkv_kernel<64>, gk, ATT_THREADS, 0, st, qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dk,
                                                         lddk, (bf16*)dv, lddv, Nq, Nk, H, scale);
   } else {
-    attn_delta_kernel<32><<<B * Nq, 128, 0, st>>>(op, ldo, dop, lddo, delta_ws, Nq, H);
-    attn_bwd_dq_kernel<32><<<gq, ATT_THREADS, 0, st>>>(qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dq,
+    launch_k(attn_delta_kernel<32>, B * Nq, 128, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H);
+    launch_k(attn_bwd_dq_kernel<32>, gq, ATT_THREADS, 0, st, qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dq,
                                                        lddq, Nq, Nk, H, scale);
-    attn_bwd_dkv_kernel<32><<<gk, ATT_THREADS, 0, st>>>(qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dk,
+    launch_k(attn_bwd_dkv_kernel<32>, gk, ATT_THREADS, 0, st, qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dk,
                                                         lddk, (bf16*)dv, lddv, Nq, Nk, H, scale);
   }
   count_launch();

@@ -49,6 +49,7 @@ struct AttnTcParams {
 __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                           const __grid_constant__ CUtensorMap tmK,
                                                           const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const __grid_constant_
                                                           const __grid_constant__ CUtensorMap tmV,
                                                           const __grid_constant__ CUtensorMap tmdO,
                                                           const AttnTcBwdParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_gen_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap tmK,
                                                               const __grid_constant__ CUtensorMap tmV,
                                                               const AttnTcParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -533,7 +536,7 @@ int launch_fwd_gen(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
     MMAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  kern<<<dim3(ceil_div(p.Nq, TQ), p.H, B), 128, SMEM, st>>>(tq, tk, tv, p);
+  launch_k(kern, dim3(ceil_div(p.Nq, TQ), p.H, B), 128, SMEM, st, tq, tk, tv, p);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -586,6 +589,7 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_dkv_gen_kernel(const __grid_c
                                                                   const __grid_constant__ CUtensorMap tmV,
                                                                   const __grid_constant__ CUtensorMap tmdO,
                                                                   const AttnTcBwdGenParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -728,6 +732,7 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_dq_gen_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap tmV,
                                                                  const __grid_constant__ CUtensorMap tmdO,
                                                                  const AttnTcBwdGenParams p) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -863,10 +868,10 @@ int launch_bwd_gen(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
     MMAE_CUDA_OK(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_Q));
     configured = true;
   }
-  kkv<<<dim3(ceil_div(p.Nk, TQ), p.H, B), 128, SMEM_KV, st>>>(tq, tk, tv, tdo, p);
+  launch_k(kkv, dim3(ceil_div(p.Nk, TQ), p.H, B), 128, SMEM_KV, st, tq, tk, tv, tdo, p);
   count_launch();
   MMAE_LAUNCH_OK();
-  kq<<<dim3(ceil_div(p.Nq, TQ), p.H, B), 128, SMEM_Q, st>>>(tq, tk, tv, tdo, p);
+  launch_k(kq, dim3(ceil_div(p.Nq, TQ), p.H, B), 128, SMEM_Q, st, tq, tk, tv, tdo, p);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -943,7 +948,7 @@ int attn_tc_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
     MMAE_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  attn_tc_fwd_kernel<<<dim3(H, B), 128, SMEM, st>>>(tq, tk, tv, p);
+  launch_k(attn_tc_fwd_kernel, dim3(H, B), 128, SMEM, st, tq, tk, tv, p);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -968,7 +973,7 @@ int attn_tc_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, con
     MMAE_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
-  attn_tc_bwd_kernel<<<dim3(H, B), 128, SMEM, st>>>(tq, tk, tv, tdo, p);
+  launch_k(attn_tc_bwd_kernel, dim3(H, B), 128, SMEM, st, tq, tk, tv, tdo, p);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

@@ -56,6 +56,23 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
 int sm_count();  // cached multiprocessor count of the current device
+bool pdl_enabled();   // MMAE_PDL=0 / mmae_set_pdl(0) launches kernels fully serialized (A/B measurements)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 #ifdef __CUDACC__
 
@@ -131,6 +148,19 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   float cdf, e;
   gelu_parts(x, cdf, e);
   return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel is launched with programmatic stream serialization (launch_k) and begins
+// with pdl_prologue(): it lets the NEXT kernel of the stream be scheduled while this one runs (its blocks become resident
+// as resources free up and do their setup), and then waits until the PREVIOUS kernel has completed and flushed its
+// writes before touching global memory.  Removes the dependent-launch gap between the ~830 kernels of a step.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
 }
 
 // 16-byte streaming load: read once, do not keep in L1 (activations streamed by the element-wise kernels)

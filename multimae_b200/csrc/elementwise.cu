@@ -8,6 +8,7 @@ void count_launch();
 namespace {
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n) {
+  pdl_prologue();
   const int64_t stride = int64_t(gridDim.x) * blockDim.x * 8;
   for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     if (i + 8 <= n) {
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const void* __restrict
                                                           bf16* __restrict__ dst, int64_t ld_dst,
                                                           float* __restrict__ colsum, float* __restrict__ partial, int M, int N,
                                                           int rows_per_block) {
+  pdl_prologue();
   __shared__ float4 red[8][32];
   const int col = blockIdx.x * 128 + threadIdx.x * 4;
   const int r0 = blockIdx.y * rows_per_block;
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const void* __restrict
 __global__ void __launch_bounds__(256) colred_finalize_kernel(const float* __restrict__ partial, int Y, int ld, int C, int seg,
                                                               float* __restrict__ d0, float* __restrict__ d1,
                                                               float* __restrict__ d2) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(256) colred_finalize_kernel(const float* __res
 // colsum[n] += sum_m src[m, n] for a bf16 matrix: 8 columns (16 bytes) per thread, 4 rows in flight, block (32, 8)
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict__ src, int64_t ld, float* __restrict__ colsum,
                                                           float* __restrict__ partial, int M, int N, int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[8][32][9];
   const int col = blockIdx.x * 256 + threadIdx.x * 8;
   const int r0 = blockIdx.y * rows_per_block;
@@ -157,6 +161,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16* __restrict
 // instructions/element of erf-GELU overrun; a full-occupancy streaming kernel does not.
 template <bool BACKWARD>
 __global__ void __launch_bounds__(256) gelu_stream_kernel(const bf16* __restrict__ z, bf16* __restrict__ io, int64_t n) {
+  pdl_prologue();
   constexpr int U = 2;   // independent 16-byte loads in flight per thread and stream
   const int64_t stride = int64_t(gridDim.x) * blockDim.x * 8;
   for (int64_t i0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i0 < n; i0 += stride * U) {
@@ -200,6 +205,7 @@ __global__ void __launch_bounds__(256) gelu_stream_kernel(const bf16* __restrict
 __global__ void __launch_bounds__(256) dgelu_colsum_kernel(const bf16* __restrict__ z, bf16* __restrict__ dz, int64_t ld,
                                                            float* __restrict__ colsum, float* __restrict__ partial, int M, int N,
                                                            int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[8][32][9];
   const int col = blockIdx.x * 256 + threadIdx.x * 8;
   const int r0 = blockIdx.y * rows_per_block;
@@ -264,6 +270,7 @@ __global__ void __launch_bounds__(256) dgelu_colsum_kernel(const bf16* __restric
 // out[i] = x[i] + float(y_bf16[i])   (residual add of a bf16 branch output onto the fp32 stream)
 __global__ void __launch_bounds__(256) add_bf16_f32_kernel(const float* __restrict__ x, const bf16* __restrict__ y,
                                                            float* __restrict__ out, int64_t n) {
+  pdl_prologue();
   const int64_t stride = int64_t(gridDim.x) * blockDim.x * 8;
   for (int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(x + i));
@@ -278,6 +285,7 @@ __global__ void __launch_bounds__(256) add_bf16_f32_kernel(const float* __restri
 // 64x64 bf16 tile transpose through padded shared memory; block 256 threads
 __global__ void __launch_bounds__(256) transpose_bf16_kernel(const bf16* __restrict__ src, int64_t ld_src,
                                                              bf16* __restrict__ dst, int64_t ld_dst, int M, int N) {
+  pdl_prologue();
   __shared__ bf16 tile[64][66];
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   // load: each thread reads 2 consecutive columns; 32 threads cover 64 columns, 8 row groups
@@ -354,7 +362,7 @@ float* colred_scratch(size_t floats, cudaStream_t st) {
 int colred_finalize(const float* partial, int Y, int ld, int seg, float* dst0, float* dst1, float* dst2, cudaStream_t st) {
   const int nseg = dst2 ? 3 : (dst1 ? 2 : 1);
   dim3 grid(ceil_div(seg * nseg, 32)), block(32, 8);
-  colred_finalize_kernel<<<grid, block, 0, st>>>(partial, Y, ld, seg * nseg, seg, dst0, dst1, dst2);
+  launch_k(colred_finalize_kernel, grid, block, 0, st, partial, Y, ld, seg * nseg, seg, dst0, dst1, dst2);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -371,8 +379,7 @@ extern "C" int mmae_cast_f32_to_bf16(const float* src, void* dst_bf16, int64_t n
   const int64_t cap = int64_t(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  cast_f32_bf16_kernel<<<(unsigned)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, reinterpret_cast<bf16*>(dst_bf16), n);
+  launch_k(cast_f32_bf16_kernel, (unsigned)blocks, threads, 0, reinterpret_cast<cudaStream_t>(stream), src, reinterpret_cast<bf16*>(dst_bf16), n);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -390,7 +397,7 @@ extern "C" int mmae_cast_colsum_f32(const float* src, int64_t ld_src, void* dst_
     partial = colred_scratch(size_t(grid.y) * N, cst);
     if (!partial) return MMAE_ERR_CUDA;
   }
-  cast_colsum_kernel<false><<<grid, block, 0, cst>>>(src, ld_src, reinterpret_cast<bf16*>(dst_bf16), ld_dst, colsum, partial,
+  launch_k(cast_colsum_kernel<false>, grid, block, 0, cst, src, ld_src, reinterpret_cast<bf16*>(dst_bf16), ld_dst, colsum, partial,
                                                      M, N, rpb);
   count_launch();
   MMAE_LAUNCH_OK();
@@ -412,9 +419,9 @@ extern "C" int mmae_colsum_bf16(const void* src_bf16, int64_t ld_src, float* col
     if (!partial) return MMAE_ERR_CUDA;
   }
   if (wide)
-    colsum_bf16_kernel<<<grid, block, 0, cst>>>(reinterpret_cast<const bf16*>(src_bf16), ld_src, colsum, partial, M, N, rpb);
+    launch_k(colsum_bf16_kernel, grid, block, 0, cst, reinterpret_cast<const bf16*>(src_bf16), ld_src, colsum, partial, M, N, rpb);
   else
-    cast_colsum_kernel<true><<<grid, block, 0, cst>>>(src_bf16, ld_src, nullptr, 0, colsum, partial, M, N, rpb);
+    launch_k(cast_colsum_kernel<true>, grid, block, 0, cst, src_bf16, ld_src, nullptr, 0, colsum, partial, M, N, rpb);
   count_launch();
   MMAE_LAUNCH_OK();
   if (partial) return colred_finalize(partial, grid.y, N, N, colsum, nullptr, nullptr, cst);
@@ -426,8 +433,7 @@ extern "C" int mmae_transpose_bf16(const void* src, int64_t ld_src, void* dst, i
   MMAE_CHECK(src && dst && M > 0 && N > 0 && M % 2 == 0 && N % 2 == 0 && ld_src % 2 == 0 && ld_dst % 2 == 0,
              MMAE_ERR_ARG, "mmae_transpose_bf16: bad args");
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-  transpose_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(src), ld_src, reinterpret_cast<bf16*>(dst), ld_dst, M, N);
+  launch_k(transpose_bf16_kernel, grid, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const bf16*>(src), ld_src, reinterpret_cast<bf16*>(dst), ld_dst, M, N);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -442,9 +448,9 @@ extern "C" int mmae_gelu_bf16(const void* z, void* io, int64_t n, int backward, 
   if (blocks > cap) blocks = cap;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (backward)
-    gelu_stream_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(io), n);
+    launch_k(gelu_stream_kernel<true>, (unsigned)blocks, 256, 0, st, reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(io), n);
   else
-    gelu_stream_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(io), n);
+    launch_k(gelu_stream_kernel<false>, (unsigned)blocks, 256, 0, st, reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(io), n);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -456,8 +462,7 @@ extern "C" int mmae_add_bf16_f32(const float* x, const void* y_bf16, float* out,
   int64_t blocks = (n / 8 + 255) / 256;
   const int64_t cap = int64_t(sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  add_bf16_f32_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, reinterpret_cast<const bf16*>(y_bf16), out, n);
+  launch_k(add_bf16_f32_kernel, (unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), x, reinterpret_cast<const bf16*>(y_bf16), out, n);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -473,7 +478,7 @@ extern "C" int mmae_dgelu_colsum_bf16(const void* z, void* dz, int64_t ld, float
     partial = colred_scratch(size_t(grid.y) * N, cst);
     if (!partial) return MMAE_ERR_CUDA;
   }
-  dgelu_colsum_kernel<<<grid, block, 0, cst>>>(reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(dz), ld, colsum,
+  launch_k(dgelu_colsum_kernel, grid, block, 0, cst, reinterpret_cast<const bf16*>(z), reinterpret_cast<bf16*>(dz), ld, colsum,
                                                partial, M, N, rpb);
   count_launch();
   MMAE_LAUNCH_OK();

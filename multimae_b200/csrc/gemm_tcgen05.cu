@@ -123,6 +123,7 @@ template <int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
     gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const GemmParams p) {
+  pdl_launch_dependents();   // the wait follows the barrier / TMEM setup below
   using L = GemmSmem<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;  // power of two >= 32 (BN in {64,128,256})
 
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, (BN <= 128 ? 2 : 1))
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // the previous kernel's outputs (our operands) are complete and visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -263,7 +265,7 @@ int launch_gemm1(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   }
   dim3 grid(ceil_div(p.N, BN), ceil_div(p.M, BM), split_k);
   const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K, (A_MN ? 1 : 0) | (B_MN ? 2 : 0) | (split_k << 8));
-  kern<<<grid, GEMM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+  launch_k(kern, grid, GEMM_THREADS, L::TOTAL, stream, tmA, tmB, p);
   if (prof) gemm_profile_end(stream);
   count_launch();
   MMAE_LAUNCH_OK();
@@ -380,6 +382,7 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
     gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                 const __grid_constant__ CUtensorMap tmC, const GemmParams p, const Gemm2Sched sc) {
+  pdl_launch_dependents();   // the wait follows the barrier / TMEM setup below
   using C = Gemm2Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -422,6 +425,7 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // the previous kernel's outputs (our operands) are complete and visible from here on
 
   auto decode = [&](int item, int& m0, int& n0, int& kb_begin, int& nkb, int& z) {
     z = item % sc.splits;
@@ -576,7 +580,7 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   sc.total = sc.tiles_m * sc.tiles_n * split_k;
   const int grid = std::min(sc.total, sm_count());
   const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K, (A_MN ? 1 : 0) | (B_MN ? 2 : 0) | (split_k << 8));
-  kern<<<grid, C::THREADS, C::TOTAL, stream>>>(tmA, tmB, tmC, p, sc);
+  launch_k(kern, grid, C::THREADS, C::TOTAL, stream, tmA, tmB, tmC, p, sc);
   if (prof) gemm_profile_end(stream);
   count_launch();
   MMAE_LAUNCH_OK();

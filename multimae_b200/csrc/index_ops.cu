@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(mmae_embed_layout L, 
                                                            const int64_t* __restrict__ ids_keep, int T,
                                                            bf16* __restrict__ A, int* __restrict__ row_task,
                                                            int* __restrict__ row_patch) {
+  pdl_prologue();
   const int r = blockIdx.x;
   const int b = r / T;
   const int g = (int)ids_keep[r];
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) embed_assemble_kernel(const float* __rest
                                                              const int* __restrict__ row_task,
                                                              const int* __restrict__ row_patch, int T, int G, int D,
                                                              float* __restrict__ x) {
+  pdl_prologue();
   const int row = blockIdx.x;  // b*(T+G) + i
   const int b = row / (T + G), i = row % (T + G);
   float4* dst = reinterpret_cast<float4*>(x + int64_t(row) * D);
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(256) embed_assemble_bwd_kernel(const float* __
                                                                  const int* __restrict__ row_task,
                                                                  bf16* __restrict__ dC, mmae_embed_grads grads,
                                                                  int num_tasks) {
+  pdl_prologue();
   // block handles EB_ROWS consecutive sequence rows; thread c handles columns c, c+256, ...
   const int row0 = blockIdx.x * EB_ROWS;
   const int rows_total = B * (T + G);
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(256) semseg_emb_bwd_kernel(const bf16* __restr
                                                              const int* __restrict__ row_patch, int task, int T,
                                                              int rows, int rows_per_cta, int grid_w, int grid_h, int P,
                                                              int E, int num_classes, float* __restrict__ dtable) {
+  pdl_prologue();
   extern __shared__ float tab[];  // [num_classes * E]
   for (int i = threadIdx.x; i < num_classes * E; i += blockDim.x) tab[i] = 0.f;
   __syncthreads();
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(64) dec_build_kernel(const float* __restrict__
                                                        const float* __restrict__ mask_token, TaskEmbPtrs task_emb,
                                                        const float* __restrict__ pos,  // [P, Dd]
                                                        float* __restrict__ queries, float* __restrict__ context) {
+  pdl_prologue();
   const int Dd = ix.dim, T = ix.num_visible, G = ix.num_global, P = ix.num_queries;
   const int row = blockIdx.x;
   const int nq_rows = ix.batch * P;
@@ -218,6 +223,7 @@ __global__ void __launch_bounds__(256) dec_build_bwd_kernel(const float* __restr
                                                             const float* __restrict__ dcontext, mmae_decoder_index ix,
                                                             float* __restrict__ dctx, float* __restrict__ dmask_token,
                                                             TaskEmbGradPtrs dtask_emb) {
+  pdl_prologue();
   const int Dd = ix.dim, T = ix.num_visible, G = ix.num_global, P = ix.num_queries;
   const int nq_rows = ix.batch * P, nc_rows = ix.batch * (T + G);
   const int row0 = blockIdx.x * DB_ROWS;
@@ -270,6 +276,7 @@ __global__ void __launch_bounds__(256) dec_build_bwd_kernel(const float* __restr
 template <bool TO_IMAGE, typename TokT>
 __global__ void __launch_bounds__(256) unpatchify_kernel(TokT* __restrict__ tok, int64_t ld_tok, float* __restrict__ img,
                                                          int B, int C, int nh, int nw, int P) {
+  pdl_prologue();
   const int W = nw * P, H = nh * P;
   const int b = blockIdx.x / nh, ph = blockIdx.x % nh;
   const int groups_per_tok = C * P * P / 4;
@@ -298,6 +305,7 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(TokT* __restrict__ tok,
 
 __global__ void cast2d_kernel(const float* __restrict__ src, int64_t ld_src, bf16* __restrict__ dst, int64_t ld_dst,
                               int rows, int cols) {
+  pdl_prologue();
   const int r = blockIdx.y;
   for (int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4; c < cols; c += gridDim.x * blockDim.x * 4) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(src + int64_t(r) * ld_src + c));
@@ -313,7 +321,7 @@ __global__ void cast2d_kernel(const float* __restrict__ src, int64_t ld_src, bf1
 // ---- internal launchers shared with modules.cu ------------------------------------------------------------------------
 int launch_embed_gather(const mmae_embed_layout& L, const mmae_embed_inputs& in, const int64_t* ids_keep, int B, int T,
                         bf16* A, int* row_task, int* row_patch, cudaStream_t st) {
-  embed_gather_kernel<<<B * T, 256, 0, st>>>(L, in, ids_keep, T, A, row_task, row_patch);
+  launch_k(embed_gather_kernel, B * T, 256, 0, st, L, in, ids_keep, T, A, row_task, row_patch);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -321,7 +329,7 @@ int launch_embed_gather(const mmae_embed_layout& L, const mmae_embed_inputs& in,
 
 int launch_embed_assemble(const float* Cmat, const mmae_embed_params& prm, const int* row_task, const int* row_patch,
                           int B, int T, int G, int D, float* x, cudaStream_t st) {
-  embed_assemble_kernel<<<B * (T + G), 256, 0, st>>>(Cmat, prm, row_task, row_patch, T, G, D, x);
+  launch_k(embed_assemble_kernel, B * (T + G), 256, 0, st, Cmat, prm, row_task, row_patch, T, G, D, x);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -329,7 +337,7 @@ int launch_embed_assemble(const float* Cmat, const mmae_embed_params& prm, const
 
 int launch_embed_assemble_bwd(const float* dx, int B, int T, int G, int D, const int* row_task, bf16* dC,
                               const mmae_embed_grads& grads, int num_tasks, cudaStream_t st) {
-  embed_assemble_bwd_kernel<<<ceil_div(B * (T + G), EB_ROWS), 256, 0, st>>>(dx, T, G, D, B, row_task, dC, grads,
+  launch_k(embed_assemble_bwd_kernel, ceil_div(B * (T + G), EB_ROWS), 256, 0, st, dx, T, G, D, B, row_task, dC, grads,
                                                                             num_tasks);
   count_launch();
   MMAE_LAUNCH_OK();
@@ -348,7 +356,7 @@ int launch_semseg_emb_bwd(const bf16* dA, int64_t ld_dA, const int64_t* labels, 
   }
   const int ctas = std::min(rows, 2 * sm_count());
   const int rows_per_cta = ceil_div(rows, ctas);
-  semseg_emb_bwd_kernel<<<ceil_div(rows, rows_per_cta), 256, smem, st>>>(dA, ld_dA, labels, ids_keep, row_task,
+  launch_k(semseg_emb_bwd_kernel, ceil_div(rows, rows_per_cta), 256, smem, st, dA, ld_dA, labels, ids_keep, row_task,
                                                                           row_patch, task, T, rows, rows_per_cta,
                                                                           grid_w, grid_h, P, E, num_classes, dtable);
   count_launch();
@@ -359,7 +367,7 @@ int launch_semseg_emb_bwd(const bf16* dA, int64_t ld_dA, const int64_t* labels, 
 int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float* mask_token, const TaskEmbPtrs& task_emb,
                      const float* pos, float* queries, float* context, cudaStream_t st) {
   const int rows = ix.batch * ix.num_queries + ix.batch * (ix.num_visible + ix.num_global);
-  dec_build_kernel<<<rows, 64, 0, st>>>(ctx, ix, mask_token, task_emb, pos, queries, context);
+  launch_k(dec_build_kernel, rows, 64, 0, st, ctx, ix, mask_token, task_emb, pos, queries, context);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -368,7 +376,7 @@ int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float
 int launch_dec_build_bwd(const float* dqueries, const float* dcontext, const mmae_decoder_index& ix, float* dctx,
                          float* dmask_token, const TaskEmbGradPtrs& dtask_emb, cudaStream_t st) {
   const int rows = ix.batch * ix.num_queries + ix.batch * (ix.num_visible + ix.num_global);
-  dec_build_bwd_kernel<<<ceil_div(rows, DB_ROWS), 256, 0, st>>>(dqueries, dcontext, ix, dctx, dmask_token, dtask_emb);
+  launch_k(dec_build_bwd_kernel, ceil_div(rows, DB_ROWS), 256, 0, st, dqueries, dcontext, ix, dctx, dmask_token, dtask_emb);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -376,7 +384,7 @@ int launch_dec_build_bwd(const float* dqueries, const float* dcontext, const mma
 
 int launch_cast2d(const float* src, int64_t ld_src, bf16* dst, int64_t ld_dst, int rows, int cols, cudaStream_t st) {
   dim3 grid(std::max(1, std::min(8, ceil_div(cols, 1024))), rows);
-  cast2d_kernel<<<grid, 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, cols);
+  launch_k(cast2d_kernel, grid, 256, 0, st, src, ld_src, dst, ld_dst, rows, cols);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -390,8 +398,7 @@ extern "C" int mmae_unpatchify(const float* tokens, int64_t ld_tok, float* image
                                void* stream) {
   MMAE_CHECK(tokens && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG, "mmae_unpatchify: bad args");
   MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_unpatchify: P and ld must be multiples of 4");
-  unpatchify_kernel<true, const float><<<B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tokens, ld_tok, image, B, C, nh, nw, P);
+  launch_k(unpatchify_kernel<true, const float>, B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream), tokens, ld_tok, image, B, C, nh, nw, P);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -401,8 +408,7 @@ extern "C" int mmae_unpatchify_bf16(const void* tokens_bf16, int64_t ld_tok, flo
                                     int P, void* stream) {
   MMAE_CHECK(tokens_bf16 && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG, "mmae_unpatchify_bf16: bad args");
   MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_unpatchify_bf16: P and ld must be multiples of 4");
-  unpatchify_kernel<true, const bf16><<<B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(tokens_bf16), ld_tok, image, B, C, nh, nw, P);
+  launch_k(unpatchify_kernel<true, const bf16>, B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const bf16*>(tokens_bf16), ld_tok, image, B, C, nh, nw, P);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -413,8 +419,7 @@ extern "C" int mmae_patchify_bf16(const float* image, void* tokens_bf16, int64_t
   MMAE_CHECK(tokens_bf16 && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG,
              "mmae_patchify_bf16: bad args");
   MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_patchify_bf16: P and ld must be multiples of 4");
-  unpatchify_kernel<false, bf16><<<B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<bf16*>(tokens_bf16), ld_tok, const_cast<float*>(image), B, C, nh, nw, P);
+  launch_k(unpatchify_kernel<false, bf16>, B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<bf16*>(tokens_bf16), ld_tok, const_cast<float*>(image), B, C, nh, nw, P);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
                                                                int64_t ldy, float* __restrict__ y_f32, int64_t ldyf,
                                                                float* __restrict__ mean_out,
                                                                float* __restrict__ rstd_out, int M, float eps) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= M) return;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const void* __res
                                                                float* __restrict__ dx, int64_t lddx,
                                                                float* __restrict__ partial, bool want_colsum,
                                                                bf16* __restrict__ dx_bf16, int64_t lddxb, int M) {
+  pdl_prologue();
   constexpr int D = NVEC * 128;
   __shared__ float4 red[LN_WARPS][32];
   __shared__ float4 sgamma[NVEC * 32];
@@ -239,7 +241,7 @@ static int ln_forward_impl(const float* x, int64_t ldx, const bf16* addend, int6
   bf16* yb = reinterpret_cast<bf16*>(y_bf16);
 #define LN_CASE(NV)                                                                                            \
   case NV:                                                                                                     \
-    ln_fwd_kernel<NV><<<grid, block, 0, st>>>(x, ldx, addend, ldadd, x_sum, ldsum, gamma, beta, yb, ldy, y_f32, ldyf, \
+    launch_k(ln_fwd_kernel<NV>, grid, block, 0, st, x, ldx, addend, ldadd, x_sum, ldsum, gamma, beta, yb, ldy, y_f32, ldyf, \
                                               mean, rstd, M, eps);                                            \
     break;
   switch (D / 128) {
@@ -290,10 +292,10 @@ static int ln_backward_impl(const void* dy, int dy_is_bf16, int64_t lddy, const 
 #define LNB_CASE(NV)                                                                                              \
   case NV:                                                                                                        \
     if (dy_is_bf16)                                                                                               \
-      ln_bwd_kernel<NV, true><<<grid, block, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx,     \
+      launch_k(ln_bwd_kernel<NV, true>, grid, block, 0, st, dy, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx,     \
                                                       lddx, partial, dx_colsum != nullptr, dx_bf16, lddxb, M);   \
     else                                                                                                          \
-      ln_bwd_kernel<NV, false><<<grid, block, 0, st>>>(dy, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx,    \
+      launch_k(ln_bwd_kernel<NV, false>, grid, block, 0, st, dy, lddy, x, ldx, mean, rstd, gamma, dx_resid, ldr, dx,    \
                                                        lddx, partial, dx_colsum != nullptr, dx_bf16, lddxb, M);  \
     break;
   switch (D / 128) {

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) regr_loss_kernel(int kind, int n
                                                                  const float* __restrict__ coef,
                                                                  const float* __restrict__ grad_out,
                                                                  float* __restrict__ dpred) {
+  pdl_prologue();
   __shared__ float red[LOSS_THREADS / 32];
   const int nh = H / P, nw = W / P;
   const int b = blockIdx.x / nh, ph = blockIdx.x % nh;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) ce_loss_kernel(const float* __re
                                                                const float* __restrict__ coef,
                                                                const float* __restrict__ grad_out,
                                                                float* __restrict__ dlogits) {
+  pdl_prologue();
   __shared__ unsigned char pmask[MAX_NW];
   __shared__ float red[LOSS_THREADS / 32];
   const int nh = H / P, nw = W / P;
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restr
                                                             const int64_t* __restrict__ mask, int B, int npatch,
                                                             float pix_per_patch, float chan_div, float* __restrict__ coef,
                                                             float* __restrict__ loss) {
+  pdl_prologue();
   __shared__ float s_acc[256], s_valid[256];
   float acc = 0.f, valid = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -222,16 +225,16 @@ extern "C" int mmae_masked_loss_forward(int kind, int norm_pix, float label_smoo
   MMAE_CUDA_OK(cudaMemsetAsync(sample_sum, 0, sizeof(float) * B, st));
   const int nh = H / scale, nw = W / scale;
   if (kind == 2) {
-    ce_loss_kernel<false><<<B * nh, LOSS_THREADS, 0, st>>>(pred, reinterpret_cast<const int64_t*>(target), mask, C, H, W,
+    launch_k(ce_loss_kernel<false>, B * nh, LOSS_THREADS, 0, st, pred, reinterpret_cast<const int64_t*>(target), mask, C, H, W,
                                                            scale, label_smoothing, sample_sum, nullptr, nullptr, nullptr);
   } else {
-    regr_loss_kernel<false><<<B * nh, LOSS_THREADS, 0, st>>>(kind, norm_pix, pred, reinterpret_cast<const float*>(target),
+    launch_k(regr_loss_kernel<false>, B * nh, LOSS_THREADS, 0, st, kind, norm_pix, pred, reinterpret_cast<const float*>(target),
                                                              mask, C, H, W, scale, sample_sum, nullptr, nullptr, nullptr);
   }
   count_launch();
   MMAE_LAUNCH_OK();
   // mask == NULL ("loss on unmasked"): plain mean over every element == per-sample means averaged (equal counts)
-  loss_finalize_kernel<<<1, 256, 0, st>>>(sample_sum, mask, B, nh * nw, float(scale) * scale, kind == 2 ? 1.f : float(C),
+  launch_k(loss_finalize_kernel, 1, 256, 0, st, sample_sum, mask, B, nh * nw, float(scale) * scale, kind == 2 ? 1.f : float(C),
                                           coef, loss_out);
   count_launch();
   MMAE_LAUNCH_OK();
@@ -250,10 +253,10 @@ extern "C" int mmae_masked_loss_backward(int kind, int norm_pix, float label_smo
   const float* coef = ws + B;
   const int nh = H / scale;
   if (kind == 2) {
-    ce_loss_kernel<true><<<B * nh, LOSS_THREADS, 0, st>>>(pred, reinterpret_cast<const int64_t*>(target), mask, C, H, W,
+    launch_k(ce_loss_kernel<true>, B * nh, LOSS_THREADS, 0, st, pred, reinterpret_cast<const int64_t*>(target), mask, C, H, W,
                                                           scale, label_smoothing, nullptr, coef, grad_out, dpred);
   } else {
-    regr_loss_kernel<true><<<B * nh, LOSS_THREADS, 0, st>>>(kind, norm_pix, pred, reinterpret_cast<const float*>(target),
+    launch_k(regr_loss_kernel<true>, B * nh, LOSS_THREADS, 0, st, kind, norm_pix, pred, reinterpret_cast<const float*>(target),
                                                             mask, C, H, W, scale, nullptr, coef, grad_out, dpred);
   }
   count_launch();

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(MS_THREADS) mask_sampler_kernel(const float* _
                                                                   int64_t* __restrict__ task_masks,
                                                                   int64_t* __restrict__ ids_keep,
                                                                   int64_t* __restrict__ ids_restore) {
+  pdl_prologue();
   extern __shared__ unsigned long long keys[];  // n_pad entries
   const int b = blockIdx.x;
   const int total = tasks.offset[tasks.num_tasks];
@@ -130,8 +131,7 @@ extern "C" int mmae_sample_masks(const float* shares, const float* noise_task, c
     MMAE_CUDA_OK(cudaFuncSetAttribute(mask_sampler_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  mask_sampler_kernel<<<B, MS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      shares, noise_task, noise_all, tasks, num_encoded, task_masks, ids_keep, ids_restore);
+  launch_k(mask_sampler_kernel, B, MS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), shares, noise_task, noise_all, tasks, num_encoded, task_masks, ids_keep, ids_restore);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

@@ -15,6 +15,7 @@ namespace {
 // out[0] += sum(g^2) after unscaling, out[1] = 1.0 if any non-finite value was seen (left untouched otherwise)
 __global__ void __launch_bounds__(256) unscale_norm_kernel(float* __restrict__ g, int64_t n, const float* __restrict__ inv_scale_ptr,
                                                            float inv_scale_imm, float post_scale, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[8];
   const float inv = (inv_scale_ptr ? inv_scale_ptr[0] : inv_scale_imm) * post_scale;
   float acc = 0.f;
@@ -59,7 +60,8 @@ __global__ void __launch_bounds__(256) unscale_norm_kernel(float* __restrict__ g
   if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) out[1] = 1.0f;
 }
 
-__global__ void sqrt_kernel(const float* __restrict__ in, float* __restrict__ norm_out) { norm_out[0] = sqrtf(in[0]); }
+__global__ void sqrt_kernel(const float* __restrict__ in, float* __restrict__ norm_out) {
+  pdl_prologue(); norm_out[0] = sqrtf(in[0]); }
 
 // decoupled weight decay AdamW, skipping the whole update when found_inf[0] != 0 (GradScaler.step semantics)
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float eps, float wd, float bc1, float bc2_sqrt,
                                                     const float* __restrict__ found_inf, const float* __restrict__ dyn,
                                                     bf16* __restrict__ mirror) {
+  pdl_prologue();
   if (found_inf != nullptr && found_inf[0] != 0.f) return;
   if (dyn != nullptr) {   // learning rate and step count live on the device (CUDA-graph replay): dyn = {lr, step}
     lr = dyn[0];
@@ -128,12 +131,12 @@ extern "C" int mmae_grad_unscale_norm(float* grads, int64_t n, const float* inv_
     const int64_t cap = int64_t(sm_count()) * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    unscale_norm_kernel<<<(unsigned)blocks, 256, 0, st>>>(grads, n, inv_scale_dev, inv_scale, post_scale, out2);
+    launch_k(unscale_norm_kernel, (unsigned)blocks, 256, 0, st, grads, n, inv_scale_dev, inv_scale, post_scale, out2);
     count_launch();
     MMAE_LAUNCH_OK();
   }
   if (norm_out) {
-    sqrt_kernel<<<1, 1, 0, st>>>(out2, norm_out);
+    launch_k(sqrt_kernel, 1, 1, 0, st, out2, norm_out);
     count_launch();
     MMAE_LAUNCH_OK();
   }
@@ -151,8 +154,7 @@ extern "C" int mmae_adamw_step(float* params, const float* grads, float* exp_avg
   const int64_t cap = int64_t(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  adamw_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, found_inf_dev, dyn_lr_step_dev,
+  launch_k(adamw_kernel, (unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, found_inf_dev, dyn_lr_step_dev,
       const_cast<bf16*>(mirror_lookup(params)));
   count_launch();
   MMAE_LAUNCH_OK();

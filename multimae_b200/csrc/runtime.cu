@@ -198,6 +198,18 @@ extern "C" int mmae_weight_mirror_register(const float* params_f32, void* mirror
   return MMAE_OK;
 }
 
+namespace mmae {
+static int g_pdl = []() {
+  const char* e = getenv("MMAE_PDL");
+  return e ? atoi(e) : 1;
+}();
+bool pdl_enabled() { return g_pdl != 0; }
+}  // namespace mmae
+extern "C" int mmae_set_pdl(int enable) {
+  mmae::g_pdl = enable != 0;
+  return MMAE_OK;
+}
+
 extern "C" int mmae_abi_version(void) { return MMAE_ABI_VERSION; }
 extern "C" const char* mmae_last_error(void) { return mmae::g_err; }
 extern "C" int64_t mmae_launch_count(void) { return mmae::g_launches.load(std::memory_order_relaxed); }
