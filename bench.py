@@ -143,7 +143,7 @@ def run_ours(args, rank, world, local_rank):
     from multimae_b200.train_step import TrainStep
     stepper = TrainStep(model, loss_fns, opt, scaler, num_encoded_tokens=98, alphas=1.0, loss_sources={"norm_rgb": "rgb"})
     mode = "eager"
-    if args.graph and world == 1:
+    if (args.graph and world == 1) or args.graph >= 2:
         try:
             stepper.capture(resident[0], warmup=3)
             mode = "cuda-graph (whole step = one graph launch)"
@@ -382,7 +382,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (BASELINE: 128)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-baseline"])
-    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (single GPU)")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (single GPU); 2: also with data parallelism "
+                         "(NCCL all-reduces captured in the graph)")
     ap.add_argument("--gemm-shapes", default=None, help="write a per-shape GEMM time table of one profiled step here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

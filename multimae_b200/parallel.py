@@ -22,7 +22,7 @@ class FlatGradReducer:
         cur_names, hi, lo = set(), None, None
         for name in reversed(list(param_names_in_registration_order)):
             o, n, _ = arena.offsets[name]
-            end = o + (n + 3) // 4 * 4
+            end = o + (n + 7) // 8 * 8
             if hi is None:
                 hi = end
             lo = o
