@@ -335,28 +335,70 @@ static int colsum_rows_per_block(int M, int col_blocks, int blocks_per_sm) {
 
 namespace mmae {
 float* colred_scratch(size_t floats, cudaStream_t st) {
-  static float* buf = nullptr;
-  static size_t cap = 0;
-  if (floats <= cap) return buf;
+  // One buffer per stream: kernels of different streams (the task decoders) run concurrently.  All buffers are created
+  // by the first call (which must not be inside a stream capture), so a stream first seen during a capture still gets one.
+  constexpr int MAX_SLOTS = 12;
+  constexpr size_t DEFAULT_FLOATS = size_t(2) << 20;   // 8 MB each covers every shape of the MultiMAE-B step
+  struct Slot {
+    cudaStream_t st;
+    bool bound;
+    float* buf;
+    size_t cap;
+    uint64_t last_use;
+  };
+  static Slot slots[MAX_SLOTS];
+  static bool created = false;
+  static uint64_t tick = 0;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cs);
-  if (cs != cudaStreamCaptureStatusNone) {
+  const bool capturing = cs != cudaStreamCaptureStatusNone;
+  if (!created) {
+    if (capturing) {
+      set_last_error("column-reduction scratch must be created outside stream capture: run the step once eagerly first");
+      return nullptr;
+    }
+    for (int i = 0; i < MAX_SLOTS; ++i) {
+      slots[i] = {nullptr, false, nullptr, 0, 0};
+      if (cudaMalloc(&slots[i].buf, DEFAULT_FLOATS * sizeof(float)) != cudaSuccess) {
+        set_last_error("cudaMalloc of the column-reduction scratch failed");
+        return nullptr;
+      }
+      slots[i].cap = DEFAULT_FLOATS;
+    }
+    created = true;
+  }
+  Slot* s = nullptr;
+  for (int i = 0; i < MAX_SLOTS && s == nullptr; ++i)
+    if (slots[i].bound && slots[i].st == st) s = &slots[i];
+  for (int i = 0; i < MAX_SLOTS && s == nullptr; ++i)
+    if (!slots[i].bound) {
+      s = &slots[i];
+      s->bound = true;
+      s->st = st;
+    }
+  if (s == nullptr) {   // every slot is bound: hand the least recently used one to this stream
+    s = &slots[0];
+    for (int i = 1; i < MAX_SLOTS; ++i)
+      if (slots[i].last_use < s->last_use) s = &slots[i];
+    s->st = st;
+  }
+  s->last_use = ++tick;
+  if (floats <= s->cap) return s->buf;
+  if (capturing) {
     set_last_error("column-reduction scratch must grow to %zu floats during stream capture: run the step once eagerly first",
                    floats);
     return nullptr;
   }
-  // growing frees the old buffer: drain the device first (rare: first call, or a larger problem than any before)
-  cudaDeviceSynchronize();
-  if (buf) cudaFree(buf);
-  const size_t want = std::max(floats, size_t(4) << 20);   // 16 MB covers every shape of the MultiMAE-B step
-  if (cudaMalloc(&buf, want * sizeof(float)) != cudaSuccess) {
-    buf = nullptr;
-    cap = 0;
-    set_last_error("cudaMalloc of the column-reduction scratch (%zu bytes) failed", want * sizeof(float));
+  cudaDeviceSynchronize();   // growing frees the old buffer: drain the device first (rare)
+  cudaFree(s->buf);
+  s->buf = nullptr;
+  s->cap = 0;
+  if (cudaMalloc(&s->buf, floats * sizeof(float)) != cudaSuccess) {
+    set_last_error("cudaMalloc of the column-reduction scratch (%zu bytes) failed", floats * sizeof(float));
     return nullptr;
   }
-  cap = want;
-  return buf;
+  s->cap = floats;
+  return s->buf;
 }
 
 int colred_finalize(const float* partial, int Y, int ld, int seg, float* dst0, float* dst1, float* dst2, cudaStream_t st) {

@@ -22,12 +22,14 @@ def _require_cuda(t, what):
 
 
 class Workspace:
-    """One growable scratch buffer per device, reused by every Function (all launches are stream-ordered)."""
+    """One growable scratch buffer per (device, stream), reused by every Function launched on that stream (launches on
+    one stream are ordered; the task decoders run on their own streams and must not share scratch)."""
     _bufs = {}
 
     @classmethod
     def get(cls, nbytes, device):
-        key = (device.type, device.index)
+        stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
+        key = (device.type, device.index, stream)
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=device)

@@ -6,6 +6,7 @@ unchanged.  What differs is the execution plan: gather-first patch e
 fused transformer blocks, fused decoder head/tail, gradients accumulated into one flat arena.
 """
 import itertools
+import os
 import math
 import warnings
 from collections import OrderedDict
@@ -113,6 +114,9 @@ class MultiMAE(nn.Module):
         self._grad_callback = None
         self._warned_fp32 = False
         self.external_shares = None
+        # task decoders on concurrent CUDA streams (MMAE_DECODER_STREAMS=0 runs them one after the other)
+        self.decoder_streams = os.environ.get("MMAE_DECODER_STREAMS", "1") != "0"
+        self._dec_streams = None
 
     def draw_task_shares(self, B, n_tasks, alphas=1.0, sample_tasks_uniformly=False):
         """Host-side Dirichlet draw of generate_random_masks (multimae/multimae.py:182-187) as a separate step."""
@@ -316,10 +320,34 @@ class MultiMAE(nn.Module):
                           "(bf16 has fp32's exponent range, which removes the fp16 overflow the flag works around)"
                           % list(fp32_output_adapters))
             self._warned_fp32 = True
-        preds = {domain: self.output_adapters[domain](encoder_tokens=encoder_tokens, input_info=input_info,
-                                                      ids_keep=ids_keep, ids_restore=ids_restore)
-                 for domain in self.output_adapters}
+        preds = self._decode(encoder_tokens, input_info, ids_keep, ids_restore)
         return preds, task_masks
+
+    def _decode(self, encoder_tokens, input_info, ids_keep, ids_restore):
+        """The task decoders are independent of each other (multimae/multimae.py:372-381 runs them in a Python loop):
+        on CUDA each runs on its own stream, forward and (through autograd's stream tracking) backward, so their
+        1.3-wave GEMMs, phase-locked attention CTAs and element-wise tails fill each other's idle SMs."""
+        domains = list(self.output_adapters)
+        kw = dict(encoder_tokens=encoder_tokens, input_info=input_info, ids_keep=ids_keep, ids_restore=ids_restore)
+        if not (self.decoder_streams and encoder_tokens.is_cuda and len(domains) > 1):
+            return {d: self.output_adapters[d](**kw) for d in domains}
+        dev = encoder_tokens.device
+        if self._dec_streams is None or len(self._dec_streams) != len(domains):
+            self._dec_streams = [torch.cuda.Stream(device=dev) for _ in domains]
+        main = torch.cuda.current_stream(dev)
+        ready = main.record_event()
+        preds = {}
+        for d, st in zip(domains, self._dec_streams):
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                preds[d] = self.output_adapters[d](**kw)
+        for d, st in zip(domains, self._dec_streams):
+            main.wait_stream(st)
+            preds[d].record_stream(main)              # allocated on the side stream, consumed (loss) on this one
+        for t in (encoder_tokens, ids_keep, ids_restore):
+            for st in self._dec_streams:
+                t.record_stream(st)
+        return preds
 
 
 @register_model

@@ -40,9 +40,18 @@ class FlatGradReducer:
     def reset(self):
         self._pending = [len(b[2]) for b in self.buckets]
         self._works = []
+        self._events = [[] for _ in self.buckets]      # completion events of producers that ran on other streams
 
     def on_grads_ready(self, names):
         """Called from backward (after the producing kernels were enqueued on the current stream)."""
+        cuda = self.arena.flat.is_cuda
+        touched = {self.bucket_of[n] for n in names if n in self.bucket_of}
+        if cuda and self.world > 1:
+            # the task decoders run their backward on their own streams: the reduction of a bucket has to follow every
+            # producer stream, not only the one that happens to complete the bucket
+            ev = torch.cuda.current_stream().record_event()
+            for i in touched:
+                self._events[i].append(ev)
         for n in names:
             i = self.bucket_of.get(n)
             if i is None:
@@ -50,6 +59,10 @@ class FlatGradReducer:
             self._pending[i] -= 1
             if self._pending[i] == 0 and self.world > 1:
                 lo, hi, _ = self.buckets[i]
+                if cuda:
+                    cur = torch.cuda.current_stream()
+                    for e in self._events[i]:
+                        cur.wait_event(e)
                 self._works.append(dist.all_reduce(self.arena.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
                                                    async_op=True))
 
@@ -59,6 +72,9 @@ class FlatGradReducer:
             missing = [i for i, p in enumerate(self._pending) if p > 0]
             for i in missing:                      # parameters that received no gradient this step (still exchanged)
                 lo, hi, _ = self.buckets[i]
+                if self.arena.flat.is_cuda:
+                    for e in self._events[i]:
+                        torch.cuda.current_stream().wait_event(e)
                 self._works.append(dist.all_reduce(self.arena.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
                                                    async_op=True))
             for w in self._works:

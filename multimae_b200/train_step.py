@@ -74,7 +74,7 @@ class TrainStep:
         lib = L.lib()
         lib.mmae_set_pdl(0)
         try:
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=side):   # the warm-up stream: per-stream scratch already exists
                 self.static_out = self._step(self.static_x)
         finally:
             lib.mmae_set_pdl(1 if self._pdl_default else 0)
