@@ -192,47 +192,90 @@ def run_ours(args, rank, world, local_rank):
         _note("leg 1 (HBM-resident inputs): %.3f ms/step" % (ms_total / args.steps))
     # ------------------------------------------------------------------ leg 2: end to end through the public API
     # pinned host inputs -> H2D every step (prefetched on a copy stream, inside the timed region) + loss read back (D2H)
-    copy_stream = torch.cuda.Stream(device=device)
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
-
-    def prefetch(i):
-        with torch.cuda.stream(copy_stream):
-            dst = {k: v.to(device, non_blocking=True) for k, v in host[i % 2].items()}
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return dst, ev
+    from multimae_b200.train_step import InputPrefetcher
+    feeder = InputPrefetcher(host[0], device)
+    h2d_bytes = feeder.bytes_per_batch
+    # what the host link of this box delivers for exactly these copies, alone (context for the e2e figure)
+    for _ in range(2):
+        feeder.submit(host[0])
+        feeder.release(feeder.get()[0])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(4):
+        feeder.submit(host[i % 2])
+        feeder.release(feeder.get()[0])
+    torch.cuda.synchronize()
+    h2d_gbs = 4 * h2d_bytes / (time.perf_counter() - t0) / 1e9
+    if rank == 0:
+        _note("H2D of one input batch alone: %.1f MB at %.1f GB/s = %.2f ms" % (h2d_bytes / 1e6, h2d_gbs, h2d_bytes / h2d_gbs / 1e6))
 
     # The loss of every step is read on the host exactly once, one step late: its D2H copy into a pinned slot is enqueued
     # behind the step, and the host waits for it only after the NEXT step has been launched, so the device never idles
     # on the host round trip (the reference's `loss.item()` right after the step stalls the launch queue every step).
     loss_slots = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_events = [torch.cuda.Event() for _ in range(2)]
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    nxt = prefetch(0)
-    host_losses = []
-    for i in range(args.steps):
-        cur, ev = nxt
-        torch.cuda.current_stream().wait_event(ev)
-        if i + 1 < args.steps:
-            nxt = prefetch(i + 1)
-        loss, _ = train_step(cur)
-        for v in cur.values():
-            v.record_stream(torch.cuda.current_stream())
-        loss_slots[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)      # D2H read of the step's result
-        loss_events[i % 2].record()
-        if i > 0:
-            loss_events[(i - 1) % 2].synchronize()
-            host_losses.append(float(loss_slots[(i - 1) % 2]))
-    loss_events[(args.steps - 1) % 2].synchronize()
-    host_losses.append(float(loss_slots[(args.steps - 1) % 2]))
-    e1.record()
-    barrier()
-    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    def e2e_leg(use_graph):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        feeder.submit(host[0])
+        host_losses = []
+        for i in range(args.steps):
+            slot, cur = feeder.get()
+            if i + 1 < args.steps:
+                feeder.submit(host[(i + 1) % 2])
+            loss, _ = stepper(cur, use_graph=use_graph)
+            feeder.release(slot)
+            loss_slots[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)      # D2H read of the step's result
+            loss_events[i % 2].record()
+            if i > 0:
+                loss_events[(i - 1) % 2].synchronize()
+                host_losses.append(float(loss_slots[(i - 1) % 2]))
+        loss_events[(args.steps - 1) % 2].synchronize()
+        host_losses.append(float(loss_slots[(args.steps - 1) % 2]))
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # (The replayed step issues no host -> device copy of its own: a small H2D on the compute stream would queue behind the
+    # in-flight 106 MB input copy on the H2D engine and stall the step by the ~2 ms that copy takes - measured.)
+    ms_e2e, e2e_mode = e2e_leg(True), ("cuda-graph" if stepper.graph is not None else "eager")
 
     if rank == 0:
         _note("leg 2 (pinned host inputs, loss read back): %.3f ms/step" % (ms_e2e / args.steps))
+    if args.e2e_probe:
+        def timed(use_h2d, consume, read_loss, submit_after=False):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            if use_h2d:
+                feeder.submit(host[0])
+            for i in range(args.steps):
+                cur = resident[i % 2]
+                if use_h2d:
+                    slot, got = feeder.get()
+                    if consume:
+                        cur = got
+                    if i + 1 < args.steps and not submit_after:
+                        feeder.submit(host[(i + 1) % 2])
+                loss, _ = train_step(cur)
+                if use_h2d:
+                    feeder.release(slot)
+                    if i + 1 < args.steps and submit_after:
+                        feeder.submit(host[(i + 1) % 2])
+                if read_loss:
+                    loss_slots[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
+                    loss_events[i % 2].record()
+                    if i > 0:
+                        loss_events[(i - 1) % 2].synchronize()
+            b.record()
+            barrier()
+            return a.elapsed_time(b) / args.steps
+        for name, cfg in (("no H2D, no loss read", (False, False, False)), ("no H2D, loss read", (False, False, True)),
+                          ("H2D not consumed, loss read", (True, False, True)), ("H2D consumed, no loss read", (True, True, False)),
+                          ("H2D consumed, loss read", (True, True, True)),
+                          ("H2D consumed, loss read, submit after launch", (True, True, True, True))):
+            _note("probe %-46s %.3f ms/step" % (name, timed(*cfg)))
     # ------------------------------------------------------------------ roofline of the dominant kernel (tcgen05 GEMM)
     peak_tf, peak_gbs, peak_src = peaks()
     lib.mmae_profile_gemm(1)
@@ -276,9 +319,11 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "global_batch": args.batch * world, "per_gpu_batch": args.batch,
                    "parallelism": "dp%d" % world,
                    "l2": "two alternating input batches (212 MB) and a >9 GB per-step activation working set exceed the 126 MB L2",
-                   "loss_scaling": "none (bf16)", "final_loss": round(final_loss, 4), "launch_mode": mode},
+                   "loss_scaling": "none (bf16)",
+                   "e2e_pipeline": "H2D of step i+1 prefetched on a copy stream during step i; every step's loss read on "
+                                   "the host once, one step late (pinned D2H behind the step)", "final_loss": round(final_loss, 4), "launch_mode": mode},
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 4},
+                "d2h_bytes_per_step": 4, "h2d_link_gbs_measured": round(h2d_gbs, 1), "launch_mode": e2e_mode},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all operand-major variants)",
@@ -395,6 +440,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-baseline"])
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (single GPU); 2: also with data parallelism "
                          "(NCCL all-reduces captured in the graph)")
+    ap.add_argument("--e2e-probe", action="store_true", help="extra timed loops that isolate the H2D / loss-read costs")
     ap.add_argument("--gemm-shapes", default=None, help="write a per-shape GEMM time table of one profiled step here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

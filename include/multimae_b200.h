@@ -84,6 +84,10 @@ int mmae_gemm_set_tma_store(int enable);
  * (launch_dependents + wait), so the next kernel's blocks are scheduled while the previous one drains; 0: plain
  * stream order.  Env MMAE_PDL. */
 int mmae_set_pdl(int enable);
+/* 1: mmae_block_backward runs its four weight-gradient GEMMs on a library-owned side stream, forked behind the kernel
+ * that produces their dY operand and joined before the call returns (the caller's stream order is unchanged);
+ * 0 (default; no gain measured at the MultiMAE-B shapes): everything on the caller's stream.  Env MMAE_WGRAD_STREAM. */
+int mmae_set_wgrad_stream(int enable);
 
 int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
                    int M, int N, int K, int split_k, const mmae_gemm_epilogue* ep, void* stream);

@@ -114,6 +114,7 @@ SIGNATURES = {
     "mmae_gemm_set_variant": (c_int, [c_int]),
     "mmae_gemm_set_tma_store": (c_int, [c_int]),
     "mmae_set_pdl": (c_int, [c_int]),
+    "mmae_set_wgrad_stream": (c_int, [c_int]),
     "mmae_gemm_bf16": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int,
                                ctypes.POINTER(GemmEpilogue), c_void_p]),
     "mmae_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),

@@ -76,31 +76,35 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const void* __restrict
   }
 }
 
-// dst[c] += sum_y partial[y, c]: block (32, 8) per 32 columns, y strided over the 8 thread rows
-__global__ void __launch_bounds__(256) colred_finalize_kernel(const float* __restrict__ partial, int Y, int ld, int C, int seg,
-                                                              float* __restrict__ d0, float* __restrict__ d1,
-                                                              float* __restrict__ d2) {
+// dst[c] += sum_y partial[y, c]: block (32, 32) per 32 columns, y strided over the 32 thread rows (a latency-bound
+// kernel: ~Y/32 dependent-free loads per thread, all issued before the first add)
+__global__ void __launch_bounds__(1024) colred_finalize_kernel(const float* __restrict__ partial, int Y, int ld, int C, int seg,
+                                                               float* __restrict__ d0, float* __restrict__ d1,
+                                                               float* __restrict__ d2) {
   pdl_prologue();
-  __shared__ float red[8][33];
+  __shared__ float red[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
   if (c < C) {
     int y = threadIdx.y;
-    for (; y + 24 < Y; y += 32) {
-      const float a0 = partial[int64_t(y) * ld + c], a1 = partial[int64_t(y + 8) * ld + c];
-      const float a2 = partial[int64_t(y + 16) * ld + c], a3 = partial[int64_t(y + 24) * ld + c];
+    for (; y + 96 < Y; y += 128) {
+      const float a0 = partial[int64_t(y) * ld + c], a1 = partial[int64_t(y + 32) * ld + c];
+      const float a2 = partial[int64_t(y + 64) * ld + c], a3 = partial[int64_t(y + 96) * ld + c];
       acc += (a0 + a1) + (a2 + a3);
     }
-    for (; y < Y; y += 8) acc += partial[int64_t(y) * ld + c];
+    for (; y < Y; y += 32) acc += partial[int64_t(y) * ld + c];
   }
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
+  // transpose-reduce: warp w sums column w's 32 partials
+  float v = red[threadIdx.x][threadIdx.y];
 #pragma unroll
-    for (int y = 1; y < 8; ++y) acc += red[y][threadIdx.x];
-    const int k = c / seg;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int cc = blockIdx.x * 32 + threadIdx.y;
+  if (threadIdx.x == 0 && cc < C) {
+    const int k = cc / seg;
     float* d = k == 0 ? d0 : (k == 1 ? d1 : d2);
-    if (d != nullptr) d[c - k * seg] += acc;
+    if (d != nullptr) d[cc - k * seg] += v;
   }
 }
 
@@ -403,7 +407,7 @@ float* colred_scratch(size_t floats, cudaStream_t st) {
 
 int colred_finalize(const float* partial, int Y, int ld, int seg, float* dst0, float* dst1, float* dst2, cudaStream_t st) {
   const int nseg = dst2 ? 3 : (dst1 ? 2 : 1);
-  dim3 grid(ceil_div(seg * nseg, 32)), block(32, 8);
+  dim3 grid(ceil_div(seg * nseg, 32)), block(32, 32);
   launch_k(colred_finalize_kernel, grid, block, 0, st, partial, Y, ld, seg * nseg, seg, dst0, dst1, dst2);
   count_launch();
   MMAE_LAUNCH_OK();

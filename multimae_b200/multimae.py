@@ -114,6 +114,8 @@ class MultiMAE(nn.Module):
         self._grad_callback = None
         self._warned_fp32 = False
         self.external_shares = None
+        self.device_shares = False                 # draw the Dirichlet task shares on the device (graph capture)
+        self._alphas_dev = None
         # task decoders on concurrent CUDA streams (MMAE_DECODER_STREAMS=0 runs them one after the other)
         self.decoder_streams = os.environ.get("MMAE_DECODER_STREAMS", "1") != "0"
         self._dec_streams = None
@@ -210,9 +212,16 @@ class MultiMAE(nn.Module):
         B, device = first.shape[0], first.device
         alphas = [alphas] * len(input_tokens) if isinstance(alphas, float) else alphas
         if self.external_shares is not None:
-            # CUDA-graph mode (train_step.GraphedTrainStep): the host-side Dirichlet draw is made outside the captured
-            # region and copied into this static device buffer before every replay
+            # CUDA-graph mode with host draws: the Dirichlet draw is made outside the captured region and copied into
+            # this static device buffer before every replay
             shares = self.external_shares
+        elif self.device_shares and first.is_cuda and not sample_tasks_uniformly:
+            # CUDA-graph mode (train_step.TrainStep.capture): the same Dirichlet(alphas) draw with the device generator,
+            # so the replayed step needs no host -> device traffic at all
+            key = (tuple(float(a) for a in alphas), device)
+            if self._alphas_dev is None or self._alphas_dev[0] != key:      # created outside any capture (warm-up step)
+                self._alphas_dev = (key, torch.tensor(key[0], dtype=torch.float32, device=device))
+            shares = Dirichlet(self._alphas_dev[1], validate_args=False).sample((B,))
         elif sample_tasks_uniformly:
             shares = Dirichlet(self.sample_alphas(B, len(input_tokens), alphas=alphas)).sample()
         else:

@@ -42,6 +42,7 @@ class FlatAdamW(torch.optim.Optimizer):
         # with the current schedule value and an advancing bias correction
         self._dyn = torch.zeros(2, dtype=torch.float32, device=dev)
         self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(1)
+        self._lr_synced = None
         self.sync_hyperparams()
 
     def _params_version(self):
@@ -79,8 +80,12 @@ class FlatAdamW(torch.optim.Optimizer):
     def sync_hyperparams(self):
         """Push the current param_group learning rate to the device scalar (call before a graph replay)."""
         g = self.param_groups[0]
-        self._lr_host[0] = g["lr"] * g.get("lr_scale", 1.0)
+        lr = g["lr"] * g.get("lr_scale", 1.0)
+        if lr == self._lr_synced:
+            return                                  # nothing to copy: keeps a replayed step free of H2D traffic
+        self._lr_host[0] = lr
         self._dyn[0:1].copy_(self._lr_host, non_blocking=True)
+        self._lr_synced = lr
 
     @torch.no_grad()
     def fused_step(self, found_inf=None):

@@ -36,14 +36,15 @@ class TrainStep:
         grad_norm = self.scaler(loss, self.opt, clip_grad=None, skip_grad=None, parameters=None)
         return loss.detach(), grad_norm
 
-    def __call__(self, x):
-        if self.graph is None:
+    def __call__(self, x, use_graph=True):
+        if self.graph is None or not use_graph:
             return self._step(x)
-        n_tasks = len([d for d in x if d in self.model.input_adapters])
-        B = next(iter(x.values())).shape[0]
-        shares = self.model.draw_task_shares(B, n_tasks, self.alphas, self.uniform)
-        self._shares_host.copy_(shares)
-        self.model.external_shares.copy_(self._shares_host, non_blocking=True)
+        if self.model.external_shares is not None:       # host-side Dirichlet draw -> static device buffer
+            n_tasks = len([d for d in x if d in self.model.input_adapters])
+            B = next(iter(x.values())).shape[0]
+            shares = self.model.draw_task_shares(B, n_tasks, self.alphas, self.uniform)
+            self._shares_host.copy_(shares)
+            self.model.external_shares.copy_(self._shares_host, non_blocking=True)
         for k, v in x.items():
             self.static_x[k].copy_(v, non_blocking=True)
         if hasattr(self.opt, "sync_hyperparams"):
@@ -57,9 +58,16 @@ class TrainStep:
         n_tasks = len([d for d in example_x if d in self.model.input_adapters])
         B = next(iter(example_x.values())).shape[0]
         self.static_x = {k: v.clone() for k, v in example_x.items()}
-        self._shares_host = torch.empty((B, n_tasks), dtype=torch.float32).pin_memory()
-        self._shares_host.copy_(self.model.draw_task_shares(B, n_tasks, self.alphas, self.uniform))
-        self.model.external_shares = self._shares_host.to(dev)
+        # Task shares: drawn on the device inside the graph (no per-step host -> device copy: a small H2D on the compute
+        # stream queues behind the in-flight input-batch copy on the one H2D engine and stalls the step by its ~2 ms).
+        # Sampling uniformly over task subsets keeps the reference's host draw, fed through a static buffer.
+        self._shares_host = None
+        self.model.external_shares = None
+        self.model.device_shares = not self.uniform
+        if self.uniform:
+            self._shares_host = torch.empty((B, n_tasks), dtype=torch.float32).pin_memory()
+            self._shares_host.copy_(self.model.draw_task_shares(B, n_tasks, self.alphas, self.uniform))
+            self.model.external_shares = self._shares_host.to(dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -80,3 +88,43 @@ class TrainStep:
             lib.mmae_set_pdl(1 if self._pdl_default else 0)
         self.graph = graph
         return self
+
+
+class InputPrefetcher:
+    """Double-buffered host -> device staging of input batches on a copy stream (what the reference's DataLoader with
+    pin_memory + `.to(device, non_blocking=True)` does, run_pretraining_multimae.py:445-449, without per-step
+    allocations): `submit(host_batch)` enqueues the H2D copies of the NEXT batch into a free device slot while the
+    current step runs; `get()` hands out the oldest submitted batch once the compute stream has been told to wait for its
+    copies; `release(batch)` marks the slot reusable after the kernels enqueued so far."""
+
+    def __init__(self, example_host_batch, device, slots=2):
+        self.device = device
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.slots = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in example_host_batch.items()}
+                      for _ in range(slots)]
+        self.copied = [torch.cuda.Event() for _ in range(slots)]
+        self.consumed = [None] * slots
+        self.queue = []
+        self.next_slot = 0
+        self.bytes_per_batch = sum(v.numel() * v.element_size() for v in example_host_batch.values())
+
+    def submit(self, host_batch):
+        k = self.next_slot
+        self.next_slot = (k + 1) % len(self.slots)
+        with torch.cuda.stream(self.copy_stream):
+            if self.consumed[k] is not None:
+                self.copy_stream.wait_event(self.consumed[k])      # the step that read this slot has finished with it
+            for name, t in host_batch.items():
+                self.slots[k][name].copy_(t, non_blocking=True)
+            self.copied[k].record(self.copy_stream)
+        self.queue.append(k)
+
+    def get(self):
+        k = self.queue.pop(0)
+        torch.cuda.current_stream(self.device).wait_event(self.copied[k])
+        return k, self.slots[k]
+
+    def release(self, k):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.consumed[k] = ev

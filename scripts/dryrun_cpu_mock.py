@@ -50,6 +50,7 @@ class _FakeLib:
     def mmae_gemm_set_variant(self, v): return 0
     def mmae_gemm_set_tma_store(self, v): return 0
     def mmae_set_pdl(self, v): return 0
+    def mmae_set_wgrad_stream(self, v): return 0
     def mmae_weight_mirror_register(self, *a): return 0
     def mmae_attention_set_tc(self, v): return 0
 libmod = types.ModuleType("multimae_b200._lib"); libmod.lib = lambda: _FakeLib()
