@@ -75,7 +75,9 @@ typedef struct mmae_gemm_epilogue {
 } mmae_gemm_epilogue;
 
 /* Kernel variant selection for measurements: -1 = heuristic (default), 0 = one-tile-per-CTA 128x128,
- * 1 = persistent 128x128 with double-buffered TMEM, 2 = persistent 128x256, 3 = persistent 128x192.  Env MMAE_GEMM_VARIANT sets the initial value. */
+ * 1 = persistent 128x128 with double-buffered TMEM, 2 = persistent 128x256, 3 = persistent 128x192,
+ * 4 / 5 / 6 = CTA-pair kernels (cluster of 2, tcgen05 cta_group::2) with 256x256 / 256x192 / 256x128 tiles.
+ * Env MMAE_GEMM_VARIANT sets the initial value; MMAE_GEMM_PAIR=0 keeps the heuristic off the pair kernels. */
 int mmae_gemm_set_variant(int variant);
 /* 1 (default): bf16-only epilogues of the persistent kernels leave through shared memory + TMA tile stores;
  * 0: per-lane global stores (kept for A/B measurements and for epilogues with extra operands).  Env MMAE_GEMM_TMA_STORE. */

@@ -587,6 +587,265 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   return MMAE_OK;
 }
 
+// =====================================================================================================================
+// v3: CTA pairs.  A cluster of two CTAs (the two SMs of a TPC) owns a 256 x BN output tile: each CTA stages its own 128
+// rows of A and HALF of the B tile; the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2 (M = 256), which reads
+// both halves and accumulates each CTA's 128 rows in that CTA's TMEM.  Per SM and 16-deep K step the shared-memory fill +
+// read traffic drops from 2 x 12 KB to 2 x 8 KB at BN = 256: the single-CTA kernels sit at ~64 % tensor-pipe activity
+// because TMA fills and UMMA reads share the 128 B/clk shared-memory port (ncu: profiles/r01_ncu_full_hot_kernels.txt).
+//   both CTAs : warp 0 TMA producer (own A rows, own B half; bytes counted on the LEADER's "stage full" barrier)
+//               warps 2.. epilogue of the CTA's own 128 rows (same code as v2)
+//   leader    : warp 1 issues the pair MMAs; its commits are multicast to the "stage empty" / "accumulator full"
+//               barriers of both CTAs; the peers' epilogue warps arrive remotely on the leader's "accumulator empty".
+// =====================================================================================================================
+template <int BN>
+struct Gemm3Cfg {
+  static constexpr int BNH = BN / 2;                                // B rows (output columns) staged by one CTA
+  static constexpr int STAGES = 6;
+  static constexpr int EPI_WARPS = BN >= 192 ? 8 : 4;
+  static constexpr int THREADS = 64 + EPI_WARPS * 32;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BNH * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STORE_OFFSET + EPI_WARPS * 2048;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 512;
+  static constexpr int TOTAL = BIAS_OFFSET + 2 * BN * 4 + 1024;
+  static constexpr uint32_t TMEM_COLS = BN > 128 ? 512 : 256;
+  static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
+  static_assert(TOTAL <= 232448, "pair GEMM exceeds the 227 KB shared-memory limit");
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(Gemm3Cfg<BN>::THREADS, 1)
+    gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const __grid_constant__ CUtensorMap tmC, const GemmParams p, const Gemm2Sched sc) {
+  pdl_launch_dependents();
+  using C = Gemm3Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  static_assert(!B_MN || C::BNH % 64 == 0, "MN-major B halves are made of 64-column chunks");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]  (the leader's copy is the one in use)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      if (p.tma_store) tma_prefetch_desc(&tmC);
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+#pragma unroll
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);      // leader: its own expect_tx arrival; transaction bytes of both CTAs
+        mbar_init(&empty_bar[s], 1);     // one multicast commit per use
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&tmem_full_bar[b], 1);
+        mbar_init(&tmem_empty_bar[b], 2 * C::EPI_WARPS);   // epilogue warps of both CTAs
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_2cta(tmem_ptr_smem, C::TMEM_COLS);   // collective of the pair: one warp in each CTA
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // the peer's barriers exist before any remote arrival / transaction lands on them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  auto decode = [&](int item, int& m0, int& n0, int& kb_begin, int& nkb, int& z) {
+    z = item % sc.splits;
+    const int tile = item / sc.splits;
+    n0 = (tile % sc.tiles_n) * BN;
+    m0 = (tile / sc.tiles_n) * (2 * BM) + int(rank) * BM;     // this CTA's 128 rows of the 256-row pair tile
+    kb_begin = z * p.kb_per_split;
+    nkb = min(p.kb_per_split, p.num_kb - kb_begin);
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < sc.total; item += num_clusters) {
+        int m0, n0, kb_begin, nkb, z;
+        decode(item, m0, n0, kb_begin, nkb, z);
+        const int nb0 = n0 + int(rank) * C::BNH;             // this CTA's half of the B tile
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sA = smem + stage * C::STAGE_BYTES;
+          uint8_t* sB = sA + C::A_BYTES;
+          const int k0 = (kb_begin + kb) * BK;
+          if constexpr (!A_MN) {
+            tma_load_2d_2cta(sA, &tmA, full_leader, k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d_2cta(sA + c * (64 * BK * 2), &tmA, full_leader, m0 + c * 64, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2cta(sB, &tmB, full_leader, k0, nb0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < C::BNH / 64; ++c) tma_load_2d_2cta(sB + c * (64 * BK * 2), &tmB, full_leader, nb0 + c * 64, k0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && elect_one()) {
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = cluster_id; item < sc.total; item += num_clusters, ++it) {
+        int m0, n0, kb_begin, nkb, z;
+        decode(item, m0, n0, kb_begin, nkb, z);
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[buf], acc_phase ^ 1u);   // both CTAs' epilogues released this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(buf * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int j = 0; j < BK / UMMA_K; ++j) {
+            const uint64_t da = A_MN ? umma_smem_desc_sw128(a_addr + j * (UMMA_K * 128), 64 * BK * 2, 1024)
+                                     : umma_smem_desc_sw128(a_addr + j * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = B_MN ? umma_smem_desc_sw128(b_addr + j * (UMMA_K * 128), 64 * BK * 2, 1024)
+                                     : umma_smem_desc_sw128(b_addr + j * (UMMA_K * 2), 16, 1024);
+            tc_mma_f16_ss_2cta(tmem_d, da, db, idesc, (kb | j) != 0 ? 1u : 0u);
+          }
+          tc_commit_2cta(&empty_bar[stage], 0x3);          // both producers may refill this stage
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit_2cta(&tmem_full_bar[buf], 0x3);          // both epilogues may read their 128 rows
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
+    const int e = warp - 2;
+    const int q = warp & 3;
+    constexpr int COLS_PER_WARP = BN / (C::EPI_WARPS / 4);
+    const int col0 = (e >> 2) * COLS_PER_WARP;
+    int it = 0;
+    for (int item = cluster_id; item < sc.total; item += num_clusters, ++it) {
+      int m0, n0, kb_begin, nkb, z;
+      decode(item, m0, n0, kb_begin, nkb, z);
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      float* sbias = reinterpret_cast<float*>(smem + C::BIAS_OFFSET) + buf * BN;
+      const bool use_bias = p.ep.bias != nullptr && z == 0;
+      if (p.ep.bias != nullptr) {
+        if (use_bias)
+          for (int c = e * 32 + lane; c < BN; c += C::EPI_WARPS * 32) sbias[c] = n0 + c < p.N ? __ldg(p.ep.bias + n0 + c) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(C::EPI_WARPS * 32) : "memory");
+      }
+      mbar_wait(&tmem_full_bar[buf], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const bool first_split = z == 0;
+      const bool atomic_out = p.ep.accumulate != 0 || sc.splits > 1;
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
+        const int nb = n0 + col0 + c * 32;
+        if (nb >= p.N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(buf * BN + col0 + c * 32), r);
+        tc_wait_ld();
+        if (p.tma_store == 1)
+          epilogue_chunk32_tma(r, p, use_bias ? sbias + col0 + c * 32 : nullptr, smem + C::STORE_OFFSET + e * 2048, lane,
+                               &tmC, nb, m0 + q * 32);
+        else if (p.tma_store != 0)
+          epilogue_chunk32_tma_f32(r, p, use_bias ? sbias + col0 + c * 32 : nullptr, smem + C::STORE_OFFSET + e * 2048, lane,
+                                   &tmC, nb, m0 + q * 32, p.tma_store == 3);
+        else
+          epilogue_chunk32(r, row, row_ok, nb, p, first_split, atomic_out, use_bias ? sbias + col0 + c * 32 : nullptr);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[buf]), 0));   // the leader's barrier
+    }
+    if (p.tma_store && lane == 0) bulk_wait_all();
+  }
+
+  // no CTA of the pair may leave (or free TMEM) while the other can still address its shared memory / TMEM
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch_gemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int split_k,
+                 cudaStream_t stream) {
+  using C = Gemm3Cfg<BN>;
+  auto kern = gemm_bf16_pair_kernel<BN, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    MMAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+    MMAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+    configured = true;
+  }
+  Gemm2Sched sc;
+  sc.tiles_m = ceil_div(p.M, 2 * BM);
+  sc.tiles_n = ceil_div(p.N, BN);
+  sc.splits = split_k;
+  sc.total = sc.tiles_m * sc.tiles_n * split_k;
+  const int clusters = std::min(sc.total, sm_count() / 2);
+  const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K, (A_MN ? 1 : 0) | (B_MN ? 2 : 0) | (split_k << 8));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = C::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  MMAE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p, sc));
+  if (prof) gemm_profile_end(stream);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
 }  // namespace
 }  // namespace mmae
 
@@ -607,6 +866,12 @@ extern "C" int mmae_gemm_set_tma_store(int enable) {
   g_gemm_tma_store = enable != 0;
   return MMAE_OK;
 }
+
+// MMAE_GEMM_PAIR=0 keeps the heuristic on the single-CTA kernels
+static int g_gemm_pair = []() {
+  const char* e = getenv("MMAE_GEMM_PAIR");
+  return e ? atoi(e) : 1;
+}();
 
 extern "C" int mmae_gemm_set_variant(int variant) {
   g_gemm_variant = variant;
@@ -670,7 +935,8 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
              MMAE_ERR_ARG, "mmae_gemm_bf16: epilogue tensors need 16-byte alignment and ld %% 8 == 0");
 #undef MMAE_LD_OK
 
-  // kernel variant: 0 = v1 (one tile per CTA, BN=128), 1 = persistent BN=128, 2 = persistent BN=256.
+  // kernel variant: 0 = v1 (one tile per CTA, BN=128), 1 / 3 / 2 = persistent BN = 128 / 192 / 256, 6 / 5 / 4 = CTA-pair
+  // kernels with 256 x (128 / 192 / 256) tiles.
   // MMAE_GEMM_VARIANT overrides the heuristic (for A/B measurements).
   if (variant < 0) {
     // tile-quantisation model: persistent CTAs process ceil(tiles / SMs) rounds; a round costs ~(BN + c) where c
@@ -691,9 +957,29 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
         best = cand_var[i];
       }
     }
+    // CTA-pair kernels (256-row tiles, rounds counted in pairs): measured +3..6 % on the big encoder GEMMs (N*K >= 2 M
+    // elements: fc1 / fc2 forward, fc2 dgrad), slower on short-K or narrow problems - only those shapes are candidates.
+    if (split_k == 1 && g_gemm_pair && M >= 2048 && long(N) * K >= 2000000L && sms >= 2) {
+      const int tm2 = ceil_div(M, 2 * BM);
+      const int pair_bn[2] = {192, 256};
+      const int pair_var[2] = {5, 4};
+      for (int i = 0; i < 2; ++i) {
+        if (N < pair_bn[i] || (pair_bn[i] == 192 && b_mn_major)) continue;
+        const long items = long(tm2) * ceil_div(N, pair_bn[i]);
+        const long rounds = (items + sms / 2 - 1) / (sms / 2);
+        const long cost = rounds * (pair_bn[i] + 40) * 95 / 100;
+        if (cost < best_cost) {
+          best_cost = cost;
+          best = pair_var[i];
+        }
+      }
+    }
     variant = best;
   }
-  const int BNsel = variant == 2 ? 256 : (variant == 3 ? 192 : 128);
+  // variants 4 / 5 / 6: CTA-pair kernels (256 x BN tiles, BN = 256 / 192 / 128); an MN-major B needs 64-column halves
+  if (variant == 5 && b_mn_major) variant = 4;
+  const bool pair = variant >= 4;
+  const int BNsel = (variant == 2 || variant == 4) ? 256 : ((variant == 3 || variant == 5) ? 192 : 128);
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -705,7 +991,7 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
   }
   if (rc) return rc;
   if (!b_mn_major) {
-    rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, BNsel);
+    rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BK, pair ? BNsel / 2 : BNsel);
   } else {
     rc = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, BK);
   }
@@ -739,6 +1025,12 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
     if (a_mn_major && !b_mn_major) return FN<__VA_ARGS__, true, false>(tmA, tmB, tmC, p, split_k, st);   \
     return FN<__VA_ARGS__, true, true>(tmA, tmB, tmC, p, split_k, st);                                  \
   } while (0)
+  if (variant == 4) MMAE_DISPATCH(launch_gemm3, 256);
+  if (variant == 6) MMAE_DISPATCH(launch_gemm3, 128);
+  if (variant == 5) {
+    if (!a_mn_major) return launch_gemm3<192, false, false>(tmA, tmB, tmC, p, split_k, st);
+    return launch_gemm3<192, true, false>(tmA, tmB, tmC, p, split_k, st);
+  }
   if (variant == 2) MMAE_DISPATCH(launch_gemm2, 256);
   if (variant == 3) MMAE_DISPATCH(launch_gemm2, 192);
   if (variant == 1) MMAE_DISPATCH(launch_gemm2, 128);

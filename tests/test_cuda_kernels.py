@@ -31,7 +31,7 @@ def KN():
     L.lib().mmae_attention_set_tc(3)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("shape", [(128, 128, 64), (256, 384, 768), (200, 136, 200), (396, 2128, 256), (1000, 768, 512),
                                    (2560, 2304, 768)])
 def test_gemm_all_operand_majors(dev, KN, variant, shape):
@@ -49,18 +49,19 @@ def test_gemm_all_operand_majors(dev, KN, variant, shape):
             assert rel_l2(out, ref) < 3e-5, (variant, shape, a_mn, b_mn, rel_l2(out, ref))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, -1])
 def test_gemm_split_k_wgrad_shapes(dev, KN, variant):
     from multimae_b200 import _lib as L
     L.lib().mmae_gemm_set_variant(variant)
-    for (M, N, K, split) in [(768, 768, 12672, 1), (768, 768, 12672, 4), (768, 3072, 1280, 3), (256, 256, 25088, 16)]:
+    for (M, N, K, split) in [(768, 768, 12672, 1), (768, 768, 12672, 4), (768, 3072, 1280, 3), (256, 256, 25088, 16),
+                             (256, 256, 25088, 0), (2304, 768, 12672, 0)]:          # 0 = automatic split + tile choice
         A, B = _bf16(dev, M, K), _bf16(dev, N, K)
         out = torch.zeros(M, N, device=dev)
         KN.gemm(A.t().contiguous(), B.t().contiguous(), a_mn=True, b_mn=True, out_f32=out, split_k=split)
         assert rel_l2(out, A.float() @ B.float().t()) < 3e-5
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 def test_gemm_fused_epilogues(dev, KN, variant):
     from multimae_b200 import _lib as L
     L.lib().mmae_gemm_set_variant(variant)
@@ -87,7 +88,7 @@ def test_gemm_fused_epilogues(dev, KN, variant):
     assert rel_l2(out, 1 + 0.5 * acc) < 3e-5
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize("shape", [(128, 128, 64), (200, 136, 200), (396, 2128, 256), (1000, 776, 512), (2560, 2304, 768),
                                    (25088, 256, 256)])
 def test_gemm_tma_store_epilogue(dev, KN, variant, shape):
@@ -123,6 +124,21 @@ def test_gemm_tma_store_epilogue(dev, KN, variant, shape):
             outs.append(buf[:M, :N].clone())
         if "split_k" not in kw:
             assert torch.equal(outs[0], outs[1]), (variant, shape, list(kw))
+
+
+def test_gemm_heuristic_picks_pair_kernels_correctly(dev, KN):
+    """The default heuristic sends the big encoder shapes to the CTA-pair kernels: same results as the single-CTA ones."""
+    from multimae_b200 import _lib as L
+    for (M, N, K, b_mn) in [(12672, 3072, 768, False), (12672, 3072, 768, True), (12672, 768, 3072, False)]:
+        A, B = _bf16(dev, M, K), _bf16(dev, N, K)
+        bias = torch.randn(N, device=dev)
+        outs = []
+        for variant in (-1, 3):
+            L.lib().mmae_gemm_set_variant(variant)
+            o = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            KN.gemm(A, B.t().contiguous() if b_mn else B, b_mn=b_mn, bias=bias, out_bf16=o)
+            outs.append(o)
+        assert torch.equal(outs[0], outs[1]), (M, N, K, b_mn)          # same k order, same fp32 accumulation
 
 
 def test_gemm_rejects_bad_arguments(dev, KN):
