@@ -108,6 +108,14 @@ def _note(msg):
     print("[bench %6.1fs] %s" % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM (encoder fc1 forward, 12672x3072x768 + bias,
+# L2 flushed before the launch) from the committed `ncu --set full` capture profiles/r01_ncu_full_hot_kernels.txt
+NCU_GEMM_DRAM_BYTES = 24.25e6 + 25.62e6
+NCU_GEMM_TRAFFIC_NOTE = ("fc1 forward GEMM 12672x3072x768: 24.3 MB read (= the 24.2 MB of operands: no re-reads) + 25.6 MB "
+                         "written inside the capture window; the remaining ~52 MB of the 77.9 MB result are still dirty in the "
+                         "126 MB L2 when the kernel ends (algorithmic bytes per launch: 102.1 MB)")
+
+
 def synthetic_batch(B, seed, pin=False):
     g = torch.Generator().manual_seed(seed)
     x = {"rgb": torch.randn(B, 3, 224, 224, generator=g), "depth": torch.randn(B, 1, 224, 224, generator=g),
@@ -328,7 +336,8 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all operand-major variants)",
                      "achieved": round(gemm_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": round(gemm_tf / peak_tf, 4), "traffic": None, "peak_source": peak_src + " (sustained bf16)",
+                     "frac": round(gemm_tf / peak_tf, 4), "traffic": NCU_GEMM_DRAM_BYTES,
+                     "traffic_note": NCU_GEMM_TRAFFIC_NOTE, "peak_source": peak_src + " (sustained bf16)",
                      "launches_per_step": int(n_g.value), "kernel_ms_per_step": round(ms_g.value, 3),
                      "kernel_share_of_step": round(ms_g.value / ms_step, 3),
                      "step_model_flops_frac": round(value / world * ALG_FLOP_PER_SAMPLE / (peak_tf * 1e12), 4)},
