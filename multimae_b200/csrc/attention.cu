@@ -145,17 +145,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
     }
-    const float alpha0 = exp2f((m_run[0] - mx[0]) * sl2), alpha1 = exp2f((m_run[1] - mx[1]) * sl2);
+    const float alpha0 = fast_exp2((m_run[0] - mx[0]) * sl2), alpha1 = fast_exp2((m_run[1] - mx[1]) * sl2);
     m_run[0] = mx[0];
     m_run[1] = mx[1];
     const float mo0 = mx[0] * sl2, mo1 = mx[1] * sl2;
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
     for (int j = 0; j < ATT_CHUNK / 8; ++j) {
-      s[j][0] = exp2f(s[j][0] * sl2 - mo0);
-      s[j][1] = exp2f(s[j][1] * sl2 - mo0);
-      s[j][2] = exp2f(s[j][2] * sl2 - mo1);
-      s[j][3] = exp2f(s[j][3] * sl2 - mo1);
+      s[j][0] = fast_exp2(s[j][0] * sl2 - mo0);
+      s[j][1] = fast_exp2(s[j][1] * sl2 - mo0);
+      s[j][2] = fast_exp2(s[j][2] * sl2 - mo1);
+      s[j][3] = fast_exp2(s[j][3] * sl2 - mo1);
       rs0 += s[j][0] + s[j][1];
       rs1 += s[j][2] + s[j][3];
     }
@@ -208,19 +208,24 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
 // backward, part 0: delta[b,h,q] = sum_d dO[q,d] * O[q,d]
 // =====================================================================================================================
 template <int DH>
-__global__ void __launch_bounds__(128) attn_delta_kernel(const bf16* __restrict__ O, int64_t ldo,
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ O, int64_t ldo,
                                                          const bf16* __restrict__ dO, int64_t lddo,
-                                                         float* __restrict__ delta, int Nq, int H) {
+                                                         float* __restrict__ delta, int Nq, int H, int64_t rows) {
   pdl_prologue();
-  const int row = blockIdx.x;  // b * Nq + q
-  const int b = row / Nq, q = row % Nq;
-  constexpr int TPH = DH / 8;  // threads per head
-  for (int base = 0; base < H * TPH; base += 128) {
-    const int idx = base + threadIdx.x;
+  // one 16-byte segment (8 columns) per thread; a head is TPH consecutive segments = TPH consecutive lanes
+  constexpr int TPH = DH / 8;
+  const int S = H * TPH;                                    // segments per row
+  const int64_t total = rows * S;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t g0 = int64_t(blockIdx.x) * blockDim.x; g0 < total; g0 += stride) {
+    const int64_t g = g0 + threadIdx.x;
+    const bool ok = g < total;
+    const int64_t row = ok ? g / S : 0;
+    const int idx = ok ? int(g - row * S) : 0;
     float p = 0.f;
-    if (idx < H * TPH) {
-      const uint4 o = __ldg(reinterpret_cast<const uint4*>(O + int64_t(row) * ldo + idx * 8));
-      const uint4 d = __ldg(reinterpret_cast<const uint4*>(dO + int64_t(row) * lddo + idx * 8));
+    if (ok) {
+      const uint4 o = __ldg(reinterpret_cast<const uint4*>(O + row * ldo + idx * 8));
+      const uint4 d = __ldg(reinterpret_cast<const uint4*>(dO + row * lddo + idx * 8));
       const uint32_t* ou = reinterpret_cast<const uint32_t*>(&o);
       const uint32_t* du = reinterpret_cast<const uint32_t*>(&d);
 #pragma unroll
@@ -231,7 +236,11 @@ __global__ void __launch_bounds__(128) attn_delta_kernel(const bf16* __restrict_
     }
 #pragma unroll
     for (int o = TPH / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-    if (idx < H * TPH && (idx % TPH) == 0) delta[(int64_t(b) * H + idx / TPH) * Nq + q] = p;
+    if (ok && (idx % TPH) == 0) {
+      const int64_t b = row / Nq;
+      const int q = int(row - b * Nq);
+      delta[(b * H + idx / TPH) * Nq + q] = p;
+    }
   }
 }
 
@@ -305,8 +314,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
         }
         const int key = k0 + n0 + 2 * t;
         const bool v0 = key < Nk, v1 = key + 1 < Nk;
-        const float p0 = v0 ? exp2f(s[0] * sl2 - lse_a) : 0.f, p1 = v1 ? exp2f(s[1] * sl2 - lse_a) : 0.f;
-        const float p2 = v0 ? exp2f(s[2] * sl2 - lse_b) : 0.f, p3 = v1 ? exp2f(s[3] * sl2 - lse_b) : 0.f;
+        const float p0 = v0 ? fast_exp2(s[0] * sl2 - lse_a) : 0.f, p1 = v1 ? fast_exp2(s[1] * sl2 - lse_a) : 0.f;
+        const float p2 = v0 ? fast_exp2(s[2] * sl2 - lse_b) : 0.f, p3 = v1 ? fast_exp2(s[3] * sl2 - lse_b) : 0.f;
         dsa[half * 2 + 0] = pack_bf16x2(p0 * (dp[0] - del_a), p1 * (dp[1] - del_a));
         dsa[half * 2 + 1] = pack_bf16x2(p2 * (dp[2] - del_b), p3 * (dp[3] - del_b));
       }
@@ -403,8 +412,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
         }
         const int qc = n0 + 2 * t;
         const float l0 = sLse[qc], l1 = sLse[qc + 1], d0 = sDel[qc], d1 = sDel[qc + 1];
-        const float p0 = exp2f(s[0] * sl2 - l0), p1 = exp2f(s[1] * sl2 - l1);
-        const float p2 = exp2f(s[2] * sl2 - l0), p3 = exp2f(s[3] * sl2 - l1);
+        const float p0 = fast_exp2(s[0] * sl2 - l0), p1 = fast_exp2(s[1] * sl2 - l1);
+        const float p2 = fast_exp2(s[2] * sl2 - l0), p3 = fast_exp2(s[3] * sl2 - l1);
         pa[half * 2 + 0] = pack_bf16x2(p0, p1);
         pa[half * 2 + 1] = pack_bf16x2(p2, p3);
         dsa[half * 2 + 0] = pack_bf16x2(p0 * (dp[0] - d0), p1 * (dp[1] - d1));
@@ -480,6 +489,11 @@ extern "C" int mmae_attention_forward(const void* q, int64_t ldq, const void* k,
   return MMAE_OK;
 }
 
+static unsigned delta_grid(int B, int Nq, int H, int dh) {
+  const int64_t total = int64_t(B) * Nq * H * (dh / 8);
+  return (unsigned)std::min<int64_t>((total + 255) / 256, int64_t(sm_count()) * 16);
+}
+
 extern "C" int mmae_attention_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                        int64_t ldv, const void* o, int64_t ldo, const void* d_o, int64_t lddo,
                                        const float* lse, float* delta_ws, void* dq, int64_t lddq, void* dk,
@@ -497,7 +511,7 @@ extern "C" int mmae_attention_backward(const void* q, int64_t ldq, const void* k
              *dop = (const bf16*)d_o;
   dim3 gq(ceil_div(Nq, ATT_ROWS), H, B), gk(ceil_div(Nk, ATT_ROWS), H, B);
   if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim)) {
-    launch_k(attn_delta_kernel<64>, B * Nq, 128, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H);
+    launch_k(attn_delta_kernel<64>, delta_grid(B, Nq, H, 64), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
     count_launch();
     MMAE_LAUNCH_OK();
     return attn_tc_backward(q, ldq, k, ldk, v, ldv, d_o, lddo, lse, delta_ws, dq, lddq, dk, lddk, dv, lddv, B, H, Nq, Nk,
@@ -505,22 +519,22 @@ extern "C" int mmae_attention_backward(const void* q, int64_t ldq, const void* k
   }
   if ((g_attn_tc & 4) && attn_tc_bwd_gen_supported(H, Nq, Nk, head_dim)) {
     if (head_dim == 64)
-      launch_k(attn_delta_kernel<64>, B * Nq, 128, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H);
+      launch_k(attn_delta_kernel<64>, delta_grid(B, Nq, H, 64), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
     else
-      launch_k(attn_delta_kernel<32>, B * Nq, 128, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H);
+      launch_k(attn_delta_kernel<32>, delta_grid(B, Nq, H, 32), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
     count_launch();
     MMAE_LAUNCH_OK();
     return attn_tc_backward_gen(q, ldq, k, ldk, v, ldv, d_o, lddo, lse, delta_ws, dq, lddq, dk, lddk, dv, lddv, B, H, Nq,
                                 Nk, head_dim, scale, st);
   }
   if (head_dim == 64) {
-    launch_k(attn_delta_kernel<64>, B * Nq, 128, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H);
+    launch_k(attn_delta_kernel<64>, delta_grid(B, Nq, H, 64), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
     launch_k(attn_bwd_dq_kernel<64>, gq, ATT_THREADS, 0, st, qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dq,
                                                        lddq, Nq, Nk, H, scale);
     launch_k(attn_bwd_dkv_kernel<64>, gk, ATT_THREADS, 0, st, qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dk,
                                                         lddk, (bf16*)dv, lddv, Nq, Nk, H, scale);
   } else {
-    launch_k(attn_delta_kernel<32>, B * Nq, 128, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H);
+    launch_k(attn_delta_kernel<32>, delta_grid(B, Nq, H, 32), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
     launch_k(attn_bwd_dq_kernel<32>, gq, ATT_THREADS, 0, st, qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dq,
                                                        lddq, Nq, Nk, H, scale);
     launch_k(attn_bwd_dkv_kernel<32>, gk, ATT_THREADS, 0, st, qp, ldq, kp, ldk, vp, ldv, dop, lddo, lse, delta_ws, (bf16*)dk,

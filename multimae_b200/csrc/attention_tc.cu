@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const __grid_constant_
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float a = c0 + 2 * i < p.Nk ? exp2f(__uint_as_float(r[2 * i]) * sl2 - moff) : 0.f;
-        const float c = c0 + 2 * i + 1 < p.Nk ? exp2f(__uint_as_float(r[2 * i + 1]) * sl2 - moff) : 0.f;
+        const float a = c0 + 2 * i < p.Nk ? fast_exp2(__uint_as_float(r[2 * i]) * sl2 - moff) : 0.f;
+        const float c = c0 + 2 * i + 1 < p.Nk ? fast_exp2(__uint_as_float(r[2 * i + 1]) * sl2 - moff) : 0.f;
         sum += a + c;
         pk[i] = pack_bf16x2(a, c);
       }
@@ -200,23 +200,30 @@ struct AttnTcBwdParams {
   int64_t lddq, lddk, lddv;
 };
 
-// TMEM columns: S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ [384,448)
-__global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                          const __grid_constant__ CUtensorMap tmK,
-                                                          const __grid_constant__ CUtensorMap tmV,
-                                                          const __grid_constant__ CUtensorMap tmdO,
-                                                          const AttnTcBwdParams p) {
+// Two CTAs per SM: 256 TMEM columns and 7 smem tiles each.
+// TMEM columns: S [0,128)  dP [128,256); once P and dS are in shared memory the gradient accumulators reuse them:
+//               dV [0,64)  dK [64,128)  dQ [128,192).
+// smem tiles  : Q | K | dO | P panel 0 | V, later P panel 1 (V is dead once dP is complete) | dS panel 0 | dS panel 1
+constexpr int ATTN_BWD_SMEM = 7 * TILE_BYTES + 64 + 960;   // 2 x (this + 1 KB system reserve) = the SM's 228 KB
+
+__global__ void __launch_bounds__(128, 2) attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                             const __grid_constant__ CUtensorMap tmK,
+                                                             const __grid_constant__ CUtensorMap tmV,
+                                                             const __grid_constant__ CUtensorMap tmdO,
+                                                             const AttnTcBwdParams p) {
   pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  if (pad > 960u) __trap();                // the launch reserves 960 bytes of alignment slack
+  uint8_t* smem = smem_raw + pad;
   uint8_t* sQ = smem;
   uint8_t* sK = smem + 1 * TILE_BYTES;
-  uint8_t* sV = smem + 2 * TILE_BYTES;
-  uint8_t* sdO = smem + 3 * TILE_BYTES;
-  uint8_t* sP = smem + 4 * TILE_BYTES;     // 32 KB: [q][key] bf16, two 64-key panels
-  uint8_t* sdS = smem + 6 * TILE_BYTES;    // 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * TILE_BYTES);   // [0] loads, [1] S & dP ready, [2] grads ready
+  uint8_t* sdO = smem + 2 * TILE_BYTES;
+  uint8_t* sP = smem + 3 * TILE_BYTES;     // 32 KB: [q][key] bf16, two 64-key panels; panel 1 overlays V
+  uint8_t* sV = smem + 4 * TILE_BYTES;
+  uint8_t* sdS = smem + 5 * TILE_BYTES;    // 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE_BYTES);   // [0] loads, [1] S & dP ready, [2] grads ready
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int h = blockIdx.x, b = blockIdx.y;
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const __grid_constant_
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_alloc(tmem_ptr_smem, 256);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -285,8 +292,8 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const __grid_constant_
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float p0 = c0 + 2 * i < p.Nk ? exp2f(__uint_as_float(s[2 * i]) * sl2 - lse2) : 0.f;
-        const float p1 = c0 + 2 * i + 1 < p.Nk ? exp2f(__uint_as_float(s[2 * i + 1]) * sl2 - lse2) : 0.f;
+        const float p0 = c0 + 2 * i < p.Nk ? fast_exp2(__uint_as_float(s[2 * i]) * sl2 - lse2) : 0.f;
+        const float p1 = c0 + 2 * i + 1 < p.Nk ? fast_exp2(__uint_as_float(s[2 * i + 1]) * sl2 - lse2) : 0.f;
         pp[i] = pack_bf16x2(p0, p1);
         ds[i] = pack_bf16x2(p0 * (__uint_as_float(d[2 * i]) - del), p1 * (__uint_as_float(d[2 * i + 1]) - del));
       }
@@ -309,16 +316,16 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const __grid_constant_
     for (int j = 0; j < nq16 / 16; ++j) {
       const uint64_t db_do = umma_smem_desc_sw128(smem_u32(sdO) + j * 2048, TILE_BYTES, 1024);
       const uint64_t db_q = umma_smem_desc_sw128(smem_u32(sQ) + j * 2048, TILE_BYTES, 1024);
-      tc_mma_f16_ss(tmem + 256, umma_smem_desc_sw128(smem_u32(sP) + j * 2048, TILE_BYTES, 1024), db_do, idesc_t,
+      tc_mma_f16_ss(tmem + 0, umma_smem_desc_sw128(smem_u32(sP) + j * 2048, TILE_BYTES, 1024), db_do, idesc_t,
                     j != 0 ? 1u : 0u);
-      tc_mma_f16_ss(tmem + 320, umma_smem_desc_sw128(smem_u32(sdS) + j * 2048, TILE_BYTES, 1024), db_q, idesc_t,
+      tc_mma_f16_ss(tmem + 64, umma_smem_desc_sw128(smem_u32(sdS) + j * 2048, TILE_BYTES, 1024), db_q, idesc_t,
                     j != 0 ? 1u : 0u);
     }
     // dQ[q x dh] = dS K : A = dS K-major, B = K MN-major; K extent = keys
     const uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);
     for (int j = 0; j < nk16 / 16; ++j) {
       const uint32_t a_addr = smem_u32(sdS) + (j >> 2) * TILE_BYTES + (j & 3) * 32;
-      tc_mma_f16_ss(tmem + 384, umma_smem_desc_sw128(a_addr, 16, 1024),
+      tc_mma_f16_ss(tmem + 128, umma_smem_desc_sw128(a_addr, 16, 1024),
                     umma_smem_desc_sw128(smem_u32(sK) + j * 2048, TILE_BYTES, 1024), idesc_q, j != 0 ? 1u : 0u);
     }
     tc_commit(&bars[2]);
@@ -337,7 +344,7 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const __grid_constant_
 #pragma unroll
     for (int c0 = 0; c0 < DH; c0 += 32) {
       uint32_t r[32];
-      tmem_ld_32x32(trow + 256 + which * 64 + c0, r);
+      tmem_ld_32x32(trow + which * 64 + c0, r);
       tc_wait_ld();
       if (row < limit) {
         bf16* dst = base + (int64_t(b) * limit + row) * ld + h * DH + c0;
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(128) attn_tc_bwd_kernel(const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 
@@ -465,8 +472,8 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_gen_kernel(const __grid_const
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int k0 = kbase + c0 + 2 * i;
-          const float a = k0 < p.Nk ? exp2f(__uint_as_float(r[2 * i]) * sl2 - moff) : 0.f;
-          const float c = k0 + 1 < p.Nk ? exp2f(__uint_as_float(r[2 * i + 1]) * sl2 - moff) : 0.f;
+          const float a = k0 < p.Nk ? fast_exp2(__uint_as_float(r[2 * i]) * sl2 - moff) : 0.f;
+          const float c = k0 + 1 < p.Nk ? fast_exp2(__uint_as_float(r[2 * i + 1]) * sl2 - moff) : 0.f;
           sum += a + c;
           pk[i] = pack_bf16x2(a, c);
         }
@@ -569,8 +576,8 @@ __device__ __forceinline__ void bwd_tile_elementwise(uint32_t trow, int row, int
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float p0 = c0 + 2 * i < nk_valid ? exp2f(__uint_as_float(s[2 * i]) * sl2 - lse2) : 0.f;
-        const float p1 = c0 + 2 * i + 1 < nk_valid ? exp2f(__uint_as_float(s[2 * i + 1]) * sl2 - lse2) : 0.f;
+        const float p0 = c0 + 2 * i < nk_valid ? fast_exp2(__uint_as_float(s[2 * i]) * sl2 - lse2) : 0.f;
+        const float p1 = c0 + 2 * i + 1 < nk_valid ? fast_exp2(__uint_as_float(s[2 * i + 1]) * sl2 - lse2) : 0.f;
         pp[i] = pack_bf16x2(p0, p1);
         ds[i] = pack_bf16x2(p0 * (__uint_as_float(d[2 * i]) - del), p1 * (__uint_as_float(d[2 * i + 1]) - del));
       }
@@ -967,10 +974,11 @@ int attn_tc_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, con
   p.lse = lse; p.delta = delta;
   p.dQ = reinterpret_cast<bf16*>(dq); p.dK = reinterpret_cast<bf16*>(dk); p.dV = reinterpret_cast<bf16*>(dv);
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
-  constexpr int SMEM = 8 * TILE_BYTES + 64 + 1024;
+  constexpr int SMEM = ATTN_BWD_SMEM;
   static bool configured = false;
   if (!configured) {
     MMAE_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    MMAE_CUDA_OK(cudaFuncSetAttribute(attn_tc_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
   launch_k(attn_tc_bwd_kernel, dim3(H, B), 128, SMEM, st, tq, tk, tv, tdo, p);

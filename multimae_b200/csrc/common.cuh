@@ -139,6 +139,12 @@ __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf_unnor
   cdf = x >= 0.f ? 0.5f + half_erf : 0.5f - half_erf;
   pdf_unnorm = e;
 }
+// 2^x with one MUFU.EX2 (exp2f without fast-math adds range fix-ups around the same instruction)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   float cdf, e;
   gelu_parts(x, cdf, e);
