@@ -45,20 +45,28 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// Fragment loads with ldmatrix (one instruction per fragment instead of 2-4 scalar LDS; the 80-byte row pitch keeps the
+// eight 16-byte row segments of a matrix on distinct banks).
 // A fragment (16 rows x 16 k) from row-major smem s[row][k]
 __device__ __forceinline__ void load_a_frag(uint32_t (&a)[4], const bf16* s, int ld, int row0, int k0, int g, int t) {
-  const bf16* p0 = s + (row0 + g) * ld + k0 + 2 * t;
-  const bf16* p1 = p0 + 8 * ld;
-  a[0] = *reinterpret_cast<const uint32_t*>(p0);
-  a[1] = *reinterpret_cast<const uint32_t*>(p1);
-  a[2] = *reinterpret_cast<const uint32_t*>(p0 + 8);
-  a[3] = *reinterpret_cast<const uint32_t*>(p1 + 8);
+  const int lane = g * 4 + t;
+  const bf16* p = s + (row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ld + k0 + (lane >> 4) * 8;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3])
+               : "r"(smem_u32(p)));
 }
 // B fragment (16 k x 8 n) from smem stored as s[n][k] (k contiguous)
 __device__ __forceinline__ void load_b_frag(uint32_t (&b)[2], const bf16* s, int ld, int n0, int k0, int g, int t) {
-  const bf16* p = s + (n0 + g) * ld + k0 + 2 * t;
-  b[0] = *reinterpret_cast<const uint32_t*>(p);
-  b[1] = *reinterpret_cast<const uint32_t*>(p + 8);
+  const int lane = (g * 4 + t) & 15;
+  const bf16* p = s + (n0 + (lane & 7)) * ld + k0 + (lane >> 3) * 8;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(b[0]), "=r"(b[1]) : "r"(smem_u32(p)));
+}
+// B fragment (16 k x 8 n) from smem stored as s[k][n] (n contiguous: a row-major [rows = k][cols = n] tile as it was
+// loaded) - the transposing ldmatrix replaces a transposed copy of the tile in shared memory
+__device__ __forceinline__ void load_b_frag_t(uint32_t (&b)[2], const bf16* s, int ld, int k0, int n0, int g, int t) {
+  const int lane = (g * 4 + t) & 15;
+  const bf16* p = s + (k0 + (lane & 7) + (lane >> 3) * 8) * ld + n0;
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b[0]), "=r"(b[1]) : "r"(smem_u32(p)));
 }
 
 // Copy `ATT_CHUNK` rows x DH columns of a global [rows, ld] matrix into row-major smem (pitch DH+8), zero-filling
@@ -93,7 +101,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
   constexpr int LDS = DH + 8, LDT = ATT_CHUNK + 8;
   __shared__ __align__(16) bf16 sQ[ATT_ROWS * LDS];
   __shared__ __align__(16) bf16 sK[ATT_CHUNK * LDS];
-  __shared__ __align__(16) bf16 sVt[DH * LDT];
+  __shared__ __align__(16) bf16 sV[ATT_CHUNK * LDS];
 
   const int q0 = blockIdx.x * ATT_ROWS, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -116,7 +124,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
   for (int k0 = 0; k0 < Nk; k0 += ATT_CHUNK) {
     __syncthreads();
     load_chunk<DH, true, false>(sK, nullptr, Kb, ldk, k0, Nk);
-    load_chunk<DH, false, true>(nullptr, sVt, Vb, ldv, k0, Nk);
+    load_chunk<DH, true, false>(sV, nullptr, Vb, ldv, k0, Nk);
     __syncthreads();
 
     float s[ATT_CHUNK / 8][4];
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
 #pragma unroll
       for (int jd = 0; jd < DH / 8; ++jd) {
         uint32_t bfr[2];
-        load_b_frag(bfr, sVt, LDT, jd * 8, ks * 16, g, t);
+        load_b_frag_t(bfr, sV, LDS, ks * 16, jd * 8, g, t);
         mma_bf16_16816(acc[jd], pa, bfr);
       }
     }
@@ -261,7 +269,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
   __shared__ __align__(16) bf16 sA[ATT_ROWS * LDS];   // Q tile, then dO tile (staging for the A fragments)
   __shared__ __align__(16) bf16 sK[ATT_CHUNK * LDS];
   __shared__ __align__(16) bf16 sV[ATT_CHUNK * LDS];
-  __shared__ __align__(16) bf16 sKt[DH * LDT];
 
   const int q0 = blockIdx.x * ATT_ROWS, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -294,7 +301,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
 
   for (int k0 = 0; k0 < Nk; k0 += ATT_CHUNK) {
     __syncthreads();
-    load_chunk<DH, true, true>(sK, sKt, Kb, ldk, k0, Nk);
+    load_chunk<DH, true, false>(sK, nullptr, Kb, ldk, k0, Nk);
     load_chunk<DH, true, false>(sV, nullptr, Vb, ldv, k0, Nk);
     __syncthreads();
 #pragma unroll
@@ -322,7 +329,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
 #pragma unroll
       for (int jd = 0; jd < DH / 8; ++jd) {
         uint32_t bfr[2];
-        load_b_frag(bfr, sKt, LDT, jd * 8, ks * 16, g, t);
+        load_b_frag_t(bfr, sK, LDS, ks * 16, jd * 8, g, t);
         mma_bf16_16816(acc[jd], dsa, bfr);
       }
     }
@@ -353,8 +360,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
   constexpr int LDS = DH + 8, LDT = ATT_CHUNK + 8;
   __shared__ __align__(16) bf16 sQ[ATT_CHUNK * LDS];
   __shared__ __align__(16) bf16 sdO[ATT_CHUNK * LDS];
-  __shared__ __align__(16) bf16 sQt[DH * LDT];
-  __shared__ __align__(16) bf16 sdOt[DH * LDT];
   __shared__ float sLse[ATT_CHUNK], sDel[ATT_CHUNK];
 
   const int k0 = blockIdx.x * ATT_ROWS, h = blockIdx.y, b = blockIdx.z;
@@ -387,8 +392,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
 
   for (int q0 = 0; q0 < Nq; q0 += ATT_CHUNK) {
     __syncthreads();
-    load_chunk<DH, true, true>(sQ, sQt, Qb, ldq, q0, Nq);
-    load_chunk<DH, true, true>(sdO, sdOt, dOb, lddo, q0, Nq);
+    load_chunk<DH, true, false>(sQ, nullptr, Qb, ldq, q0, Nq);
+    load_chunk<DH, true, false>(sdO, nullptr, dOb, lddo, q0, Nq);
     if (threadIdx.x < ATT_CHUNK) {
       const int q = q0 + threadIdx.x;
       sLse[threadIdx.x] = q < Nq ? Lp[q] * LOG2E : INFINITY;   // +inf -> P = 0 for padded queries
@@ -422,8 +427,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
 #pragma unroll
       for (int jd = 0; jd < DH / 8; ++jd) {
         uint32_t b1[2], b2[2];
-        load_b_frag(b1, sdOt, LDT, jd * 8, qs * 16, g, t);
-        load_b_frag(b2, sQt, LDT, jd * 8, qs * 16, g, t);
+        load_b_frag_t(b1, sdO, LDS, qs * 16, jd * 8, g, t);
+        load_b_frag_t(b2, sQ, LDS, qs * 16, jd * 8, g, t);
         mma_bf16_16816(dv[jd], pa, b1);    // dV += P^T dO
         mma_bf16_16816(dk[jd], dsa, b2);   // dK += dS^T Q
       }
