@@ -150,8 +150,9 @@ int mmae_layernorm_backward_ex(const void* dy, int dy_is_bf16, int64_t lddy, con
  * [b*N, (b+1)*N).  head_dim in {32, 64}.  lse[B,H,Nq] = log-sum-exp of the scaled scores (saved for backward).
  * backward: delta_ws is a [B,H,Nq] fp32 scratch; dq/dk/dv are written (not accumulated).
  * ---------------------------------------------------------------------------------------------- */
-/* bit mask: 1 = fused single-tile tcgen05 kernels (Nq, Nk <= 128, head_dim 64), 2 = general tcgen05 forward (<= 256 keys,
- * head_dim 32/64), 4 = general tcgen05 backward; 0 = warp-MMA kernels everywhere.  Default 3 (env MMAE_ATTN_TC). */
+/* bit mask: 1 = fused single-tile tcgen05 kernels (Nq, Nk <= 128, head_dim 64), 2 = general tcgen05 forward (head_dim
+ * 32/64; used for <= 128 keys, with 8 also for <= 256 keys), 4 = general tcgen05 backward; 0 = warp-MMA (mma.sync +
+ * ldmatrix + cp.async) kernels everywhere.  Default 3 (env MMAE_ATTN_TC). */
 int mmae_attention_set_tc(int enable);
 int mmae_attention_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                            void* o, int64_t ldo, float* lse, int B, int H, int Nq, int Nk, int head_dim,

@@ -87,6 +87,31 @@ __device__ __forceinline__ void load_chunk(bf16* s, bf16* st, const bf16* gbase,
   }
 }
 
+// Asynchronous variant for the streamed operand: 16-byte cp.async per (row, 8 columns), rows >= rows_valid zero-filled
+// (src-size 0), so the next chunk is in flight while the current one is consumed.
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(valid ? 4 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <int DH>
+__device__ __forceinline__ void load_chunk_async(bf16* s, const bf16* gbase, int64_t ld, int row0, int rows_valid) {
+  constexpr int LDS = DH + 8, VPR = DH / 8;
+  for (int idx = threadIdx.x; idx < ATT_CHUNK * VPR; idx += ATT_THREADS) {
+    const int r = idx / VPR, cv = idx % VPR;
+    const bool ok = row0 + r < rows_valid;
+    cp_async_16(s + r * LDS + cv * 8, gbase + int64_t(ok ? row0 + r : 0) * ld + cv * 8, ok);
+  }
+}
+
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
@@ -100,8 +125,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
   pdl_prologue();
   constexpr int LDS = DH + 8, LDT = ATT_CHUNK + 8;
   __shared__ __align__(16) bf16 sQ[ATT_ROWS * LDS];
-  __shared__ __align__(16) bf16 sK[ATT_CHUNK * LDS];
-  __shared__ __align__(16) bf16 sV[ATT_CHUNK * LDS];
+  __shared__ __align__(16) bf16 sKb[2][ATT_CHUNK * LDS];
+  __shared__ __align__(16) bf16 sVb[2][ATT_CHUNK * LDS];
 
   const int q0 = blockIdx.x * ATT_ROWS, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -109,6 +134,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
   const bf16* Kb = K + int64_t(b) * Nk * ldk + h * DH;
   const bf16* Vb = V + int64_t(b) * Nk * ldv + h * DH;
 
+  load_chunk_async<DH>(sKb[0], Kb, ldk, 0, Nk);      // first key chunk flies while Q is staged
+  load_chunk_async<DH>(sVb[0], Vb, ldv, 0, Nk);
+  cp_async_commit();
   load_chunk<DH, true, false>(sQ, nullptr, Qb, ldq, q0, Nq);
   __syncthreads();
   uint32_t qa[DH / 16][4];
@@ -121,10 +149,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const float sl2 = scale * LOG2E;
 
-  for (int k0 = 0; k0 < Nk; k0 += ATT_CHUNK) {
-    __syncthreads();
-    load_chunk<DH, true, false>(sK, nullptr, Kb, ldk, k0, Nk);
-    load_chunk<DH, true, false>(sV, nullptr, Vb, ldv, k0, Nk);
+  for (int k0 = 0, it = 0; k0 < Nk; k0 += ATT_CHUNK, ++it) {
+    const bf16* sK = sKb[it & 1];
+    const bf16* sV = sVb[it & 1];
+    if (k0 + ATT_CHUNK < Nk) {      // prefetch the next chunk into the other buffer (its readers finished last iteration)
+      load_chunk_async<DH>(sKb[(it + 1) & 1], Kb, ldk, k0 + ATT_CHUNK, Nk);
+      load_chunk_async<DH>(sVb[(it + 1) & 1], Vb, ldv, k0 + ATT_CHUNK, Nk);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
 
     float s[ATT_CHUNK / 8][4];
@@ -189,6 +224,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const bf16* __res
         mma_bf16_16816(acc[jd], pa, bfr);
       }
     }
+    __syncthreads();   // every warp is done with this buffer before the next iteration's prefetch overwrites it
   }
 
 #pragma unroll
@@ -267,8 +303,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
   pdl_prologue();
   constexpr int LDS = DH + 8, LDT = ATT_CHUNK + 8;
   __shared__ __align__(16) bf16 sA[ATT_ROWS * LDS];   // Q tile, then dO tile (staging for the A fragments)
-  __shared__ __align__(16) bf16 sK[ATT_CHUNK * LDS];
-  __shared__ __align__(16) bf16 sV[ATT_CHUNK * LDS];
+  __shared__ __align__(16) bf16 sKb[2][ATT_CHUNK * LDS];
+  __shared__ __align__(16) bf16 sVb[2][ATT_CHUNK * LDS];
 
   const int q0 = blockIdx.x * ATT_ROWS, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -278,6 +314,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
   const bf16* dOb = dO + int64_t(b) * Nq * lddo + h * DH;
 
   uint32_t qa[DH / 16][4], doa[DH / 16][4];
+  load_chunk_async<DH>(sKb[0], Kb, ldk, 0, Nk);      // first key chunk flies while Q / dO are staged
+  load_chunk_async<DH>(sVb[0], Vb, ldv, 0, Nk);
+  cp_async_commit();
   load_chunk<DH, true, false>(sA, nullptr, Qb, ldq, q0, Nq);
   __syncthreads();
 #pragma unroll
@@ -299,10 +338,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
 #pragma unroll
   for (int j = 0; j < DH / 8; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 
-  for (int k0 = 0; k0 < Nk; k0 += ATT_CHUNK) {
-    __syncthreads();
-    load_chunk<DH, true, false>(sK, nullptr, Kb, ldk, k0, Nk);
-    load_chunk<DH, true, false>(sV, nullptr, Vb, ldv, k0, Nk);
+  for (int k0 = 0, it = 0; k0 < Nk; k0 += ATT_CHUNK, ++it) {
+    const bf16* sK = sKb[it & 1];
+    const bf16* sV = sVb[it & 1];
+    if (k0 + ATT_CHUNK < Nk) {
+      load_chunk_async<DH>(sKb[(it + 1) & 1], Kb, ldk, k0 + ATT_CHUNK, Nk);
+      load_chunk_async<DH>(sVb[(it + 1) & 1], Vb, ldv, k0 + ATT_CHUNK, Nk);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
 #pragma unroll
     for (int ks = 0; ks < ATT_CHUNK / 16; ++ks) {
@@ -333,6 +379,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dq_kernel(const bf16* __
         mma_bf16_16816(acc[jd], dsa, bfr);
       }
     }
+    __syncthreads();   // buffer free for the prefetch of the next iteration
   }
   bf16* dQb = dQ + int64_t(b) * Nq * lddq + h * DH;
 #pragma unroll
@@ -358,9 +405,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
                                                                    int H, float scale) {
   pdl_prologue();
   constexpr int LDS = DH + 8, LDT = ATT_CHUNK + 8;
-  __shared__ __align__(16) bf16 sQ[ATT_CHUNK * LDS];
-  __shared__ __align__(16) bf16 sdO[ATT_CHUNK * LDS];
-  __shared__ float sLse[ATT_CHUNK], sDel[ATT_CHUNK];
+  __shared__ __align__(16) bf16 sQb[2][ATT_CHUNK * LDS];
+  __shared__ __align__(16) bf16 sdOb[2][ATT_CHUNK * LDS];
+  __shared__ float sLseb[2][ATT_CHUNK], sDelb[2][ATT_CHUNK];
+  bf16* sQ = sQb[0];      // the stationary K / V tiles are staged through buffer 0 first
+  bf16* sdO = sdOb[0];
 
   const int k0 = blockIdx.x * ATT_ROWS, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -390,14 +439,31 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
   }
   const float sl2 = scale * LOG2E;
 
-  for (int q0 = 0; q0 < Nq; q0 += ATT_CHUNK) {
-    __syncthreads();
-    load_chunk<DH, true, false>(sQ, nullptr, Qb, ldq, q0, Nq);
-    load_chunk<DH, true, false>(sdO, nullptr, dOb, lddo, q0, Nq);
+  // query chunks stream through two buffers: Q, dO rows and their lse / delta arrive by cp.async while the previous chunk
+  // is consumed.  Rows past Nq are zero-filled: Q = dO = 0 and delta = 0 make their P and dS contributions vanish.
+  auto issue_chunk = [&](int buf, int q0) {
+    load_chunk_async<DH>(sQb[buf], Qb, ldq, q0, Nq);
+    load_chunk_async<DH>(sdOb[buf], dOb, lddo, q0, Nq);
     if (threadIdx.x < ATT_CHUNK) {
       const int q = q0 + threadIdx.x;
-      sLse[threadIdx.x] = q < Nq ? Lp[q] * LOG2E : INFINITY;   // +inf -> P = 0 for padded queries
-      sDel[threadIdx.x] = q < Nq ? Dp[q] : 0.f;
+      const bool ok = q < Nq;
+      cp_async_4(&sLseb[buf][threadIdx.x], Lp + (ok ? q : 0), ok);
+      cp_async_4(&sDelb[buf][threadIdx.x], Dp + (ok ? q : 0), ok);
+    }
+    cp_async_commit();
+  };
+  __syncthreads();          // all K / V fragments are in registers: buffer 0 may be overwritten
+  issue_chunk(0, 0);
+  for (int q0 = 0, it = 0; q0 < Nq; q0 += ATT_CHUNK, ++it) {
+    sQ = sQb[it & 1];
+    sdO = sdOb[it & 1];
+    const float* sLse = sLseb[it & 1];
+    const float* sDel = sDelb[it & 1];
+    if (q0 + ATT_CHUNK < Nq) {
+      issue_chunk((it + 1) & 1, q0 + ATT_CHUNK);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
 #pragma unroll
@@ -416,7 +482,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
           mma_bf16_16816(dp, va[kk], bd);   // dP^T[key, q]
         }
         const int qc = n0 + 2 * t;
-        const float l0 = sLse[qc], l1 = sLse[qc + 1], d0 = sDel[qc], d1 = sDel[qc + 1];
+        const float l0 = sLse[qc] * LOG2E, l1 = sLse[qc + 1] * LOG2E, d0 = sDel[qc], d1 = sDel[qc + 1];
         const float p0 = fast_exp2(s[0] * sl2 - l0), p1 = fast_exp2(s[1] * sl2 - l1);
         const float p2 = fast_exp2(s[2] * sl2 - l0), p3 = fast_exp2(s[3] * sl2 - l1);
         pa[half * 2 + 0] = pack_bf16x2(p0, p1);
@@ -433,6 +499,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_dkv_kernel(const bf16* _
         mma_bf16_16816(dk[jd], dsa, b2);   // dK += dS^T Q
       }
     }
+    __syncthreads();   // buffer free for the prefetch of the next iteration
   }
   const int row_a = k0 + warp * 16 + g, row_b = row_a + 8;
   bf16* dKb = dK + int64_t(b) * Nk * lddk + h * DH;
@@ -482,7 +549,10 @@ extern "C" int mmae_attention_forward(const void* q, int64_t ldq, const void* k,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim))
     return attn_tc_forward(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, scale, st);
-  if ((g_attn_tc & 2) && attn_tc_fwd_gen_supported(H, Nq, Nk, head_dim))
+  // general tcgen05 forward: wins for up to 128 keys (26-29 us vs 33 us at 196 x 99 x 32, B*H = 1024); with a second key
+  // box the mma.sync kernel with ldmatrix + cp.async double buffering is ahead (50 vs 63 us at 196 x 196 x 32); bit 3 of
+  // the switch (8) forces the tcgen05 kernel for every supported shape
+  if ((g_attn_tc & 2) && attn_tc_fwd_gen_supported(H, Nq, Nk, head_dim) && (Nk <= 128 || (g_attn_tc & 8)))
     return attn_tc_forward_gen(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, head_dim, scale, st);
   const bf16 *qp = (const bf16*)q, *kp = (const bf16*)k, *vp = (const bf16*)v;
   if (head_dim == 64)

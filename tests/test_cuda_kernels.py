@@ -184,7 +184,7 @@ ATTN_CASES = [(3, 12, 99, 99, 64, True), (2, 8, 196, 99, 32, False), (2, 8, 196,
               (1, 2, 100, 33, 64, False)]
 
 
-@pytest.mark.parametrize("tc", [0, 1, 3, 7])
+@pytest.mark.parametrize("tc", [0, 1, 3, 7, 15])     # 15: every tcgen05 kernel wherever it is supported
 @pytest.mark.parametrize("case", ATTN_CASES)
 def test_attention_forward_backward(dev, KN, tc, case):
     from multimae_b200 import _lib as L
