@@ -79,8 +79,7 @@ __global__ void __launch_bounds__(256) cast_colsum_kernel(const void* __restrict
 // dst[c] += sum_y partial[y, c]: block (32, 32) per 32 columns, y strided over the 32 thread rows (a latency-bound
 // kernel: ~Y/32 dependent-free loads per thread, all issued before the first add)
 __global__ void __launch_bounds__(1024) colred_finalize_kernel(const float* __restrict__ partial, int Y, int ld, int C, int seg,
-                                                               float* __restrict__ d0, float* __restrict__ d1,
-                                                               float* __restrict__ d2) {
+                                                               const ColredDst dsts) {
   pdl_prologue();
   __shared__ float red[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
@@ -103,7 +102,7 @@ __global__ void __launch_bounds__(1024) colred_finalize_kernel(const float* __re
   const int cc = blockIdx.x * 32 + threadIdx.y;
   if (threadIdx.x == 0 && cc < C) {
     const int k = cc / seg;
-    float* d = k == 0 ? d0 : (k == 1 ? d1 : d2);
+    float* d = dsts.p[k];
     if (d != nullptr) d[cc - k * seg] += v;
   }
 }
@@ -405,13 +404,20 @@ float* colred_scratch(size_t floats, cudaStream_t st) {
   return s->buf;
 }
 
-int colred_finalize(const float* partial, int Y, int ld, int seg, float* dst0, float* dst1, float* dst2, cudaStream_t st) {
-  const int nseg = dst2 ? 3 : (dst1 ? 2 : 1);
+int colred_finalize_n(const float* partial, int Y, int ld, int seg, const ColredDst& dst, int nseg, cudaStream_t st) {
   dim3 grid(ceil_div(seg * nseg, 32)), block(32, 32);
-  launch_k(colred_finalize_kernel, grid, block, 0, st, partial, Y, ld, seg * nseg, seg, dst0, dst1, dst2);
+  launch_k(colred_finalize_kernel, grid, block, 0, st, partial, Y, ld, seg * nseg, seg, dst);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
+}
+int colred_finalize(const float* partial, int Y, int ld, int seg, float* dst0, float* dst1, float* dst2, cudaStream_t st) {
+  ColredDst dst;
+  for (int i = 0; i < 9; ++i) dst.p[i] = nullptr;
+  dst.p[0] = dst0;
+  dst.p[1] = dst1;
+  dst.p[2] = dst2;
+  return colred_finalize_n(partial, Y, ld, seg, dst, dst2 ? 3 : (dst1 ? 2 : 1), st);
 }
 }  // namespace mmae
 

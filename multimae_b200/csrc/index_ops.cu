@@ -166,105 +166,166 @@ __global__ void __launch_bounds__(256) semseg_emb_bwd_kernel(const bf16* __restr
 //   context[b, i]  = ctx[b, i] + task_emb[task(i)] + pos[patch(i)]   (i < T);   context[b, T+g] = ctx[b, T+g]
 // One CTA row per output row; rows [0, B*P) are queries, rows [B*P, B*P + B*(T+G)) are context.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) dec_build_kernel(const float* __restrict__ ctx, mmae_decoder_index ix,
-                                                       const float* __restrict__ mask_token, TaskEmbPtrs task_emb,
-                                                       const float* __restrict__ pos,  // [P, Dd]
-                                                       float* __restrict__ queries, float* __restrict__ context) {
+constexpr int DBF_ROWS = 16;   // rows per block: 4 row lanes x 4 rows in flight per thread
+__global__ void __launch_bounds__(256) dec_build_kernel(const float* __restrict__ ctx, mmae_decoder_index ix,
+                                                        const float* __restrict__ mask_token, TaskEmbPtrs task_emb,
+                                                        const float* __restrict__ pos,  // [P, Dd]
+                                                        float* __restrict__ queries, float* __restrict__ context) {
   pdl_prologue();
   const int Dd = ix.dim, T = ix.num_visible, G = ix.num_global, P = ix.num_queries;
-  const int row = blockIdx.x;
-  const int nq_rows = ix.batch * P;
-  const float4 *base, *te = nullptr, *pe = nullptr;
-  float4* dst;
-  if (row < nq_rows) {
-    const int b = row / P, j = row % P;
-    const int g = ix.tok_offset[ix.own_task] + j;
-    const int rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
-    base = rank < T ? reinterpret_cast<const float4*>(ctx + (int64_t(b) * (T + G) + rank) * Dd)
-                    : reinterpret_cast<const float4*>(mask_token);
-    te = reinterpret_cast<const float4*>(task_emb.p[ix.own_task]);
-    pe = reinterpret_cast<const float4*>(pos + int64_t(j) * Dd);
-    dst = reinterpret_cast<float4*>(queries + int64_t(row) * Dd);
-  } else {
-    const int cr = row - nq_rows;
-    const int b = cr / (T + G), i = cr % (T + G);
-    base = reinterpret_cast<const float4*>(ctx + int64_t(cr) * Dd);
-    dst = reinterpret_cast<float4*>(context + int64_t(cr) * Dd);
-    te = nullptr;
-    pe = nullptr;
-    if (i < T) {
-      const int g = (int)ix.ids_keep[int64_t(b) * T + i];
-      int t = 0;
+  const int nq_rows = ix.batch * P, n_rows = nq_rows + ix.batch * (T + G);
+  const int rl = threadIdx.x >> 6, ct = threadIdx.x & 63;     // row lane, column thread (float4 columns ct, ct+64, ...)
+  // resolve the 4 rows of this thread first (index loads in flight together), then move the data
+  const float4 *base[4], *te[4], *pe[4];
+  float4* dst[4];
 #pragma unroll
-      for (int q = 1; q < MMAE_MAX_TASKS; ++q)
-        if (q < ix.num_tasks && g >= ix.tok_offset[q]) t = q;
-      te = reinterpret_cast<const float4*>(task_emb.p[t]);
-      pe = reinterpret_cast<const float4*>(pos + int64_t(g - ix.tok_offset[t]) * Dd);
+  for (int u = 0; u < 4; ++u) {
+    const int row = blockIdx.x * DBF_ROWS + u * 4 + rl;
+    base[u] = te[u] = pe[u] = nullptr;
+    dst[u] = nullptr;
+    if (row >= n_rows) continue;
+    if (row < nq_rows) {
+      const int b = row / P, j = row % P;
+      const int g = ix.tok_offset[ix.own_task] + j;
+      const int rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
+      base[u] = rank < T ? reinterpret_cast<const float4*>(ctx + (int64_t(b) * (T + G) + rank) * Dd)
+                         : reinterpret_cast<const float4*>(mask_token);
+      te[u] = reinterpret_cast<const float4*>(task_emb.p[ix.own_task]);
+      pe[u] = reinterpret_cast<const float4*>(pos + int64_t(j) * Dd);
+      dst[u] = reinterpret_cast<float4*>(queries + int64_t(row) * Dd);
+    } else {
+      const int cr = row - nq_rows;
+      const int b = cr / (T + G), i = cr % (T + G);
+      base[u] = reinterpret_cast<const float4*>(ctx + int64_t(cr) * Dd);
+      dst[u] = reinterpret_cast<float4*>(context + int64_t(cr) * Dd);
+      if (i < T) {
+        const int g = (int)ix.ids_keep[int64_t(b) * T + i];
+        int t = 0;
+#pragma unroll
+        for (int q = 1; q < MMAE_MAX_TASKS; ++q)
+          if (q < ix.num_tasks && g >= ix.tok_offset[q]) t = q;
+        te[u] = reinterpret_cast<const float4*>(task_emb.p[t]);
+        pe[u] = reinterpret_cast<const float4*>(pos + int64_t(g - ix.tok_offset[t]) * Dd);
+      }
     }
   }
-  for (int c = threadIdx.x; c < Dd / 4; c += blockDim.x) {
-    float4 v = __ldg(base + c);
-    if (pe) {
-      const float4 p4 = __ldg(pe + c);
-      v.x += p4.x; v.y += p4.y; v.z += p4.z; v.w += p4.w;
+  for (int c = ct; c < Dd / 4; c += 64) {
+    float4 v[4], p4[4], a4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (dst[u] == nullptr) continue;
+      v[u] = __ldg(base[u] + c);
+      p4[u] = pe[u] ? __ldg(pe[u] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      a4[u] = te[u] ? __ldg(te[u] + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (te) {
-      const float4 a = __ldg(te + c);
-      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (dst[u] == nullptr) continue;
+      // same association as the reference: (ctx + pos) + task_emb
+      float4 o = make_float4(v[u].x + p4[u].x, v[u].y + p4[u].y, v[u].z + p4[u].z, v[u].w + p4[u].w);
+      if (te[u]) o = make_float4(o.x + a4[u].x, o.y + a4[u].y, o.z + a4[u].z, o.w + a4[u].w);
+      dst[u][c] = o;
     }
-    dst[c] = v;
   }
 }
 
 // backward: dctx[b,i] = dcontext[b,i] (+ dqueries[b, g-start] if token i belongs to the own task);
 // dmask_token += dqueries of masked positions; dtask_emb[t] += dcontext rows of task t (+ all dqueries for own).
-constexpr int DB_ROWS = 16;
+// Block = 4 row lanes x 64 column threads (float4 columns), DB_ROWS rows per block, 4 rows in flight per thread.  The
+// column sums (mask token, one task embedding per task) leave as one partial row per block [1 + MAX_TASKS segments of Dd]
+// and are added up by colred_finalize_n: thousands of blocks x Dd x (1 + tasks) scalar atomics on ~5 KB serialise in L2.
+constexpr int DB_ROWS = 64;
 __global__ void __launch_bounds__(256) dec_build_bwd_kernel(const float* __restrict__ dqueries,
                                                             const float* __restrict__ dcontext, mmae_decoder_index ix,
-                                                            float* __restrict__ dctx, float* __restrict__ dmask_token,
-                                                            TaskEmbGradPtrs dtask_emb) {
+                                                            float* __restrict__ dctx, float* __restrict__ partial) {
   pdl_prologue();
+  extern __shared__ float4 dbred[];   // [4 row lanes][1 + MAX_TASKS][Dd / 4]
   const int Dd = ix.dim, T = ix.num_visible, G = ix.num_global, P = ix.num_queries;
-  const int nq_rows = ix.batch * P, nc_rows = ix.batch * (T + G);
-  const int row0 = blockIdx.x * DB_ROWS;
-  const int c = threadIdx.x;  // one column per thread; Dd <= 256 handled by the loop below
-  for (int col = c; col < Dd; col += blockDim.x) {
-    float acc_mask = 0.f;
-    float acc_te[MMAE_MAX_TASKS];
+  const int nq_rows = ix.batch * P, n_rows = nq_rows + ix.batch * (T + G);
+  const int rl = threadIdx.x >> 6, ct = threadIdx.x & 63;
+  const int d4 = Dd / 4;
+  for (int c = ct; c < d4; c += 64) {
+    float4 acc[1 + MMAE_MAX_TASKS];
 #pragma unroll
-    for (int t = 0; t < MMAE_MAX_TASKS; ++t) acc_te[t] = 0.f;
-    for (int row = row0; row < min(row0 + DB_ROWS, nq_rows + nc_rows); ++row) {
-      if (row < nq_rows) {
-        const int b = row / P, j = row % P;
-        const int g = ix.tok_offset[ix.own_task] + j;
-        const int rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
-        const float v = dqueries[int64_t(row) * Dd + col];
-        if (rank >= T) acc_mask += v;
+    for (int k = 0; k < 1 + MMAE_MAX_TASKS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r0 = 0; r0 < DB_ROWS; r0 += 16) {
+      // resolve 4 rows, load, then combine
+      int kind[4], task[4];          // kind: -1 none, 0 query row, 1 context row of a visible token, 2 global-token row
+      int64_t src_q[4], src_c[4];
+      bool masked[4];
 #pragma unroll
-        for (int t = 0; t < MMAE_MAX_TASKS; ++t)
-          if (t == ix.own_task) acc_te[t] += v;
-      } else {
-        const int cr = row - nq_rows;
-        const int b = cr / (T + G), i = cr % (T + G);
-        float v = dcontext[int64_t(cr) * Dd + col];
-        if (i < T) {
-          const int g = (int)ix.ids_keep[int64_t(b) * T + i];
-          int t = 0;
+      for (int u = 0; u < 4; ++u) {
+        const int row = blockIdx.x * DB_ROWS + r0 + u * 4 + rl;
+        kind[u] = -1;
+        task[u] = 0;
+        src_q[u] = src_c[u] = -1;
+        masked[u] = false;
+        if (row >= n_rows) continue;
+        if (row < nq_rows) {
+          const int b = row / P, j = row % P;
+          const int g = ix.tok_offset[ix.own_task] + j;
+          const int rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
+          kind[u] = 0;
+          task[u] = ix.own_task;
+          masked[u] = rank >= T;
+          src_q[u] = int64_t(row);
+        } else {
+          const int cr = row - nq_rows;
+          const int b = cr / (T + G), i = cr % (T + G);
+          src_c[u] = int64_t(cr);
+          kind[u] = 2;
+          if (i < T) {
+            const int g = (int)ix.ids_keep[int64_t(b) * T + i];
+            int t = 0;
 #pragma unroll
-          for (int q = 1; q < MMAE_MAX_TASKS; ++q)
-            if (q < ix.num_tasks && g >= ix.tok_offset[q]) t = q;
-#pragma unroll
-          for (int tt = 0; tt < MMAE_MAX_TASKS; ++tt)
-            if (tt == t) acc_te[tt] += v;
-          if (t == ix.own_task) v += dqueries[(int64_t(b) * P + (g - ix.tok_offset[t])) * Dd + col];
+            for (int q = 1; q < MMAE_MAX_TASKS; ++q)
+              if (q < ix.num_tasks && g >= ix.tok_offset[q]) t = q;
+            kind[u] = 1;
+            task[u] = t;
+            if (t == ix.own_task) src_q[u] = int64_t(b) * P + (g - ix.tok_offset[t]);
+          }
         }
-        dctx[int64_t(cr) * Dd + col] = v;
+      }
+      float4 vq[4], vc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vq[u] = src_q[u] >= 0 ? __ldg(reinterpret_cast<const float4*>(dqueries + src_q[u] * Dd) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vc[u] = src_c[u] >= 0 ? __ldg(reinterpret_cast<const float4*>(dcontext + src_c[u] * Dd) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (kind[u] < 0) continue;
+        if (kind[u] == 0) {          // query row: mask token (if masked) and the own task embedding
+          if (masked[u]) { acc[0].x += vq[u].x; acc[0].y += vq[u].y; acc[0].z += vq[u].z; acc[0].w += vq[u].w; }
+#pragma unroll
+          for (int t = 0; t < MMAE_MAX_TASKS; ++t)
+            if (t == task[u]) { acc[1 + t].x += vq[u].x; acc[1 + t].y += vq[u].y; acc[1 + t].z += vq[u].z; acc[1 + t].w += vq[u].w; }
+        } else {
+          float4 v = vc[u];
+          if (kind[u] == 1) {
+#pragma unroll
+            for (int t = 0; t < MMAE_MAX_TASKS; ++t)
+              if (t == task[u]) { acc[1 + t].x += v.x; acc[1 + t].y += v.y; acc[1 + t].z += v.z; acc[1 + t].w += v.w; }
+            if (src_q[u] >= 0) { v.x += vq[u].x; v.y += vq[u].y; v.z += vq[u].z; v.w += vq[u].w; }
+          }
+          reinterpret_cast<float4*>(dctx + src_c[u] * Dd)[c] = v;
+        }
       }
     }
-    if (acc_mask != 0.f) atomicAdd(dmask_token + col, acc_mask);
+    // block reduction over the 4 row lanes, then this block's partial row
 #pragma unroll
-    for (int t = 0; t < MMAE_MAX_TASKS; ++t)
-      if (t < ix.num_tasks && dtask_emb.p[t] != nullptr && acc_te[t] != 0.f) atomicAdd(dtask_emb.p[t] + col, acc_te[t]);
+    for (int k = 0; k < 1 + MMAE_MAX_TASKS; ++k) dbred[(rl * (1 + MMAE_MAX_TASKS) + k) * d4 + c] = acc[k];
+  }
+  __syncthreads();
+  const int nseg = 1 + MMAE_MAX_TASKS;
+  for (int i = threadIdx.x; i < nseg * d4; i += blockDim.x) {
+    float4 a = dbred[i];
+#pragma unroll
+    for (int r = 1; r < 4; ++r) {
+      const float4 o = dbred[r * nseg * d4 + i];
+      a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+    }
+    reinterpret_cast<float4*>(partial + int64_t(blockIdx.x) * nseg * Dd)[i] = a;
   }
 }
 
@@ -301,6 +362,61 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(TokT* __restrict__ tok,
       *reinterpret_cast<uint2*>(tp) = o;
     }
   }
+}
+
+// bf16 token rows <-> fp32 image through a shared-memory tile of one patch row (b, ph): both sides move whole lines
+// (token rows with 16-byte accesses, image rows W pixels wide), instead of 64-byte image-row pieces per warp.
+// smem: [nw][cols + 16] bf16 (the 32-byte row pad spreads the patch columns over the banks), cols = C * P * P.
+template <bool TO_IMAGE>
+__global__ void __launch_bounds__(256) unpatchify_tile_kernel(bf16* __restrict__ tok, int64_t ld_tok, float* __restrict__ img,
+                                                              int B, int C, int nh, int nw, int P) {
+  pdl_prologue();
+  extern __shared__ __align__(16) uint8_t up_smem[];
+  bf16* tile = reinterpret_cast<bf16*>(up_smem);
+  const int W = nw * P, H = nh * P, cols = C * P * P, pitch = cols + 16;
+  const int b = blockIdx.x / nh, ph = blockIdx.x % nh;
+  bf16* trow0 = tok + (int64_t(b) * nh * nw + int64_t(ph) * nw) * ld_tok;
+  const int vec_per_row = cols / 8;
+  if constexpr (TO_IMAGE) {
+    for (int idx = threadIdx.x; idx < nw * vec_per_row; idx += blockDim.x) {
+      const int pw = idx / vec_per_row, v = idx % vec_per_row;
+      *reinterpret_cast<uint4*>(tile + pw * pitch + v * 8) = ld_stream_16(trow0 + int64_t(pw) * ld_tok + v * 8);
+    }
+    __syncthreads();
+  }
+  // image side: rows (c, py), 4 consecutive pixels per thread
+  const int quads = W / 4, rows = C * P;
+  for (int idx = threadIdx.x; idx < rows * quads; idx += blockDim.x) {
+    const int r = idx / quads, x = (idx % quads) * 4;
+    const int c = r / P, py = r % P, pw = x / P, px = x % P;
+    float* ip = img + ((int64_t(b) * C + c) * H + ph * P + py) * W + x;
+    bf16* tp = tile + pw * pitch + (c * P + py) * P + px;
+    if constexpr (TO_IMAGE) {
+      const uint2 u = *reinterpret_cast<const uint2*>(tp);
+      const float2 a = unpack_bf16x2(u.x), b2 = unpack_bf16x2(u.y);
+      *reinterpret_cast<float4*>(ip) = make_float4(a.x, a.y, b2.x, b2.y);
+    } else {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ip));
+      uint2 o;
+      o.x = pack_bf16x2(v.x, v.y);
+      o.y = pack_bf16x2(v.z, v.w);
+      *reinterpret_cast<uint2*>(tp) = o;
+    }
+  }
+  if constexpr (!TO_IMAGE) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nw * vec_per_row; idx += blockDim.x) {
+      const int pw = idx / vec_per_row, v = idx % vec_per_row;
+      *reinterpret_cast<uint4*>(trow0 + int64_t(pw) * ld_tok + v * 8) = *reinterpret_cast<const uint4*>(tile + pw * pitch + v * 8);
+    }
+  }
+}
+
+// shared-memory tile variant usable: 16-byte token vectors, 4-pixel quads inside a patch row, tile within the opt-in limit
+static bool unpatchify_tile_ok(int64_t ld_tok, int C, int nw, int P, const void* tok, size_t* smem) {
+  const int cols = C * P * P;
+  *smem = size_t(nw) * (cols + 16) * sizeof(bf16);
+  return cols % 8 == 0 && ld_tok % 8 == 0 && P % 4 == 0 && (reinterpret_cast<uintptr_t>(tok) & 15) == 0 && *smem <= 200 * 1024;
 }
 
 __global__ void cast2d_kernel(const float* __restrict__ src, int64_t ld_src, bf16* __restrict__ dst, int64_t ld_dst,
@@ -367,7 +483,7 @@ int launch_semseg_emb_bwd(const bf16* dA, int64_t ld_dA, const int64_t* labels, 
 int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float* mask_token, const TaskEmbPtrs& task_emb,
                      const float* pos, float* queries, float* context, cudaStream_t st) {
   const int rows = ix.batch * ix.num_queries + ix.batch * (ix.num_visible + ix.num_global);
-  launch_k(dec_build_kernel, rows, 64, 0, st, ctx, ix, mask_token, task_emb, pos, queries, context);
+  launch_k(dec_build_kernel, ceil_div(rows, DBF_ROWS), 256, 0, st, ctx, ix, mask_token, task_emb, pos, queries, context);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -376,10 +492,23 @@ int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float
 int launch_dec_build_bwd(const float* dqueries, const float* dcontext, const mmae_decoder_index& ix, float* dctx,
                          float* dmask_token, const TaskEmbGradPtrs& dtask_emb, cudaStream_t st) {
   const int rows = ix.batch * ix.num_queries + ix.batch * (ix.num_visible + ix.num_global);
-  launch_k(dec_build_bwd_kernel, ceil_div(rows, DB_ROWS), 256, 0, st, dqueries, dcontext, ix, dctx, dmask_token, dtask_emb);
+  const int blocks = ceil_div(rows, DB_ROWS);
+  constexpr int NSEG = 1 + MMAE_MAX_TASKS;
+  float* partial = colred_scratch(size_t(blocks) * NSEG * ix.dim, st);
+  if (!partial) return MMAE_ERR_CUDA;
+  const size_t smem = size_t(4) * NSEG * ix.dim * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    MMAE_CUDA_OK(cudaFuncSetAttribute(dec_build_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * NSEG * 1024 * 4));
+    configured = true;
+  }
+  launch_k(dec_build_bwd_kernel, blocks, 256, smem, st, dqueries, dcontext, ix, dctx, partial);
   count_launch();
   MMAE_LAUNCH_OK();
-  return MMAE_OK;
+  ColredDst dst;
+  dst.p[0] = dmask_token;
+  for (int t = 0; t < MMAE_MAX_TASKS; ++t) dst.p[1 + t] = t < ix.num_tasks ? dtask_emb.p[t] : nullptr;
+  return colred_finalize_n(partial, blocks, NSEG * ix.dim, ix.dim, dst, NSEG, st);
 }
 
 int launch_cast2d(const float* src, int64_t ld_src, bf16* dst, int64_t ld_dst, int rows, int cols, cudaStream_t st) {
@@ -408,7 +537,18 @@ extern "C" int mmae_unpatchify_bf16(const void* tokens_bf16, int64_t ld_tok, flo
                                     int P, void* stream) {
   MMAE_CHECK(tokens_bf16 && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG, "mmae_unpatchify_bf16: bad args");
   MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_unpatchify_bf16: P and ld must be multiples of 4");
-  launch_k(unpatchify_kernel<true, const bf16>, B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const bf16*>(tokens_bf16), ld_tok, image, B, C, nh, nw, P);
+  size_t smem = 0;
+  if (unpatchify_tile_ok(ld_tok, C, nw, P, tokens_bf16, &smem)) {
+    static size_t configured = 0;
+    if (smem > configured) {
+      MMAE_CUDA_OK(cudaFuncSetAttribute(unpatchify_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    launch_k(unpatchify_tile_kernel<true>, B * nh, 256, smem, reinterpret_cast<cudaStream_t>(stream),
+             reinterpret_cast<bf16*>(const_cast<void*>(tokens_bf16)), ld_tok, image, B, C, nh, nw, P);
+  } else {
+    launch_k(unpatchify_kernel<true, const bf16>, B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const bf16*>(tokens_bf16), ld_tok, image, B, C, nh, nw, P);
+  }
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -419,7 +559,18 @@ extern "C" int mmae_patchify_bf16(const float* image, void* tokens_bf16, int64_t
   MMAE_CHECK(tokens_bf16 && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG,
              "mmae_patchify_bf16: bad args");
   MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_patchify_bf16: P and ld must be multiples of 4");
-  launch_k(unpatchify_kernel<false, bf16>, B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<bf16*>(tokens_bf16), ld_tok, const_cast<float*>(image), B, C, nh, nw, P);
+  size_t smem = 0;
+  if (unpatchify_tile_ok(ld_tok, C, nw, P, tokens_bf16, &smem)) {
+    static size_t configured = 0;
+    if (smem > configured) {
+      MMAE_CUDA_OK(cudaFuncSetAttribute(unpatchify_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    launch_k(unpatchify_tile_kernel<false>, B * nh, 256, smem, reinterpret_cast<cudaStream_t>(stream),
+             reinterpret_cast<bf16*>(tokens_bf16), ld_tok, const_cast<float*>(image), B, C, nh, nw, P);
+  } else {
+    launch_k(unpatchify_kernel<false, bf16>, B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<bf16*>(tokens_bf16), ld_tok, const_cast<float*>(image), B, C, nh, nw, P);
+  }
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

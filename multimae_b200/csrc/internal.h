@@ -24,6 +24,12 @@ void count_launch();
 float* colred_scratch(size_t floats, cudaStream_t st);   // nullptr + last error if it cannot be provided
 int colred_finalize(const float* partial, int Y, int ld, int seg, float* dst0, float* dst1, float* dst2, cudaStream_t st);
 
+// same with up to 9 destinations of `seg` columns each (null entries are skipped)
+struct ColredDst {
+  float* p[9];
+};
+int colred_finalize_n(const float* partial, int Y, int ld, int seg, const ColredDst& dst, int nseg, cudaStream_t st);
+
 // bf16 weight mirror registry (runtime.cu): the bf16 twin of a registered fp32 parameter buffer, or nullptr
 const bf16* mirror_lookup(const float* w);
 

@@ -136,20 +136,35 @@ __global__ void __launch_bounds__(LOSS_THREADS) ce_loss_kernel(const float* __re
         for (int c = 0; c < C; ++c) dlogits[int64_t(b) * C * HW + c * HW + off] = 0.f;
       continue;
     }
-    float m = -INFINITY;
-    for (int c = 0; c < C; ++c) m = fmaxf(m, lb[c * HW + off]);
-    float s = 0.f, sum_logits = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float v = lb[c * HW + off];
-      s += __expf(v - m);
-      sum_logits += v;
+    // one pass for max, sum of exponentials and sum of logits: 8 independent loads in flight, running maximum with
+    // rescaling (the three-pass version walked the C-strided column three times with one load in flight each)
+    float m = -INFINITY, s = 0.f, sum_logits = 0.f;
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = c0 + i < C ? __ldg(lb + int64_t(c0 + i) * HW + off) : -INFINITY;
+      float cm = v[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) cm = fmaxf(cm, v[i]);
+      const float m_new = fmaxf(m, cm);
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (c0 + i < C) {
+          part += __expf(v[i] - m_new);
+          sum_logits += v[i];
+        }
+      }
+      s = s * __expf(m - m_new) + part;
+      m = m_new;
     }
     const float lse = m + logf(s);
     const int64_t tcls = target[int64_t(b) * HW + off];
     if constexpr (BWD) {
       const float inv = 1.0f / s;
+#pragma unroll 8
       for (int c = 0; c < C; ++c) {
-        const float p = __expf(lb[c * HW + off] - m) * inv;
+        const float p = __expf(__ldg(lb + int64_t(c) * HW + off) - m) * inv;
         const float y = (c == tcls ? 1.f - smoothing : 0.f) + smoothing / C;
         dlogits[int64_t(b) * C * HW + c * HW + off] = (p - y) * gscale;
       }

@@ -217,3 +217,20 @@ def test_attention_forward_backward(dev, KN, tc, case):
     assert rel_l2(dq, qf.grad.transpose(1, 2).reshape(B * Nq, D)) < 1e-2
     assert rel_l2(dk, kf.grad.transpose(1, 2).reshape(B * Nk, D)) < 1e-2
     assert rel_l2(dv, vf.grad.transpose(1, 2).reshape(B * Nk, D)) < 1e-2
+
+
+@pytest.mark.parametrize("case", [(3, 3, 14, 14, 16), (2, 1, 14, 14, 16), (2, 133, 14, 14, 4), (2, 5, 3, 7, 8), (1, 2, 2, 3, 4)])
+def test_unpatchify_and_patchify_bf16(dev, case):
+    """tokens [B*nh*nw, C*P*P] (c, py, px) <-> image [B, C, nh*P, nw*P] (output_adapters.py:277-280), strided token rows."""
+    from multimae_b200 import _lib as L
+    B, C, nh, nw, P = case
+    cols = C * P * P
+    tok = torch.full((B * nh * nw, cols + 8), 3.0, device=dev, dtype=torch.bfloat16)
+    tok[:, :cols] = _bf16(dev, B * nh * nw, cols)
+    img = torch.empty(B, C, nh * P, nw * P, device=dev)
+    L.check(L.lib().mmae_unpatchify_bf16(tok.data_ptr(), tok.stride(0), img.data_ptr(), B, C, nh, nw, P, L.current_stream()))
+    ref = tok[:, :cols].float().reshape(B, nh, nw, C, P, P).permute(0, 3, 1, 4, 2, 5).reshape(B, C, nh * P, nw * P)
+    assert torch.equal(img, ref)
+    back = torch.full_like(tok, 5.0)
+    L.check(L.lib().mmae_patchify_bf16(img.data_ptr(), back.data_ptr(), back.stride(0), B, C, nh, nw, P, L.current_stream()))
+    assert torch.equal(back[:, :cols], tok[:, :cols]) and bool((back[:, cols:] == 5).all())
