@@ -328,6 +328,16 @@ int mmae_unpatchify_bf16(const void* tokens_bf16, int64_t ld_tok, float* image, 
 int mmae_patchify_bf16(const float* image, void* tokens_bf16, int64_t ld_tok, int B, int C, int nh, int nw, int P,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Truncated depth standardisation — the caller-side step of train_one_epoch, run_pretraining_multimae.py:487-492
+ * (torch.sort of every depth map, slice [int(0.1 n), int(0.9 n)), mean / unbiased var of the slice, standardise
+ * the whole map).  depth, out: [B, n] fp32 (out may alias depth); lo / hi: the slice bounds as the reference
+ * computes them on the host; eps: 1e-6 in the reference; stats (optional): [B, 2] = {mean, var} of the kept
+ * values.  One launch: radix select of the two order statistics instead of a sort.
+ * ---------------------------------------------------------------------------------------------- */
+int mmae_standardize_depth(const float* depth, float* out, int B, int n, int lo, int hi, float eps, float* stats,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

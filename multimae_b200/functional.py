@@ -431,6 +431,29 @@ def sample_masks(shares, noise_task, noise_all, tokens_per_task, num_encoded):
     return masks, ids_keep, ids_restore
 
 
+def standardize_depth(depth, lo_frac=0.1, hi_frac=0.9, eps=1e-6, out=None, return_stats=False):
+    """Truncated depth standardisation of train_one_epoch (run_pretraining_multimae.py:487-492) in one kernel launch.
+
+    depth [B, ...] fp32 on the device -> (depth - mean_b) / sqrt(var_b + eps), mean_b / var_b (unbiased) taken over the
+    values of sample b whose rank lies in [int(lo_frac n), int(hi_frac n)) — the reference's sort + slice.  `out` may be
+    `depth` itself.  With return_stats also returns the [B, 2] tensor of (mean, var)."""
+    _require_cuda(depth, "standardize_depth")
+    if depth.dtype != torch.float32:
+        raise TypeError("standardize_depth: fp32 depth maps expected, got %s" % depth.dtype)
+    x = depth.contiguous()
+    B = x.shape[0]
+    n = x[0].numel()
+    lo, hi = int(lo_frac * n), int(hi_frac * n)           # the reference's own host-side expressions (:490)
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+        raise ValueError("standardize_depth: `out` must be a contiguous fp32 tensor of the input's shape on its device")
+    stats = torch.empty((B, 2), dtype=torch.float32, device=x.device) if return_stats else None
+    L.check(L.lib().mmae_standardize_depth(x.data_ptr(), out.data_ptr(), B, n, lo, hi, float(eps), L.ptr(stats),
+                                           L.current_stream()), "mmae_standardize_depth")
+    return (out, stats) if return_stats else out
+
+
 def grad_unscale_norm(flat, inv_scale=1.0, post_scale=1.0, inv_scale_tensor=None):
     """In-place flat *= inv_scale*post_scale; returns (norm tensor [1], out2 = [sum_sq, found_inf])."""
     _require_cuda(flat, "grad_unscale_norm")

@@ -14,8 +14,11 @@ from . import _lib as L
 
 class TrainStep:
     def __init__(self, model, loss_fns, optimizer, scaler, num_encoded_tokens=98, alphas=1.0, sample_tasks_uniformly=False,
-                 loss_sources=None):
+                 loss_sources=None, standardize_depth=False):
         self.model, self.loss_fns, self.opt, self.scaler = model, loss_fns, optimizer, scaler
+        # truncated depth standardisation of the 'depth' entry before it is used as input AND as loss target
+        # (run_pretraining_multimae.py:487-492; --standardize_depth): one radix-select kernel instead of a full sort
+        self.standardize_depth = standardize_depth
         self._pdl_default = os.environ.get("MMAE_PDL", "1") != "0"
         self.num_encoded_tokens, self.alphas, self.uniform = num_encoded_tokens, alphas, sample_tasks_uniformly
         self.loss_sources = loss_sources or {}          # output key -> input key holding its target / mask
@@ -25,6 +28,10 @@ class TrainStep:
 
     # the eager step: exactly the body of train_one_epoch between the H2D copy and the optimizer step
     def _step(self, x):
+        if self.standardize_depth and "depth" in x:
+            from .functional import standardize_depth
+            x = dict(x)
+            x["depth"] = standardize_depth(x["depth"])
         preds, masks = self.model(x, num_encoded_tokens=self.num_encoded_tokens, alphas=self.alphas,
                                   sample_tasks_uniformly=self.uniform)
         task_losses = {}

@@ -341,6 +341,16 @@ def step_losses(p, x, cfg: OracleConfig, task_masks: Dict[str, torch.Tensor], id
     return losses, preds
 
 
+def standardize_depth(depth: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """Truncated depth standardisation, run_pretraining_multimae.py:487-492: per sample, sort the flattened map, drop the
+    bottom and top 10 % of the values, standardise the whole map with the mean / unbiased variance of the rest."""
+    flat = depth.reshape(depth.shape[0], -1)
+    trunc = torch.sort(flat, dim=1)[0]                                       # :489
+    trunc = trunc[:, int(0.1 * trunc.shape[1]): int(0.9 * trunc.shape[1])]   # :490
+    shape = (-1,) + (1,) * (depth.dim() - 1)
+    return (depth - trunc.mean(dim=1).reshape(shape)) / torch.sqrt(trunc.var(dim=1).reshape(shape) + eps)   # :491
+
+
 def grad_norm(grads) -> torch.Tensor:
     """utils/native_scaler.py:49-62 — L2 norm of per-tensor L2 norms."""
     return torch.norm(torch.stack([g.detach().norm(2) for g in grads if g is not None]), 2)

@@ -12,6 +12,10 @@ Fixtures (all fp32, CPU, torch.save of plain dicts of tensors):
   interp.pt    : RGB-only model built with the default 224 pos-emb grid run on 32x32 inputs (bicubic/bilinear resize)
   cuda_*.pt    : shapes the CUDA path supports (head_dim 64/32); weights come from tests/helpers.formula_fill_ (not
                  stored) and gradients are stored as digests (norm + strided samples)
+  depth_std.pt : truncated depth standardisation; the reference has it inline in train_one_epoch
+                 (run_pretraining_multimae.py:487-492), so the statements are cut out of the reference source and executed
+
+    python tests/golden/make_golden.py [fixture.pt ...]     (no names: regenerate everything)
 """
 import math
 import os
@@ -141,8 +145,41 @@ def record_model(R, name, in_domains, B, size, num_encoded, seed, formula=False,
     print("wrote", name, {k: round(float(v), 6) for k, v in losses.items()}, "grad_norm", float(gnorm))
 
 
+def record_depth_standardize(name):
+    """Executes the reference's OWN statements (the body of `if standardize_depth and 'depth' in tasks_dict:` in
+    train_one_epoch, run_pretraining_multimae.py:487-492) on synthetic depth maps and records input and result."""
+    import textwrap
+    from einops import rearrange
+    src = open(os.path.join(REF, "run_pretraining_multimae.py")).read().splitlines()
+    start = next(i for i, ln in enumerate(src) if "if standardize_depth and 'depth' in tasks_dict" in ln)
+    body = []
+    for ln in src[start + 1:]:
+        if ln.strip() and (len(ln) - len(ln.lstrip())) <= (len(src[start]) - len(src[start].lstrip())):
+            break
+        body.append(ln)
+    code = textwrap.dedent("\n".join(body))
+    assert "torch.sort" in code and "trunc_depth.var" in code, code
+    g = torch.Generator().manual_seed(31)
+    depth = torch.randn(4, 1, 24, 24, generator=g)
+    depth[1] = depth[1].abs() * 3 + 0.5                                   # metric-depth-like: positive, skewed
+    depth[2] = torch.round(depth[2] * 2) / 2                              # heavy ties, also across the 10 % / 90 % cuts
+    depth[3, :, :12] = 7.25                                               # one value covering half of the map
+    ns = {"torch": torch, "rearrange": rearrange, "tasks_dict": {"depth": depth.clone()}}
+    exec(code, ns)
+    torch.save({"depth": depth, "standardized": ns["tasks_dict"]["depth"].clone()},
+               os.path.join(HERE, name))
+    print("wrote", name, "(executed %d reference source lines)" % len(code.splitlines()))
+
+
 if __name__ == "__main__":
+    only = set(sys.argv[1:])
+    if only == {"depth_std.pt"}:
+        if not os.path.isdir(REF):
+            raise SystemExit("reference tree %s not present" % REF)
+        record_depth_standardize("depth_std.pt")
+        raise SystemExit(0)
     R = import_reference()
+    record_depth_standardize("depth_std.pt")
     record_sampler(R, "sampler_small.pt", B=16, tokens_per_task=[16, 16, 16], num_encoded=12, alphas=1.0, seed=3)
     record_sampler(R, "sampler_cfg2.pt", B=8, tokens_per_task=[196, 196, 196], num_encoded=98, alphas=1.0, seed=4)
     record_sampler(R, "sampler_alpha.pt", B=8, tokens_per_task=[196, 196], num_encoded=98, alphas=[0.5, 2.0], seed=5)

@@ -234,3 +234,47 @@ def test_unpatchify_and_patchify_bf16(dev, case):
     back = torch.full_like(tok, 5.0)
     L.check(L.lib().mmae_patchify_bf16(img.data_ptr(), back.data_ptr(), back.stride(0), B, C, nh, nw, P, L.current_stream()))
     assert torch.equal(back[:, :cols], tok[:, :cols]) and bool((back[:, cols:] == 5).all())
+
+
+def _depth_cases():
+    g = torch.Generator().manual_seed(17)
+    a = torch.randn(4, 1, 224, 224, generator=g)
+    a[1] = a[1].abs() * 3 + 0.5                      # metric-depth-like: positive, skewed, few exponent bins
+    a[2] = torch.round(a[2] * 4) / 4                 # heavy ties, also across both cut points
+    a[3, :, :120] = -2.5                             # one value covering more than half of the map (L == H side cases)
+    yield "224", a
+    yield "448 (global-memory passes)", torch.randn(2, 1, 448, 448, generator=g) * 5 - 1
+    yield "odd length (scalar path)", torch.randn(3, 1, 13, 77, generator=g)
+    c = torch.full((2, 1, 32, 32), 0.75)
+    c[0, 0, 0, :20] = torch.randn(20, generator=g)    # both cut values fall into the constant run (L == H, variance 0)
+    yield "mostly constant", c
+    yield "tiny", torch.tensor([[3.0, 1.0, 2.0, 2.0, 5.0, -1.0, 0.0, -0.0, 4.0, 2.0]]).reshape(1, 1, 2, 5)
+
+
+def test_standardize_depth_against_oracle_and_golden(dev, golden_dir):
+    """mmae_standardize_depth (radix select of the two cut values) against the sort-based oracle
+    (run_pretraining_multimae.py:487-492): fp32, differences only from the summation order -> 2e-5 absolute on O(1)
+    outputs, 1e-5 relative on mean / variance; in-place operation; fixture recorded from the reference's own lines."""
+    import os
+    from multimae_b200 import functional as Fn
+    from oracle import multimae_oracle as O
+    fx = torch.load(os.path.join(golden_dir, "depth_std.pt"), map_location="cpu", weights_only=False)
+    got = Fn.standardize_depth(fx["depth"].to(dev))
+    assert got.shape == fx["standardized"].shape
+    assert float((got.cpu() - fx["standardized"]).abs().max()) < 2e-5
+    for name, x in _depth_cases():
+        ref = O.standardize_depth(x)
+        flat = x.reshape(x.shape[0], -1)
+        n = flat.shape[1]
+        trunc = torch.sort(flat, dim=1)[0][:, int(0.1 * n):int(0.9 * n)]
+        xd = x.to(dev)
+        out, stats = Fn.standardize_depth(xd, return_stats=True)
+        assert out.shape == x.shape and torch.equal(xd.cpu(), x), name           # input untouched
+        torch.testing.assert_close(stats[:, 0].cpu(), trunc.mean(1), rtol=1e-5, atol=1e-6, msg=name)
+        torch.testing.assert_close(stats[:, 1].cpu(), trunc.var(1), rtol=1e-5, atol=1e-7, msg=name)
+        scale = max(1.0, float(ref.abs().max()))
+        assert float((out.cpu() - ref).abs().max()) < 2e-5 * scale, (name, float((out.cpu() - ref).abs().max()))
+        same = Fn.standardize_depth(xd, out=xd)                                   # in place
+        assert same.data_ptr() == xd.data_ptr() and torch.equal(same, out), name
+    with pytest.raises(TypeError):
+        Fn.standardize_depth(torch.zeros(2, 1, 8, 8, device=dev, dtype=torch.float16))

@@ -161,11 +161,12 @@ def test_model_against_golden_and_oracle(golden_dir, dev, name):
         assert abs(float(named[k].grad.float().norm()) - float(d["norm"])) < PER_TENSOR_TOL * max(float(d["norm"]), fair), k
 
 
-def test_full_size_model_against_oracle(dev):
-    """MultiMAE-B, rgb+depth+semseg, 224^2, 98 visible tokens (BASELINE config 2 at B=2) against the fp32 oracle."""
+def _full_model_case(dev, size, image_size, n_visible, B):
+    """One full-size step (forward, 4 losses, backward) of the CUDA path against the fp32 oracle on the same weights,
+    synthetic inputs (SURVEY.md §8d generator) and oracle-sampled masks."""
     from test_host_api import _build
-    B = 2
-    model = _build(("rgb", "depth", "semseg"), 768, 12, 12, 256, 2, 8, 224)
+    dim, depth, heads = (768, 12, 12) if size == "base" else (1024, 24, 16)     # multimae/multimae.py:387-397, 405-415
+    model = _build(("rgb", "depth", "semseg"), dim, depth, heads, 256, 2, 8, image_size)
     torch.manual_seed(0)
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     g = torch.Generator().manual_seed(3)
@@ -174,10 +175,11 @@ def test_full_size_model_against_oracle(dev):
             if k.endswith(".bias") or k.endswith("mask_token"):
                 v.add_(torch.randn(v.shape, generator=g) * 0.05)
     model.load_state_dict(sd)
-    cfg = O.make_config()
-    x = O.synthetic_inputs(cfg, B, 224, seed=0)
-    shares, noises, noise_all = O.synthetic_mask_draws(cfg, B, 224, seed=1)
-    m, ids_keep, ids_restore = O.sample_masks(shares, noises, noise_all, 98)
+    cfg = O.make_config(size=size)
+    cfg.posemb_grid = image_size // 16
+    x = O.synthetic_inputs(cfg, B, image_size, seed=0)
+    shares, noises, noise_all = O.synthetic_mask_draws(cfg, B, image_size, seed=1)
+    m, ids_keep, ids_restore = O.sample_masks(shares, noises, noise_all, n_visible)
     tmask = {d.name: mm for d, mm in zip(cfg.in_domains, m)}
 
     p = {k: v.clone() for k, v in sd.items()}
@@ -191,10 +193,66 @@ def test_full_size_model_against_oracle(dev):
     triple = ({k: v.to(dev) for k, v in tmask.items()}, ids_keep.to(dev), ids_restore.to(dev))
     preds, masks, losses = _run_cuda_step(model, x, triple, dev)
     for k in o_preds:
+        assert preds[k].shape == o_preds[k].shape, k
         assert rel_l2(preds[k], o_preds[k]) < BF16_TOL, (k, rel_l2(preds[k], o_preds[k]))
         assert abs(float(losses[k]) - float(o_losses[k])) < BF16_TOL * abs(float(o_losses[k])), k
     named = dict(model.named_parameters())
     _check_grads({k: named[k].grad for k in train}, {k: v.grad for k, v in train.items()})
+
+
+def test_full_size_model_against_oracle(dev):
+    """MultiMAE-B, rgb+depth+semseg, 224^2, 98 visible tokens (BASELINE config 2 at B=2) against the fp32 oracle."""
+    _full_model_case(dev, "base", 224, 98, B=2)
+
+
+def test_large_model_against_oracle(dev):
+    """MultiMAE-L (24 layers, d=1024, 16 heads), rgb+depth+semseg, 224^2, 98 visible tokens: BASELINE config 4 at B=1."""
+    _full_model_case(dev, "large", 224, 98, B=1)
+
+
+def test_448_model_against_oracle(dev):
+    """MultiMAE-B at 448^2: 3 x 784 patches, 392 visible tokens (393-token encoder sequence, 784-query decoders):
+    BASELINE config 5 at B=1."""
+    _full_model_case(dev, "base", 448, 392, B=1)
+
+
+def test_multivit_encoder_against_oracle(dev):
+    """MultiViT (multimae/multimae.py:419-502): no masking, every token of every given modality encoded; encoder tokens of
+    the last layer and of every layer (return_all_layers) against the oracle run with ids_keep = all tokens."""
+    from multimae_b200.input_adapters import PatchedInputAdapter
+    from multimae_b200.multimae import multivit_base
+    B, S = 2, 224
+    ins = {"rgb": PatchedInputAdapter(num_channels=3, stride_level=1, patch_size_full=16, image_size=S),
+           "depth": PatchedInputAdapter(num_channels=1, stride_level=1, patch_size_full=16, image_size=S)}
+    torch.manual_seed(0)
+    model = multivit_base(ins, None)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        for k, v in sd.items():
+            if k.endswith(".bias"):
+                v.add_(torch.randn(v.shape, generator=g) * 0.05)
+    model.load_state_dict(sd)
+    cfg = O.make_config(in_domains=("rgb", "depth"), out_domains=[], extra_norm_pix=False)
+    x = O.synthetic_inputs(cfg, B, S, seed=0)
+    n_tok = 2 * (S // 16) ** 2
+    ids = torch.arange(n_tok).unsqueeze(0).expand(B, -1).contiguous()
+    p = {k: v.clone() for k, v in sd.items()}
+    _, o_tokens = O.forward(p, x, cfg, ids, ids)
+
+    model = model.to(dev).eval()
+    xd = {k: v.to(dev) for k, v in x.items()}
+    with torch.no_grad():
+        got = model(xd)
+        layers = model(xd, return_all_layers=True)
+    assert got.shape == (B, n_tok + 1, 768) and len(layers) == 12
+    assert rel_l2(got, o_tokens) < BF16_TOL, rel_l2(got, o_tokens)
+    assert rel_l2(layers[-1], o_tokens) < BF16_TOL
+    # a Tensor input is taken as RGB (multimae/multimae.py:441-442)
+    model_rgb = multivit_base({"rgb": PatchedInputAdapter(num_channels=3, stride_level=1, patch_size_full=16, image_size=S)},
+                              None).to(dev).eval()
+    with torch.no_grad():
+        assert model_rgb(xd["rgb"]).shape == (B, (S // 16) ** 2 + 1, 768)
 
 
 def test_losses_against_oracle(dev):

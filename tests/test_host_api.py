@@ -100,6 +100,9 @@ def test_no_cpu_fallback():
         model(x, num_encoded_tokens=12)
     with pytest.raises(L.MmaeError):
         MaskedMSELoss()(torch.randn(1, 3, 32, 32), torch.randn(1, 3, 32, 32))
+    from multimae_b200.functional import standardize_depth
+    with pytest.raises(L.MmaeError):
+        standardize_depth(torch.randn(2, 1, 16, 16))
 
 
 def test_grad_arena_layout():
