@@ -26,6 +26,19 @@ sys.path.insert(0, ROOT)
 ALG_FLOP_PER_SAMPLE = 65.41e9        # fwd+bwd, algorithmic
 METRIC = "MultiMAE-B pretrain samples/sec @ bs=128/GPU"
 WORKLOAD = "MultiMAE-B rgb+depth+semseg(+norm_rgb) 224x224, 98 visible tokens, bs=128/GPU, fwd+4 losses+bwd+allreduce+AdamW"
+# --workload: the default is the configuration BASELINE.json's metric is quoted on (configs[1] / [2]); configs[3] and [4]
+# are its per-GPU stress cases (algorithmic FLOP per sample: SURVEY.md §8d table)
+WORKLOADS = {
+    "cfg2": dict(size="base", image=224, visible=98, batch=128, flop=ALG_FLOP_PER_SAMPLE, metric=METRIC, name=WORKLOAD),
+    "cfg4": dict(size="large", image=224, visible=98, batch=64, flop=196.40e9,
+                 metric="MultiMAE-L pretrain samples/sec @ bs=64/GPU",
+                 name="MultiMAE-L (24 layers, d=1024, 16 heads) rgb+depth+semseg(+norm_rgb) 224x224, 98 visible tokens, "
+                      "bs=64/GPU, fwd+4 losses+bwd+allreduce+AdamW"),
+    "cfg5": dict(size="base", image=448, visible=392, batch=32, flop=287.0e9,
+                 metric="MultiMAE-B 448x448 pretrain samples/sec @ bs=32/GPU",
+                 name="MultiMAE-B rgb+depth+semseg(+norm_rgb) 448x448 (784 patches/modality, 392 visible tokens), bs=32/GPU, "
+                      "fwd+4 losses+bwd+allreduce+AdamW"),
+}
 
 
 def peaks():
@@ -79,22 +92,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model_and_losses(device):
+def build_model_and_losses(device, size="base", image=224):
     from multimae_b200.criterion import MaskedCrossEntropyLoss, MaskedL1Loss, MaskedMSELoss
     from multimae_b200.input_adapters import PatchedInputAdapter, SemSegInputAdapter
-    from multimae_b200.multimae import pretrain_multimae_base
+    from multimae_b200.multimae import pretrain_multimae_base, pretrain_multimae_large
     from multimae_b200.output_adapters import SpatialOutputAdapter
     doms = ["rgb", "depth", "semseg"]
-    ins = {"rgb": PatchedInputAdapter(num_channels=3, stride_level=1, patch_size_full=16),
-           "depth": PatchedInputAdapter(num_channels=1, stride_level=1, patch_size_full=16),
+    # adapters are built with image_size = --input_size like get_model does (run_pretraining_multimae.py:243-283)
+    ins = {"rgb": PatchedInputAdapter(num_channels=3, stride_level=1, patch_size_full=16, image_size=image),
+           "depth": PatchedInputAdapter(num_channels=1, stride_level=1, patch_size_full=16, image_size=image),
            "semseg": SemSegInputAdapter(num_classes=133, dim_class_emb=64, interpolate_class_emb=False, stride_level=4,
-                                        patch_size_full=16)}
+                                        patch_size_full=16, image_size=image)}
     outs = {}
     for key, (ch, stride, task) in {"rgb": (3, 1, "rgb"), "depth": (1, 1, "depth"), "semseg": (133, 4, "semseg"),
                                     "norm_rgb": (3, 1, "rgb")}.items():
         outs[key] = SpatialOutputAdapter(num_channels=ch, stride_level=stride, patch_size_full=16, dim_tokens=256, depth=2,
-                                         num_heads=8, use_task_queries=True, task=task, context_tasks=doms, use_xattn=True)
-    model = pretrain_multimae_base(ins, outs, num_global_tokens=1, drop_path_rate=0.0).to(device).train()
+                                         num_heads=8, use_task_queries=True, task=task, context_tasks=doms, use_xattn=True,
+                                         image_size=image)
+    factory = pretrain_multimae_base if size == "base" else pretrain_multimae_large
+    model = factory(ins, outs, num_global_tokens=1, drop_path_rate=0.0).to(device).train()
     losses = {"rgb": MaskedMSELoss(16, 1), "depth": MaskedL1Loss(16, 1), "semseg": MaskedCrossEntropyLoss(16, 4),
               "norm_rgb": MaskedMSELoss(16, 1, norm_pix=True)}
     return model, losses
@@ -116,10 +132,10 @@ NCU_GEMM_TRAFFIC_NOTE = ("fc1 forward GEMM 12672x3072x768: 24.3 MB read (= the 2
                          "126 MB L2 when the kernel ends (algorithmic bytes per launch: 102.1 MB)")
 
 
-def synthetic_batch(B, seed, pin=False):
+def synthetic_batch(B, seed, pin=False, image=224):
     g = torch.Generator().manual_seed(seed)
-    x = {"rgb": torch.randn(B, 3, 224, 224, generator=g), "depth": torch.randn(B, 1, 224, 224, generator=g),
-         "semseg": torch.randint(0, 133, (B, 56, 56), generator=g)}
+    x = {"rgb": torch.randn(B, 3, image, image, generator=g), "depth": torch.randn(B, 1, image, image, generator=g),
+         "semseg": torch.randint(0, 133, (B, image // 4, image // 4), generator=g)}
     return {k: v.pin_memory() for k, v in x.items()} if pin else x
 
 
@@ -135,21 +151,23 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     torch.manual_seed(0)                                   # identical init on every rank
-    model, loss_fns = build_model_and_losses(device)
+    wl = WORKLOADS[args.workload]
+    model, loss_fns = build_model_and_losses(device, wl["size"], wl["image"])
     broadcast_parameters(model)
-    opt = FlatAdamW(model, lr=1e-4 * 128 * world / 256, betas=(0.9, 0.95), weight_decay=0.05)
+    opt = FlatAdamW(model, lr=1e-4 * args.batch * world / 256, betas=(0.9, 0.95), weight_decay=0.05)
     # bf16 operands keep fp32's exponent range: no loss scaling needed (the reference's GradScaler exists for fp16)
     scaler = NativeScalerWithGradNormCount(enabled=False).attach_arena(model.grad_arena())
     if world > 1:
         attach_data_parallel(model, scaler)
     torch.manual_seed(1234 + rank)                         # per-rank data / masks (run_pretraining_multimae.py:300)
     B = args.batch
-    host = [synthetic_batch(B, 100 * rank + i, pin=True) for i in range(2)]     # 2 x 106 MB: > L2 together
+    host = [synthetic_batch(B, 100 * rank + i, pin=True, image=wl["image"]) for i in range(2)]   # 2 x 106 MB: > L2 together
     resident = [{k: v.to(device) for k, v in hb.items()} for hb in host]
     lib = L.lib()
 
     from multimae_b200.train_step import TrainStep
-    stepper = TrainStep(model, loss_fns, opt, scaler, num_encoded_tokens=98, alphas=1.0, loss_sources={"norm_rgb": "rgb"})
+    stepper = TrainStep(model, loss_fns, opt, scaler, num_encoded_tokens=wl["visible"], alphas=1.0,
+                        loss_sources={"norm_rgb": "rgb"}, standardize_depth=bool(args.standardize_depth))
     mode = "eager"
     if (args.graph and world == 1) or args.graph >= 2:
         try:
@@ -321,10 +339,11 @@ def run_ours(args, rank, world, local_rank):
     value = args.batch * world / (ms_step * 1e-3)
     e2e_value = args.batch * world / (ms_e2e / args.steps * 1e-3)
     out = {
-        "metric": METRIC, "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "metric": wl["metric"], "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": args.batch * world, "per_gpu_batch": args.batch,
+        "config": {"workload": wl["name"] + (" + truncated depth standardisation" if args.standardize_depth else ""),
+                   "global_batch": args.batch * world, "per_gpu_batch": args.batch,
                    "parallelism": "dp%d" % world,
                    "l2": "two alternating input batches (212 MB) and a >9 GB per-step activation working set exceed the 126 MB L2",
                    "loss_scaling": "none (bf16)",
@@ -340,11 +359,14 @@ def run_ours(args, rank, world, local_rank):
                      "traffic_note": NCU_GEMM_TRAFFIC_NOTE, "peak_source": peak_src + " (sustained bf16)",
                      "launches_per_step": int(n_g.value), "kernel_ms_per_step": round(ms_g.value, 3),
                      "kernel_share_of_step": round(ms_g.value / ms_step, 3),
-                     "step_model_flops_frac": round(value / world * ALG_FLOP_PER_SAMPLE / (peak_tf * 1e12), 4)},
+                     "step_model_flops_frac": round(value / world * wl["flop"] / (peak_tf * 1e12), 4)},
     }
-    if world == 1:
+    if args.workload != "cfg2":
+        # the committed ncu traffic figure belongs to the cfg2 fc1 GEMM shape
+        out["roofline"]["traffic"], out["roofline"]["traffic_note"] = None, "no ncu capture for this workload's GEMM shapes"
+    if world == 1 and args.cpu_baseline:
         _note("GPU legs done (%.1f samples/s); timing the CPU baseline sample" % value)
-        out["cpu_baseline"] = cpu_baseline_bounded()
+        out["cpu_baseline"] = cpu_baseline_bounded(workload=args.workload)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -353,17 +375,19 @@ def run_ours(args, rank, world, local_rank):
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (oracle/multimae_oracle.py) on the host cores — test infrastructure timed as the baseline
 # ----------------------------------------------------------------------------------------------------------------------
-def _cpu_steps(batch, steps, warmup, threads=None):
+def _cpu_steps(batch, steps, warmup, threads=None, workload="cfg2"):
     from oracle import multimae_oracle as O
+    wl = WORKLOADS[workload]
     torch.set_num_threads(threads or (os.cpu_count() or 1))
-    cfg = O.make_config()
+    cfg = O.make_config(size=wl["size"])
+    cfg.posemb_grid = wl["image"] // 16
     p = O.init_params(cfg, seed=0)
     train = O.trainable(p)
     for v in train.values():
         v.requires_grad_(True)
-    x = O.synthetic_inputs(cfg, batch, 224, seed=0)
-    shares, noises, noise_all = O.synthetic_mask_draws(cfg, batch, 224, seed=1)
-    m, ids_keep, ids_restore = O.sample_masks(shares, noises, noise_all, 98)
+    x = O.synthetic_inputs(cfg, batch, wl["image"], seed=0)
+    shares, noises, noise_all = O.synthetic_mask_draws(cfg, batch, wl["image"], seed=1)
+    m, ids_keep, ids_restore = O.sample_masks(shares, noises, noise_all, wl["visible"])
     tmask = {d.name: mm for d, mm in zip(cfg.in_domains, m)}
     times = []
     for i in range(warmup + steps):
@@ -378,7 +402,7 @@ def _cpu_steps(batch, steps, warmup, threads=None):
     return times
 
 
-def _best_thread_count(batch):
+def _best_thread_count(batch, workload="cfg2"):
     """torch's CPU kernels collapse when a 100+-core host is oversubscribed by this small problem: give the CPU arm
     the thread count at which it is FASTEST (one probe step each), which is the fair baseline."""
     ncpu = os.cpu_count() or 1
@@ -386,7 +410,7 @@ def _best_thread_count(batch):
     best, best_t = cands[0], float("inf")
     t_begin = time.perf_counter()
     for c in cands:                      # ascending; stop once more threads make it slower, or the probe budget is spent
-        t = _cpu_steps(batch, 1, 1, threads=c)[0]
+        t = _cpu_steps(batch, 1, 1, threads=c, workload=workload)[0]
         if t < best_t:
             best, best_t = c, t
         elif t > 1.2 * best_t:
@@ -396,20 +420,20 @@ def _best_thread_count(batch):
     return best
 
 
-def cpu_baseline(sample_steps=2, batch=4):
-    threads = _best_thread_count(batch)
-    times = _cpu_steps(batch, sample_steps, 1, threads=threads)
+def cpu_baseline(sample_steps=2, batch=4, workload="cfg2"):
+    threads = _best_thread_count(batch, workload)
+    times = _cpu_steps(batch, sample_steps, 1, threads=threads, workload=workload)
     med = statistics.median(times)
     return {"value": round(batch / med, 2), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d steps of fwd+4 losses+bwd at bs=%d (same model/inputs shape, fp32, oracle port of the reference "
                       "PyTorch path; no optimizer step; thread count chosen by a probe over 8/16/32/64)" % (sample_steps, batch)}
 
 
-def cpu_baseline_bounded(limit_s=150):
+def cpu_baseline_bounded(limit_s=150, workload="cfg2"):
     """The CPU sample in a child process with a hard time limit: a slow or oversubscribed host must not cost the GPU line."""
     try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-baseline"], capture_output=True,
-                           text=True, timeout=limit_s)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu-baseline", "--workload", workload],
+                           capture_output=True, text=True, timeout=limit_s)
         for line in reversed(r.stdout.splitlines()):
             if line.startswith("{"):
                 return json.loads(line)
@@ -422,18 +446,20 @@ def cpu_baseline_bounded(limit_s=150):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    batch = 8
-    threads = _best_thread_count(batch)
-    times = _cpu_steps(batch, args.steps, max(1, min(args.warmup, 2)), threads=threads)
+    wl = WORKLOADS[args.workload]
+    batch = 8 if args.workload == "cfg2" else 2
+    threads = _best_thread_count(batch, args.workload)
+    times = _cpu_steps(batch, args.steps, max(1, min(args.warmup, 2)), threads=threads, workload=args.workload)
     ms_step = statistics.mean(times) * 1e3
     value = batch / (ms_step * 1e-3)
     base = {"value": round(value, 2), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "each step = fwd+4 losses+bwd of bs=%d on the host cores (bounded sample of the bs=128 workload)" % batch}
+            "sample": "each step = fwd+4 losses+bwd of bs=%d on the host cores (bounded sample of the bs=%d workload)"
+                      % (batch, wl["batch"])}
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world,
+        "impl": "reference", "metric": wl["metric"], "value": round(value, 2), "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm: oracle port of the reference path (the reference is pure "
+        "config": {"workload": wl["name"], "note": "CPU arm: oracle port of the reference path (the reference is pure "
                    "PyTorch and /root/reference does not travel to the GPU box)"},
         "cpu_baseline": base,
         "e2e": {"value": round(value, 2), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -445,18 +471,26 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (BASELINE: 128)")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the workload's, 128 for cfg2)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="cfg2: MultiMAE-B 224 bs=128 (BASELINE metric, default); cfg4: MultiMAE-L bs=64; cfg5: MultiMAE-B 448x448 bs=32")
+    ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the bounded CPU sample (development runs only)")
+    ap.add_argument("--standardize-depth", type=int, default=0,
+                    help="1: truncated depth standardisation (run_pretraining_multimae.py:487-492) inside the step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-baseline"])
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (single GPU); 2: also with data parallelism "
                          "(NCCL all-reduces captured in the graph)")
     ap.add_argument("--e2e-probe", action="store_true", help="extra timed loops that isolate the H2D / loss-read costs")
     ap.add_argument("--gemm-shapes", default=None, help="write a per-shape GEMM time table of one profiled step here")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = WORKLOADS[args.workload]["batch"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "cpu-baseline":
-        print(json.dumps(cpu_baseline(sample_steps=2, batch=4)), flush=True)
+        print(json.dumps(cpu_baseline(sample_steps=2, batch=4 if args.workload == "cfg2" else 2, workload=args.workload)),
+              flush=True)
         return
     if args.impl == "reference":
         if args.steps > 5:
