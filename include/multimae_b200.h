@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MMAE_ABI_VERSION 1
+#define MMAE_ABI_VERSION 2
 
 int mmae_abi_version(void);
 const char* mmae_last_error(void);
@@ -250,6 +250,11 @@ int mmae_block_backward(const float* x_in, const float* dx_out, float* dx_in, in
  * ---------------------------------------------------------------------------------------------- */
 typedef struct mmae_decoder_index {
   int batch, dim, num_visible, num_global, num_queries, total_tokens, num_tasks, own_task;
+  /* query_mode 0 (output_adapters.py:209-213): the queries are the own_task rows of the restored context, own_task in
+   * [0, num_tasks).  query_mode 1 (:214-221, use_task_queries=False or a task that is not among the inputs): every query
+   * is mask_token + pos (+ task_emb[own_task] when own_task >= 0; the slot may be num_tasks, an embedding that belongs to
+   * no input task). */
+  int query_mode;
   int tok_offset[MMAE_MAX_TASKS + 1];
   const int64_t* ids_keep;    /* [B, num_visible] */
   const int64_t* ids_restore; /* [B, total_tokens] */

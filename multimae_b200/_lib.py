@@ -79,7 +79,7 @@ class BlockGrads(ctypes.Structure):
 class DecoderIndex(ctypes.Structure):
     _fields_ = [("batch", c_int), ("dim", c_int), ("num_visible", c_int), ("num_global", c_int),
                 ("num_queries", c_int), ("total_tokens", c_int), ("num_tasks", c_int), ("own_task", c_int),
-                ("tok_offset", c_int * (MAX_TASKS + 1)), ("ids_keep", c_void_p), ("ids_restore", c_void_p)]
+                ("query_mode", c_int), ("tok_offset", c_int * (MAX_TASKS + 1)), ("ids_keep", c_void_p), ("ids_restore", c_void_p)]
 
 
 HEAD_TAIL_FIELDS = ["context_norm_w", "context_norm_b", "query_norm_w", "query_norm_b", "out_norm_w", "out_norm_b",
@@ -183,7 +183,7 @@ SIGNATURES = {
     "mmae_standardize_depth": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
 }
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 def lib():

@@ -186,11 +186,14 @@ __global__ void __launch_bounds__(256) dec_build_kernel(const float* __restrict_
     if (row >= n_rows) continue;
     if (row < nq_rows) {
       const int b = row / P, j = row % P;
-      const int g = ix.tok_offset[ix.own_task] + j;
-      const int rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
+      int rank = T;                                           // query_mode 1: every query starts from the mask token
+      if (ix.query_mode == 0) {
+        const int g = ix.tok_offset[ix.own_task] + j;
+        rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
+      }
       base[u] = rank < T ? reinterpret_cast<const float4*>(ctx + (int64_t(b) * (T + G) + rank) * Dd)
                          : reinterpret_cast<const float4*>(mask_token);
-      te[u] = reinterpret_cast<const float4*>(task_emb.p[ix.own_task]);
+      te[u] = ix.own_task >= 0 ? reinterpret_cast<const float4*>(task_emb.p[ix.own_task]) : nullptr;
       pe[u] = reinterpret_cast<const float4*>(pos + int64_t(j) * Dd);
       dst[u] = reinterpret_cast<float4*>(queries + int64_t(row) * Dd);
     } else {
@@ -263,10 +266,13 @@ __global__ void __launch_bounds__(256) dec_build_bwd_kernel(const float* __restr
         if (row >= n_rows) continue;
         if (row < nq_rows) {
           const int b = row / P, j = row % P;
-          const int g = ix.tok_offset[ix.own_task] + j;
-          const int rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
+          int rank = T;
+          if (ix.query_mode == 0) {
+            const int g = ix.tok_offset[ix.own_task] + j;
+            rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
+          }
           kind[u] = 0;
-          task[u] = ix.own_task;
+          task[u] = ix.own_task;                                // -1: no task embedding on the queries
           masked[u] = rank >= T;
           src_q[u] = int64_t(row);
         } else {
@@ -282,7 +288,7 @@ __global__ void __launch_bounds__(256) dec_build_bwd_kernel(const float* __restr
               if (q < ix.num_tasks && g >= ix.tok_offset[q]) t = q;
             kind[u] = 1;
             task[u] = t;
-            if (t == ix.own_task) src_q[u] = int64_t(b) * P + (g - ix.tok_offset[t]);
+            if (ix.query_mode == 0 && t == ix.own_task) src_q[u] = int64_t(b) * P + (g - ix.tok_offset[t]);
           }
         }
       }
@@ -507,7 +513,7 @@ int launch_dec_build_bwd(const float* dqueries, const float* dcontext, const mma
   MMAE_LAUNCH_OK();
   ColredDst dst;
   dst.p[0] = dmask_token;
-  for (int t = 0; t < MMAE_MAX_TASKS; ++t) dst.p[1 + t] = t < ix.num_tasks ? dtask_emb.p[t] : nullptr;
+  for (int t = 0; t < MMAE_MAX_TASKS; ++t) dst.p[1 + t] = dtask_emb.p[t];   // null entries are skipped
   return colred_finalize_n(partial, blocks, NSEG * ix.dim, ix.dim, dst, NSEG, st);
 }
 

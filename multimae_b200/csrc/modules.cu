@@ -421,8 +421,12 @@ extern "C" int mmae_dechead_forward(const float* enc, int De, const mmae_decoder
   MMAE_CHECK(enc && ixp && p && x_out && saved && ws, MMAE_ERR_ARG, "mmae_dechead_forward: bad args");
   const mmae_decoder_index& ix = *ixp;
   const int Dd = ix.dim, B = ix.batch, P = ix.num_queries, Nc = ix.num_visible + ix.num_global;
-  MMAE_CHECK(Dd % H == 0 && ix.num_tasks <= MMAE_MAX_TASKS && ix.own_task >= 0 && ix.own_task < ix.num_tasks,
+  MMAE_CHECK(Dd % H == 0 && ix.num_tasks <= MMAE_MAX_TASKS &&
+                 ((ix.query_mode == 0 && ix.own_task >= 0 && ix.own_task < ix.num_tasks) ||
+                  (ix.query_mode == 1 && ix.own_task >= -1 && ix.own_task <= ix.num_tasks && ix.own_task < MMAE_MAX_TASKS)),
              MMAE_ERR_ARG, "mmae_dechead_forward: bad decoder index");
+  MMAE_CHECK(ix.own_task < 0 || p->task_emb[ix.own_task] != nullptr || ix.query_mode == 0, MMAE_ERR_ARG,
+             "mmae_dechead_forward: query task embedding slot %d is empty", ix.own_task);
   const int Mq = B * P, Mc = B * Nc, dh = Dd / H;
   HeadSaved s = head_saved(saved, ix, De, H, hidden);
   HeadWs w = head_ws(ws, ix, De, H, hidden);

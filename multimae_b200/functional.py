@@ -277,6 +277,7 @@ class DecoderHeadFunction(torch.autograd.Function):
         ix.num_visible = Nc - meta["num_global"]
         ix.num_queries, ix.total_tokens = meta["num_queries"], meta["tok_offset"][-1]
         ix.num_tasks, ix.own_task = len(meta["tok_offset"]) - 1, meta["own_task"]
+        ix.query_mode = meta.get("query_mode", 0)
         for i, o in enumerate(meta["tok_offset"]):
             ix.tok_offset[i] = o
         ids_keep = ids_keep.contiguous()

@@ -113,10 +113,25 @@ class SpatialOutputAdapter(nn.Module, _PosEmbCache):
         nh = H // (self.stride_level * self.P_H)
         nw = W // (self.stride_level * self.P_W)
         tasks = list(input_info["tasks"].keys())
-        if not (self.use_task_queries and self.task in tasks):
-            raise NotImplementedError(
-                "multimae_b200: output adapter task '%s' must be one of the input tasks %s with use_task_queries=True "
-                "(the configuration run_pretraining_multimae.py builds)" % (self.task, tasks))
+        task_names = list(tasks)
+        task_embs = [self.task_embeddings[t] if (self.task_embeddings is not None and t in self.task_embeddings) else None
+                     for t in tasks]
+        if self.use_task_queries and self.task in tasks:
+            # queries = this task's rows of the restored, embedded context (multimae/output_adapters.py:209-213)
+            query_mode, own_task = 0, tasks.index(self.task)
+        else:
+            # queries = mask_token + pos_emb (+ this task's embedding when there is one) (:214-221): use_task_queries=False,
+            # or a task that is reconstructed without being an input (e.g. --in_domains rgb --out_domains rgb-depth-semseg)
+            query_mode, own_task = 1, -1
+            if self.task_embeddings is not None and self.task in self.task_embeddings:
+                if self.task in tasks:
+                    own_task = tasks.index(self.task)
+                else:                                        # an embedding that belongs to none of the given inputs
+                    if len(tasks) >= Fn.L.MAX_TASKS:
+                        raise Fn.L.MmaeError("multimae_b200: no free task slot for the query task embedding")
+                    own_task = len(tasks)
+                    task_names.append(self.task)
+                    task_embs.append(self.task_embeddings[self.task])
         tok_offset = [input_info["tasks"][t]["start_idx"] for t in tasks] + [input_info["num_task_tokens"]]
         for t in tasks:
             assert input_info["tasks"][t]["num_tokens"] == nh * nw, "context tasks must share the adapter's patch grid"
@@ -127,11 +142,9 @@ class SpatialOutputAdapter(nn.Module, _PosEmbCache):
         if getattr(self, "_own_arena", False) and torch.is_grad_enabled():
             self._bound["arena"].zero_()
         head_meta = dict(self._bound, dim=self.dim_tokens, num_global=input_info.get("num_global_tokens", 0),
-                         num_queries=nh * nw, tok_offset=tok_offset, own_task=tasks.index(self.task),
+                         num_queries=nh * nw, tok_offset=tok_offset, own_task=own_task, query_mode=query_mode,
                          heads=self.num_heads, hidden=self.mlp_hidden, eps=self.query_norm.eps,
-                         pos=self._resized_pos(nh, nw, "bilinear"), task_names=tasks)
-        task_embs = [self.task_embeddings[t] if (self.task_embeddings is not None and t in self.task_embeddings) else None
-                     for t in tasks]
+                         pos=self._resized_pos(nh, nw, "bilinear"), task_names=task_names)
         x = Fn.DecoderHeadFunction.apply(encoder_tokens, head_meta, ids_keep, ids_restore, *self._head_params(),
                                          *task_embs)
         x = self.decoder_transformer(x)

@@ -50,6 +50,8 @@ class OracleConfig:
     num_global_tokens: int = 1
     eps: float = 1e-6
     posemb_grid: int = 14   # image_size 224 // 16 (adapters are always built with image_size=224)
+    use_task_queries: bool = True               # --decoder_use_task_queries (run_pretraining_multimae.py:264,278)
+    context_tasks: Optional[List[str]] = None   # names with a task embedding in every decoder; None: the in_domains
 
 
 RGB = DomainSpec("rgb", "image", 3, 1)
@@ -222,8 +224,13 @@ def decode_task(enc, p, key: str, spec: DomainSpec, cfg: OracleConfig, token_cou
         embs.append(e)
     full = full + torch.cat(embs, dim=0)[None]                              # :207
     task = spec.name
-    assert task in token_counts, "oracle covers use_task_queries=True with the task among the inputs"
-    queries = full[:, start[task]:start[task] + token_counts[task]]         # :210-213
+    if cfg.use_task_queries and task in token_counts:
+        queries = full[:, start[task]:start[task] + token_counts[task]]     # :209-213
+    else:                                                                   # :214-221 — mask-token queries
+        queries = p[prefix + ".mask_token"].expand(B, nh * nw, -1) + pos[None]
+        te = p.get(prefix + ".task_embeddings." + task)
+        if te is not None:
+            queries = queries + te.reshape(1, 1, -1)
     vis = torch.gather(full, 1, ids_keep[:, :, None].expand(-1, -1, full.shape[2]))   # :224-225
     context = torch.cat([vis, glob], dim=1)                                 # :229-230 (global token: no embedding)
 
@@ -250,7 +257,7 @@ def forward(p: Dict[str, torch.Tensor], x: Dict[str, torch.Tensor], cfg: OracleC
         H, W = [s * SEMSEG.stride_level for s in x["semseg"].shape[1:]]
     else:
         H, W = x[first.name].shape[2:]
-    tokens = {d.name: embed_domain(x[d.name], p, d, cfg) for d in cfg.in_domains}       # :312-316
+    tokens = {d.name: embed_domain(x[d.name], p, d, cfg) for d in cfg.in_domains if d.name in x}   # :312-316
     counts = {k: v.shape[1] for k, v in tokens.items()}
     seq = torch.cat(list(tokens.values()), dim=1)                           # :340
     B = seq.shape[0]
@@ -330,14 +337,17 @@ def default_losses(cfg: OracleConfig):
     return out
 
 
-def step_losses(p, x, cfg: OracleConfig, task_masks: Dict[str, torch.Tensor], ids_keep, ids_restore):
-    """One train_one_epoch body up to the loss (run_pretraining_multimae.py:500-523): returns (losses, preds)."""
+def step_losses(p, x, cfg: OracleConfig, task_masks: Dict[str, torch.Tensor], ids_keep, ids_restore, targets=None):
+    """One train_one_epoch body up to the loss (run_pretraining_multimae.py:494-523): returns (losses, preds).
+    `x` is the input_dict handed to the model (:494-498); `targets` is tasks_dict (defaults to x) — it may hold tasks that
+    are reconstructed without being fed, whose loss then runs without a mask (masks.get(task, None), :520)."""
+    targets = x if targets is None else targets
     preds, _ = forward(p, x, cfg, ids_keep, ids_restore)
     fns = default_losses(cfg)
     losses = {}
     for key, spec in cfg.out_tasks:
         mask = task_masks.get(spec.name)
-        losses[key] = fns[key](preds[key].float(), x[spec.name], mask)
+        losses[key] = fns[key](preds[key].float(), targets[spec.name], mask)
     return losses, preds
 
 
@@ -402,8 +412,8 @@ def init_params(cfg: OracleConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
         P = spec.patch(cfg.patch_size)
         p[pre + ".mask_token"] = torch.zeros(1, 1, Dd)
         p[pre + ".pos_emb"] = sincos_posemb(G, G, Dd)
-        for d in cfg.in_domains:
-            p[pre + ".task_embeddings." + d.name] = torch.randn(1, 1, Dd, generator=g).clamp(-2, 2) * 0.02
+        for name in (cfg.context_tasks if cfg.context_tasks is not None else [d.name for d in cfg.in_domains]):
+            p[pre + ".task_embeddings." + name] = torch.randn(1, 1, Dd, generator=g).clamp(-2, 2) * 0.02
         linear(pre + ".proj_context", Dd, D)
         for n in ("context_norm", "query_norm", "out_norm"):
             norm(pre + "." + n, Dd)

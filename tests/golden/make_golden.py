@@ -12,6 +12,8 @@ Fixtures (all fp32, CPU, torch.save of plain dicts of tensors):
   interp.pt    : RGB-only model built with the default 224 pos-emb grid run on 32x32 inputs (bicubic/bilinear resize)
   cuda_*.pt    : shapes the CUDA path supports (head_dim 64/32); weights come from tests/helpers.formula_fill_ (not
                  stored) and gradients are stored as digests (norm + strided samples)
+  xtask_tiny / xout_tiny / noq_tiny / cuda_xtask / cuda_noq .pt : mask-token decoder queries (output_adapters.py:214-221) —
+                 a context task left out of the call, an output task that is no context task, use_task_queries=False
   depth_std.pt : truncated depth standardisation; the reference has it inline in train_one_epoch
                  (run_pretraining_multimae.py:487-492), so the statements are cut out of the reference source and executed
 
@@ -69,9 +71,11 @@ def record_sampler(R, name, B, tokens_per_task, num_encoded, alphas, seed):
     print("wrote", name)
 
 
-def build_model(R, in_domains, dim, depth, heads, dec_dim, dec_depth, dec_heads, image_size, extra_norm_pix=True):
+def build_model(R, in_domains, dim, depth, heads, dec_dim, dec_depth, dec_heads, image_size, extra_norm_pix=True,
+                out_domains=None, use_task_queries=True):
     conf = {"rgb": (3, 1), "depth": (1, 1)}
     inputs, outputs = {}, {}
+    out_domains = list(in_domains) if out_domains is None else list(out_domains)
     for d in in_domains:
         if d == "semseg":
             inputs[d] = R.SemSeg(num_classes=133, dim_class_emb=64, interpolate_class_emb=False, stride_level=4,
@@ -82,10 +86,10 @@ def build_model(R, in_domains, dim, depth, heads, dec_dim, dec_depth, dec_heads,
     def out_adapter(task):
         ch, stride = (133, 4) if task == "semseg" else conf[task]
         return R.Spatial(num_channels=ch, stride_level=stride, patch_size_full=16, dim_tokens=dec_dim, depth=dec_depth,
-                         num_heads=dec_heads, use_task_queries=True, task=task, context_tasks=list(in_domains),
-                         use_xattn=True, image_size=image_size)
+                         num_heads=dec_heads, use_task_queries=use_task_queries, task=task,
+                         context_tasks=list(in_domains), use_xattn=True, image_size=image_size)
 
-    for d in in_domains:
+    for d in out_domains:
         outputs[d] = out_adapter(d)
     if extra_norm_pix:
         outputs["norm_rgb"] = out_adapter("rgb")
@@ -101,25 +105,29 @@ def build_model(R, in_domains, dim, depth, heads, dec_dim, dec_depth, dec_heads,
     return model.float().train()
 
 
-def record_model(R, name, in_domains, B, size, num_encoded, seed, formula=False, **kw):
+def record_model(R, name, in_domains, B, size, num_encoded, seed, formula=False, feed=None, **kw):
+    """`feed`: the subset of in_domains handed to model() (train_one_epoch's input_dict); targets exist for every output
+    task.  kw may carry out_domains / use_task_queries (get_model wiring, run_pretraining_multimae.py:256-283)."""
     torch.manual_seed(seed)
     model = build_model(R, in_domains, **kw)
+    feed = list(in_domains) if feed is None else list(feed)
+    out_domains = list(kw.get("out_domains") or in_domains)
     if formula:
         sys.path.insert(0, os.path.dirname(HERE))
         from helpers import digest, formula_fill_
         formula_fill_(list(model.named_parameters()))
     g = torch.Generator().manual_seed(seed + 1)
     x = {}
-    for d in in_domains:
+    for d in list(in_domains) + [o for o in out_domains if o not in in_domains]:
         if d == "semseg":
             x[d] = torch.randint(0, 133, (B, size // 4, size // 4), generator=g)
         else:
             x[d] = torch.randn(B, 3 if d == "rgb" else 1, size, size, generator=g)
     torch.manual_seed(seed + 2)
-    tokens_like = {d: torch.zeros(B, (size // 16) ** 2, 1) for d in in_domains}
+    tokens_like = {d: torch.zeros(B, (size // 16) ** 2, 1) for d in feed}
     triple = model.generate_random_masks(tokens_like, num_encoded, alphas=1.0)
     model.generate_random_masks = lambda *a, **k: triple          # SURVEY.md §A.5 step 3
-    preds, masks = model(x, num_encoded_tokens=num_encoded, alphas=1.0)
+    preds, masks = model({d: x[d] for d in feed}, num_encoded_tokens=num_encoded, alphas=1.0)
     loss_fns = {"rgb": R.MSE(16, 1), "depth": R.L1(16, 1), "semseg": R.CE(16, 4), "norm_rgb": R.MSE(16, 1, norm_pix=True)}
     losses = {}
     for task in preds:
@@ -133,7 +141,8 @@ def record_model(R, name, in_domains, B, size, num_encoded, seed, formula=False,
     else:
         state, grads_out = {k: v.detach().clone() for k, v in model.state_dict().items()}, grads
     torch.save({
-        "config": dict(in_domains=list(in_domains), B=B, size=size, num_encoded=num_encoded, formula=formula, **kw),
+        "config": dict(in_domains=list(in_domains), B=B, size=size, num_encoded=num_encoded, formula=formula, feed=feed,
+                       **kw),
         "state_dict": state,
         "inputs": x,
         "task_masks": {k: v.clone() for k, v in masks.items()},
@@ -179,6 +188,33 @@ if __name__ == "__main__":
         record_depth_standardize("depth_std.pt")
         raise SystemExit(0)
     R = import_reference()
+    # mask-token queries (multimae/output_adapters.py:214-221): a task that is reconstructed without being fed
+    # (its embedding exists: context task left out of this call / does not exist: not a context task), and
+    # --decoder_use_task_queries False
+    xtask = dict(
+        xtask_tiny=lambda: record_model(R, "xtask_tiny.pt", ("rgb", "depth", "semseg"), B=3, size=64, num_encoded=10, seed=31,
+                                        feed=("rgb", "semseg"), dim=32, depth=2, heads=2, dec_dim=16, dec_depth=1,
+                                        dec_heads=2, image_size=64),
+        xout_tiny=lambda: record_model(R, "xout_tiny.pt", ("rgb",), B=2, size=64, num_encoded=6, seed=33,
+                                       out_domains=("rgb", "depth"), dim=32, depth=1, heads=2, dec_dim=16, dec_depth=1,
+                                       dec_heads=2, image_size=64),
+        noq_tiny=lambda: record_model(R, "noq_tiny.pt", ("rgb", "depth"), B=2, size=64, num_encoded=8, seed=35,
+                                      use_task_queries=False, dim=32, depth=1, heads=2, dec_dim=16, dec_depth=1,
+                                      dec_heads=2, image_size=64),
+        cuda_xtask=lambda: record_model(R, "cuda_xtask.pt", ("rgb", "depth", "semseg"), B=2, size=64, num_encoded=10, seed=37,
+                                        formula=True, feed=("rgb", "semseg"), dim=128, depth=1, heads=2, dec_dim=128,
+                                        dec_depth=1, dec_heads=4, image_size=64),
+        cuda_noq=lambda: record_model(R, "cuda_noq.pt", ("rgb", "depth"), B=2, size=64, num_encoded=8, seed=39, formula=True,
+                                      use_task_queries=False, out_domains=("rgb", "depth", "semseg"), dim=128, depth=1,
+                                      heads=2, dec_dim=128, dec_depth=1, dec_heads=4, image_size=64),
+    )
+    if only and only <= {k + ".pt" for k in xtask}:
+        for k, fn in xtask.items():
+            if k + ".pt" in only:
+                fn()
+        raise SystemExit(0)
+    for fn in xtask.values():
+        fn()
     record_depth_standardize("depth_std.pt")
     record_sampler(R, "sampler_small.pt", B=16, tokens_per_task=[16, 16, 16], num_encoded=12, alphas=1.0, seed=3)
     record_sampler(R, "sampler_cfg2.pt", B=8, tokens_per_task=[196, 196, 196], num_encoded=98, alphas=1.0, seed=4)

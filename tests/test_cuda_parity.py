@@ -31,11 +31,12 @@ def _load(golden_dir, name):
 def _build_model(c):
     from test_host_api import _build
     return _build(tuple(c["in_domains"]), c["dim"], c["depth"], c["heads"], c["dec_dim"], c["dec_depth"], c["dec_heads"],
-                  c["image_size"])
+                  c["image_size"], out_domains=c.get("out_domains"), use_task_queries=c.get("use_task_queries", True))
 
 
 def _oracle_cfg(c):
-    cfg = O.make_config(in_domains=tuple(c["in_domains"]))
+    cfg = O.make_config(in_domains=tuple(c["in_domains"]), out_domains=c.get("out_domains"))
+    cfg.use_task_queries = c.get("use_task_queries", True)
     cfg.dim, cfg.depth, cfg.heads = c["dim"], c["depth"], c["heads"]
     cfg.dec_dim, cfg.dec_depth, cfg.dec_heads = c["dec_dim"], c["dec_depth"], c["dec_heads"]
     cfg.posemb_grid = c["image_size"] // 16
@@ -84,9 +85,12 @@ def _loss_modules():
             "norm_rgb": MaskedMSELoss(16, 1, norm_pix=True)}
 
 
-def _run_cuda_step(model, x, triple, dev):
+def _run_cuda_step(model, x, triple, dev, feed=None):
+    """`x` holds the targets of every output task; `feed` names the entries handed to the model (default: all of x that
+    have an input adapter), like train_one_epoch's input_dict / tasks_dict (run_pretraining_multimae.py:482-498)."""
     model.generate_random_masks = lambda *a, **k: triple
-    preds, masks = model({k: v.to(dev) for k, v in x.items()}, num_encoded_tokens=triple[1].shape[1], alphas=1.0)
+    fed = {k: v.to(dev) for k, v in x.items() if (feed is None or k in feed)}
+    preds, masks = model(fed, num_encoded_tokens=triple[1].shape[1], alphas=1.0)
     fns = _loss_modules()
     losses = {}
     for task in preds:
@@ -127,15 +131,20 @@ def test_mask_sampler_large_and_properties(dev):
     assert bool((torch.sort(ids_restore, 1).values == torch.arange(sum(counts), device=dev)).all())   # a permutation
 
 
-@pytest.mark.parametrize("name", ["cuda_small.pt", "cuda_interp.pt"])
+# cuda_xtask / cuda_noq: mask-token decoder queries (multimae/output_adapters.py:214-221) — a context task that is not fed
+# in this call (its embedding rides in the spare task slot), --decoder_use_task_queries False, and an output task that is
+# no context task at all (no embedding); their losses run without a mask (run_pretraining_multimae.py:520)
+@pytest.mark.parametrize("name", ["cuda_small.pt", "cuda_interp.pt", "cuda_xtask.pt", "cuda_noq.pt"])
 def test_model_against_golden_and_oracle(golden_dir, dev, name):
     fx = _load(golden_dir, name)
     c = fx["config"]
+    feed = c.get("feed") or c["in_domains"]
     model = _build_model(c)
     formula_fill_(list(model.named_parameters()))
     model = model.to(dev).train()
     triple = ({k: v.to(dev) for k, v in fx["task_masks"].items()}, fx["ids_keep"].to(dev), fx["ids_restore"].to(dev))
-    preds, masks, losses = _run_cuda_step(model, fx["inputs"], triple, dev)
+    preds, masks, losses = _run_cuda_step(model, fx["inputs"], triple, dev, feed=feed)
+    assert set(preds) == set(fx["preds"])
 
     for k, ref in fx["preds"].items():
         assert rel_l2(preds[k], ref) < BF16_TOL, (k, rel_l2(preds[k], ref))
@@ -151,11 +160,17 @@ def test_model_against_golden_and_oracle(golden_dir, dev, name):
     formula_fill_(list(train.items()))
     for v in train.values():
         v.requires_grad_(True)
-    o_losses, _ = O.step_losses(p, fx["inputs"], cfg, fx["task_masks"], fx["ids_keep"], fx["ids_restore"])
+    o_losses, _ = O.step_losses(p, {d: fx["inputs"][d] for d in feed}, cfg, fx["task_masks"], fx["ids_keep"],
+                                fx["ids_restore"], targets=fx["inputs"])
     sum(o_losses.values()).backward()
     named = dict(model.named_parameters())
-    _check_grads({k: named[k].grad for k in train}, {k: v.grad for k, v in train.items()})
-    for k in train:                                        # and the reference's own digests
+    used = [k for k in train if train[k].grad is not None]      # e.g. the input adapter of a domain that was not fed
+    assert set(used) == set(fx["grads"])
+    for k in train:
+        if k not in used:
+            assert named[k].grad is None or float(named[k].grad.abs().sum()) == 0.0, k
+    _check_grads({k: named[k].grad for k in used}, {k: train[k].grad for k in used})
+    for k in used:                                         # and the reference's own digests
         d = fx["grads"][k]
         fair = float(fx["grad_norm"]) * (named[k].numel() / sum(v.numel() for v in train.values())) ** 0.5
         assert abs(float(named[k].grad.float().norm()) - float(d["norm"])) < PER_TENSOR_TOL * max(float(d["norm"]), fair), k

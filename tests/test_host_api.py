@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _build(in_domains=("rgb", "depth", "semseg"), dim=128, depth=2, heads=2, dec_dim=128, dec_depth=1, dec_heads=4,
-           image_size=64):
+           image_size=64, out_domains=None, use_task_queries=True):
     from multimae_b200.input_adapters import PatchedInputAdapter, SemSegInputAdapter
     from multimae_b200.multimae import MultiMAE
     from multimae_b200.output_adapters import SpatialOutputAdapter
@@ -27,12 +27,12 @@ def _build(in_domains=("rgb", "depth", "semseg"), dim=128, depth=2, heads=2, dec
                                         image_size=image_size)
         else:
             ins[d] = PatchedInputAdapter(num_channels=conf[d][0], stride_level=1, patch_size_full=16, image_size=image_size)
-    for key in list(in_domains) + ["norm_rgb"]:
+    for key in list(in_domains if out_domains is None else out_domains) + ["norm_rgb"]:
         task = "rgb" if key == "norm_rgb" else key
         ch, stride = conf[task]
         outs[key] = SpatialOutputAdapter(num_channels=ch, stride_level=stride, patch_size_full=16, dim_tokens=dec_dim,
                                          depth=dec_depth, num_heads=dec_heads, task=task, context_tasks=list(in_domains),
-                                         image_size=image_size)
+                                         image_size=image_size, use_task_queries=use_task_queries)
     return MultiMAE(ins, outs, num_global_tokens=1, dim_tokens=dim, depth=depth, num_heads=heads)
 
 
