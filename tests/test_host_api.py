@@ -117,3 +117,40 @@ def test_grad_arena_layout():
     arena.flat.fill_(1.0)
     arena.zero_()
     assert float(arena.flat.abs().sum()) == 0.0
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """Every struct of include/multimae_b200.h against its ctypes twin in multimae_b200/_lib.py: sizeof and the offset of
+    every field, as a C compiler lays them out (gcc on the header itself - the header is plain C)."""
+    import ctypes
+    import shutil
+    import subprocess
+    from multimae_b200 import _lib as L
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    pairs = {"mmae_gemm_epilogue": L.GemmEpilogue, "mmae_embed_layout": L.EmbedLayout, "mmae_embed_inputs": L.EmbedInputs,
+             "mmae_embed_params": L.EmbedParams, "mmae_embed_grads": L.EmbedGrads, "mmae_block_params": L.BlockParams,
+             "mmae_block_grads": L.BlockGrads, "mmae_decoder_index": L.DecoderIndex, "mmae_dechead_params": L.DecHeadParams,
+             "mmae_dechead_grads": L.DecHeadGrads}
+    header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "multimae_b200.h")
+    declared = set(re.findall(r"^\} (mmae_\w+);", open(header).read(), re.M))
+    assert declared == set(pairs), declared ^ set(pairs)
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "%s"' % header, "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append('  printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('  printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    for line in out.strip().splitlines():
+        cname, field, value = line.split()
+        cls = pairs[cname]
+        mine = ctypes.sizeof(cls) if field == "sizeof" else getattr(cls, field).offset
+        assert mine == int(value), "%s.%s: ctypes %d, C %s" % (cname, field, mine, value)
+    assert L.MAX_TASKS == int(re.search(r"#define MMAE_MAX_TASKS (\d+)", open(header).read()).group(1))
+    assert L.ABI_VERSION == int(re.search(r"#define MMAE_ABI_VERSION (\d+)", open(header).read()).group(1))

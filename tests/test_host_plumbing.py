@@ -118,3 +118,44 @@ def test_fixed_masks_and_no_masking(stub):
     assert preds["depth"].shape == (1, 1, 64, 64)
     with pytest.raises(ValueError):
         model(_inputs(B=2), task_masks={k: torch.cat([v, torch.ones_like(v)]) for k, v in tm.items()})
+
+
+def test_mask_token_queries_plumbing(stub):
+    """Host side of the mask-token decoder queries (multimae/output_adapters.py:214-221): a context task that is not fed
+    rides in the spare task-embedding slot, an output task that is no context task has no embedding, and
+    use_task_queries=False keeps the task's own slot; gradients are announced under the reference's parameter names."""
+    from multimae_b200.criterion import MaskedL1Loss
+    seen = []
+    real_apply = Fn.DecoderHeadFunction.apply
+
+    def spy(enc, meta, *rest):
+        seen.append((meta["prefix"], meta["query_mode"], meta["own_task"], list(meta["task_names"])))
+        return real_apply(enc, meta, *rest)
+
+    Fn.DecoderHeadFunction.apply = staticmethod(spy)
+    try:
+        # built for rgb+depth+semseg, fed rgb+semseg: 'depth' is decoded from mask-token queries + its own embedding
+        model = _build().train()
+        ready = []
+        model.set_grad_callback(lambda names: ready.extend(names))
+        x = _inputs()
+        preds, masks = model({"rgb": x["rgb"], "semseg": x["semseg"]}, num_encoded_tokens=10)
+        assert set(preds) == {"rgb", "depth", "semseg", "norm_rgb"} and set(masks) == {"rgb", "semseg"}
+        by_prefix = {p: (mode, own, names) for p, mode, own, names in seen}
+        assert by_prefix["output_adapters.depth."] == (1, 2, ["rgb", "semseg", "depth"])
+        assert by_prefix["output_adapters.rgb."] == (0, 0, ["rgb", "semseg"])
+        assert by_prefix["output_adapters.semseg."] == (0, 1, ["rgb", "semseg"])
+        MaskedL1Loss(16, 1)(preds["depth"], x["depth"], mask=masks.get("depth")).backward()    # no mask: plain mean
+        assert "output_adapters.depth.task_embeddings.depth" in ready
+        assert "output_adapters.depth.mask_token" in ready
+        assert not any(n.startswith("input_adapters.depth.") for n in ready)                   # never embedded
+        # an output task that is no context task at all, and use_task_queries=False
+        seen.clear()
+        model = _build(in_domains=("rgb",), out_domains=("rgb", "depth"), use_task_queries=False).train()
+        preds, masks = model({"rgb": x["rgb"]}, num_encoded_tokens=6)
+        by_prefix = {p: (mode, own, names) for p, mode, own, names in seen}
+        assert by_prefix["output_adapters.depth."] == (1, -1, ["rgb"])
+        assert by_prefix["output_adapters.rgb."] == (1, 0, ["rgb"])
+        assert preds["depth"].shape == (2, 1, 64, 64)
+    finally:
+        Fn.DecoderHeadFunction.apply = real_apply
