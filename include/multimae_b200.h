@@ -342,6 +342,9 @@ int mmae_patchify_bf16(const float* image, void* tokens_bf16, int64_t ld_tok, in
  * ---------------------------------------------------------------------------------------------- */
 int mmae_standardize_depth(const float* depth, float* out, int B, int n, int lo, int hi, float eps, float* stats,
                            void* stream);
+/* 1 (default): the kernel validated in round 1; 2: experimental second version (histogram copies, cluster split of
+ * large maps over distributed shared memory) - also MMAE_DEPTH_STD_VARIANT=2 */
+int mmae_standardize_depth_set_variant(int variant);
 
 #ifdef __cplusplus
 }

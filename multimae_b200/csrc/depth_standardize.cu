@@ -14,6 +14,8 @@
 //     {x : L < x < H}  +  (copies of L with rank >= lo)  +  (copies of H with rank <= hi-1)
 // which equals the reference's slice of the sorted array exactly; the sums differ from torch only by fp32 summation
 // order (per-thread fp32 partials, fp64 across threads).
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace mmae {
@@ -221,12 +223,34 @@ depth_standardize_kernel(const float* x, float* y, int n, int lo, int hi, float 
 
 using namespace mmae;
 
+namespace {
+// 1: the validated kernel of this file (default).  2: depth_standardize_v2.cu (experimental, see its header).
+int depth_std_variant() {
+  static int v = [] {
+    const char* e = getenv("MMAE_DEPTH_STD_VARIANT");
+    return (e != nullptr && atoi(e) == 2) ? 2 : 1;
+  }();
+  return v;
+}
+int g_depth_std_variant = 0;   // 0: not set through the API -> environment / default
+}  // namespace
+
+extern "C" int mmae_standardize_depth_set_variant(int variant) {
+  MMAE_CHECK(variant == 1 || variant == 2, MMAE_ERR_ARG, "mmae_standardize_depth_set_variant: 1 or 2");
+  g_depth_std_variant = variant;
+  return MMAE_OK;
+}
+
 extern "C" int mmae_standardize_depth(const float* depth, float* out, int B, int n, int lo, int hi, float eps,
                                       float* stats, void* stream) {
   MMAE_CHECK(depth && out && B > 0 && n > 0, MMAE_ERR_ARG, "mmae_standardize_depth: bad args");
   MMAE_CHECK(lo >= 0 && lo < hi && hi <= n, MMAE_ERR_ARG, "mmae_standardize_depth: need 0 <= lo < hi <= n (lo %d, hi %d, n %d)",
              lo, hi, n);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((g_depth_std_variant != 0 ? g_depth_std_variant : depth_std_variant()) == 2) {
+    const int rc = launch_depth_standardize_v2(depth, out, B, n, lo, hi, eps, stats, st);
+    if (rc != MMAE_ERR_UNSUPPORTED) return rc;            // maps beyond 8 CTAs' shared memory: the kernel below
+  }
   const size_t cache = size_t(n) * sizeof(uint32_t);
   if (cache + 4096 <= size_t(227) * 1024) {
     static size_t configured = 0;

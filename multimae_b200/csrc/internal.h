@@ -46,6 +46,9 @@ int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float
                      const float* pos, float* queries, float* context, cudaStream_t st);
 int launch_dec_build_bwd(const float* dqueries, const float* dcontext, const mmae_decoder_index& ix, float* dctx,
                          float* dmask_token, const TaskEmbGradPtrs& dtask_emb, cudaStream_t st);
+// depth_standardize_v2.cu (experimental variant 2); MMAE_ERR_UNSUPPORTED when the map exceeds 8 CTAs' shared memory
+int launch_depth_standardize_v2(const float* depth, float* out, int B, int n, int lo, int hi, float eps, float* stats,
+                                cudaStream_t st);
 int launch_cast2d(const float* src, int64_t ld_src, bf16* dst, int64_t ld_dst, int rows, int cols, cudaStream_t st);
 
 }  // namespace mmae
