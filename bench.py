@@ -98,17 +98,18 @@ def build_model_and_losses(device, size="base", image=224):
     from multimae_b200.multimae import pretrain_multimae_base, pretrain_multimae_large
     from multimae_b200.output_adapters import SpatialOutputAdapter
     doms = ["rgb", "depth", "semseg"]
-    # adapters are built with image_size = --input_size like get_model does (run_pretraining_multimae.py:243-283)
-    ins = {"rgb": PatchedInputAdapter(num_channels=3, stride_level=1, patch_size_full=16, image_size=image),
-           "depth": PatchedInputAdapter(num_channels=1, stride_level=1, patch_size_full=16, image_size=image),
+    # like get_model (run_pretraining_multimae.py:248-283) the adapters keep their default image_size=224: at 448^2 inputs
+    # the 14x14 sin-cos tables are resized to 28x28 (bicubic / bilinear) - once, the resized table is cached
+    del image
+    ins = {"rgb": PatchedInputAdapter(num_channels=3, stride_level=1, patch_size_full=16),
+           "depth": PatchedInputAdapter(num_channels=1, stride_level=1, patch_size_full=16),
            "semseg": SemSegInputAdapter(num_classes=133, dim_class_emb=64, interpolate_class_emb=False, stride_level=4,
-                                        patch_size_full=16, image_size=image)}
+                                        patch_size_full=16)}
     outs = {}
     for key, (ch, stride, task) in {"rgb": (3, 1, "rgb"), "depth": (1, 1, "depth"), "semseg": (133, 4, "semseg"),
                                     "norm_rgb": (3, 1, "rgb")}.items():
         outs[key] = SpatialOutputAdapter(num_channels=ch, stride_level=stride, patch_size_full=16, dim_tokens=256, depth=2,
-                                         num_heads=8, use_task_queries=True, task=task, context_tasks=doms, use_xattn=True,
-                                         image_size=image)
+                                         num_heads=8, use_task_queries=True, task=task, context_tasks=doms, use_xattn=True)
     factory = pretrain_multimae_base if size == "base" else pretrain_multimae_large
     model = factory(ins, outs, num_global_tokens=1, drop_path_rate=0.0).to(device).train()
     losses = {"rgb": MaskedMSELoss(16, 1), "depth": MaskedL1Loss(16, 1), "semseg": MaskedCrossEntropyLoss(16, 4),
@@ -379,8 +380,7 @@ def _cpu_steps(batch, steps, warmup, threads=None, workload="cfg2"):
     from oracle import multimae_oracle as O
     wl = WORKLOADS[workload]
     torch.set_num_threads(threads or (os.cpu_count() or 1))
-    cfg = O.make_config(size=wl["size"])
-    cfg.posemb_grid = wl["image"] // 16
+    cfg = O.make_config(size=wl["size"])          # posemb_grid stays 14: tables resized to the input's grid as in get_model
     p = O.init_params(cfg, seed=0)
     train = O.trainable(p)
     for v in train.values():
