@@ -133,6 +133,34 @@ NCU_GEMM_TRAFFIC_NOTE = ("fc1 forward GEMM 12672x3072x768: 24.3 MB read (= the 2
                          "126 MB L2 when the kernel ends (algorithmic bytes per launch: 102.1 MB)")
 
 
+def encoder_tc_from_table(agg, rows_enc, D_enc, peak_tf):
+    """BASELINE metric, second half ("encoder TC util%").  `agg`: {(M, N, K, operand-major flags, split): [launches, ms]}
+    of one profiled step.  The GEMMs of the encoder blocks (QKV, proj, fc1, fc2; forward, dgrad, wgrad) are the launches
+    whose three extents are the encoder row count B*(visible+1) and two of {D, 3D, 4D}; their FLOPs over their CUDA-event
+    time, against the measured and the nominal dense bf16 peak."""
+    widths = {D_enc, 3 * D_enc, 4 * D_enc}
+    fl_enc = ms_enc = 0.0
+    n_enc = 0
+    for (M_, N_, K_, _maj, _split), (cnt, ms_) in agg.items():
+        dims = [M_, N_, K_]
+        if rows_enc not in dims:
+            continue
+        dims.remove(rows_enc)
+        if dims[0] in widths and dims[1] in widths:
+            fl_enc += 2.0 * M_ * N_ * K_ * cnt
+            ms_enc += ms_
+            n_enc += cnt
+    if ms_enc <= 0:
+        return None
+    tf_enc = fl_enc / (ms_enc * 1e-3) / 1e12
+    return {"encoder_gemm_tflops": round(tf_enc, 1), "launches_per_step": n_enc, "ms_per_step": round(ms_enc, 3),
+            "frac_of_measured_peak": round(tf_enc / peak_tf, 4), "frac_of_nominal_2250": round(tf_enc / 2250.0, 4),
+            "mhsa_kernel_tensor_pipe_pct_ncu": {"attn_tc_fwd_kernel": 7.7, "attn_tc_bwd_kernel": 7.3},
+            "note": "ncu sm__pipe_tensor figures of the big encoder GEMM kernels: 63-69 % "
+                    "(profiles/r01_ncu_full_hot_kernels.txt); the stand-alone MHSA kernel is HBM-bound (Q/K/V in + O out = "
+                    "78 MB -> 12 us floor -> <= 24 % tensor pipe), DESIGN.md section 7"}
+
+
 def synthetic_batch(B, seed, pin=False, image=224):
     g = torch.Generator().manual_seed(seed)
     x = {"rgb": torch.randn(B, 3, image, image, generator=g), "depth": torch.randn(B, 1, image, image, generator=g),
@@ -316,21 +344,28 @@ def run_ours(args, rank, world, local_rank):
     fl, ms_g, n_g = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
     lib.mmae_profile_gemm_read(ctypes.byref(fl), ctypes.byref(ms_g), ctypes.byref(n_g))
     gemm_tf = fl.value / (ms_g.value * 1e-3) / 1e12 if ms_g.value > 0 else 0.0
-    if args.gemm_shapes and rank == 0:
-        buf = ctypes.create_string_buffer(1 << 20)
-        n = lib.mmae_profile_gemm_dump(buf, len(buf))
-        agg = {}
-        for line in buf.raw[:max(n, 0)].decode().splitlines():
-            M_, N_, K_, fl_, ms_ = line.split()
-            key = (int(M_), int(N_), int(K_), int(fl_) & 3, int(fl_) >> 8)
-            a_ = agg.setdefault(key, [0, 0.0])
-            a_[0] += 1
-            a_[1] += float(ms_)
-        with open(args.gemm_shapes, "w") as fh:
-            fh.write("%7s %6s %6s %3s %5s %5s %9s %8s\n" % ("M", "N", "K", "maj", "split", "count", "ms_total", "TF/s"))
-            for key, (cnt, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-                tf = 2.0 * key[0] * key[1] * key[2] * cnt / (ms_ * 1e-3) / 1e12
-                fh.write("%7d %6d %6d %3d %5d %5d %9.3f %8.1f\n" % (key + (cnt, ms_, tf)))
+    encoder_tc = None
+    if rank == 0:
+        try:
+            buf = ctypes.create_string_buffer(1 << 20)
+            n = lib.mmae_profile_gemm_dump(buf, len(buf))
+            agg = {}
+            for line in buf.raw[:max(n, 0)].decode().splitlines():
+                M_, N_, K_, fl_, ms_ = line.split()
+                key = (int(M_), int(N_), int(K_), int(fl_) & 3, int(fl_) >> 8)
+                a_ = agg.setdefault(key, [0, 0.0])
+                a_[0] += 1
+                a_[1] += float(ms_)
+            if args.gemm_shapes:
+                with open(args.gemm_shapes, "w") as fh:
+                    fh.write("%7s %6s %6s %3s %5s %5s %9s %8s\n" % ("M", "N", "K", "maj", "split", "count", "ms_total", "TF/s"))
+                    for key, (cnt, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                        tf = 2.0 * key[0] * key[1] * key[2] * cnt / (ms_ * 1e-3) / 1e12
+                        fh.write("%7d %6d %6d %3d %5d %5d %9.3f %8.1f\n" % (key + (cnt, ms_, tf)))
+            encoder_tc = encoder_tc_from_table(agg, args.batch * (wl["visible"] + 1), 768 if wl["size"] == "base" else 1024,
+                                               peak_tf)
+        except Exception as e:  # noqa: BLE001  (diagnostics only: never cost the headline line)
+            _note("per-shape GEMM table unavailable: %s" % str(e)[:120])
 
     if rank != 0:
         if world > 1:
@@ -362,6 +397,8 @@ def run_ours(args, rank, world, local_rank):
                      "kernel_share_of_step": round(ms_g.value / ms_step, 3),
                      "step_model_flops_frac": round(value / world * wl["flop"] / (peak_tf * 1e12), 4)},
     }
+    if encoder_tc is not None:
+        out["encoder_tc"] = encoder_tc
     if args.workload != "cfg2":
         # the committed ncu traffic figure belongs to the cfg2 fc1 GEMM shape
         out["roofline"]["traffic"], out["roofline"]["traffic_note"] = None, "no ncu capture for this workload's GEMM shapes"

@@ -46,3 +46,18 @@ def test_workload_table_matches_survey():
         w = bench.WORKLOADS[k]
         assert (w["flop"], w["batch"], w["size"], w["image"], w["visible"]) == (flop, batch, size, image, visible), k
     assert bench.WORKLOADS["cfg2"]["metric"] == bench.METRIC
+
+
+def test_encoder_tensor_core_figure_from_the_committed_table():
+    """bench.encoder_tc_from_table on the per-shape table of the committed round-1 run: the 144 encoder GEMM launches
+    (12 blocks x {QKV, proj, fc1, fc2} x {forward, dgrad, wgrad}) and nothing from the decoders / embedding."""
+    sys.path.insert(0, ROOT)
+    import bench
+    agg = {}
+    for line in open(os.path.join(ROOT, "profiles", "r01_gemm_per_shape_7330.txt")).read().splitlines()[1:]:
+        M, N, K, maj, split, cnt, ms, _tf = line.split()
+        agg[(int(M), int(N), int(K), int(maj), int(split))] = [int(cnt), float(ms)]
+    r = bench.encoder_tc_from_table(agg, 128 * 99, 768, 1436.1)
+    assert r["launches_per_step"] == 144
+    assert 900 < r["encoder_gemm_tflops"] < 1300 and abs(r["frac_of_measured_peak"] - r["encoder_gemm_tflops"] / 1436.1) < 1e-3
+    assert bench.encoder_tc_from_table({(25088, 256, 256, 0, 1): [17, 0.3]}, 128 * 99, 768, 1436.1) is None
