@@ -245,6 +245,19 @@ def decode_task(enc, p, key: str, spec: DomainSpec, cfg: OracleConfig, token_cou
     return x
 
 
+def ids_from_task_masks(task_masks: List[torch.Tensor]):
+    """Fixed-mask branch of MultiMAE.forward (multimae/multimae.py:334-338): visible tokens (mask 0) first.  The reference
+    sorts with an unstable argsort and takes ONE visible count from the whole batch (right only when every sample keeps
+    the same number, e.g. B = 1); here the sort is stable and the count is per sample, which yields the same predictions
+    (the encoder and the decoders' context are permutation-invariant in the kept tokens)."""
+    mask_all = torch.cat(list(task_masks), dim=1)
+    ids_shuffle = torch.argsort(mask_all, dim=1, stable=True)
+    ids_restore = torch.argsort(ids_shuffle, dim=1, stable=True)
+    n_vis = (mask_all == 0).sum(dim=1)
+    assert bool((n_vis == n_vis[0]).all()), "every sample must keep the same number of visible tokens"
+    return ids_shuffle[:, :int(n_vis[0])], ids_restore
+
+
 # --------------------------------------------------------------------------------------------------------------
 # whole forward (multimae/multimae.py:271-379)
 # --------------------------------------------------------------------------------------------------------------

@@ -14,6 +14,8 @@ Fixtures (all fp32, CPU, torch.save of plain dicts of tensors):
                  stored) and gradients are stored as digests (norm + strided samples)
   xtask_tiny / xout_tiny / noq_tiny / cuda_xtask / cuda_noq .pt : mask-token decoder queries (output_adapters.py:214-221) —
                  a context task left out of the call, an output task that is no context task, use_task_queries=False
+  fixed_masks.pt : forward with caller-supplied task_masks (B = 1) and with mask_inputs=False: predictions
+  losses.pt    : the three criteria over norm_pix / label_smoothing / mask, no mask, all-zero mask: values + prediction gradients
   depth_std.pt : truncated depth standardisation; the reference has it inline in train_one_epoch
                  (run_pretraining_multimae.py:487-492), so the statements are cut out of the reference source and executed
 
@@ -154,6 +156,67 @@ def record_model(R, name, in_domains, B, size, num_encoded, seed, formula=False,
     print("wrote", name, {k: round(float(v), 6) for k, v in losses.items()}, "grad_norm", float(gnorm))
 
 
+def record_fixed_masks(R, name):
+    """MultiMAE.forward with caller-supplied task_masks (multimae/multimae.py:334-338; B = 1 like MultiMAE_Demo.ipynb) and
+    with mask_inputs=False (:324-325, every token encoded): predictions only - both are invariant to the order of the kept
+    tokens, which the reference's unstable argsort / random shuffle leaves open."""
+    torch.manual_seed(43)
+    kw = dict(dim=32, depth=2, heads=2, dec_dim=16, dec_depth=1, dec_heads=2, image_size=64)
+    model = build_model(R, ("rgb", "depth", "semseg"), **kw).eval()
+    g = torch.Generator().manual_seed(44)
+    x1 = {"rgb": torch.randn(1, 3, 64, 64, generator=g), "depth": torch.randn(1, 1, 64, 64, generator=g),
+          "semseg": torch.randint(0, 133, (1, 16, 16), generator=g)}
+    tm = {k: torch.ones(1, 16, dtype=torch.long) for k in x1}
+    tm["rgb"][0, [0, 5, 6, 11]] = 0
+    tm["depth"][0, [3, 12]] = 0
+    tm["semseg"][0, [1, 2, 8, 9, 15]] = 0
+    with torch.no_grad():
+        preds_fixed, masks_fixed = model(x1, task_masks=tm)
+    x2 = {"rgb": torch.randn(2, 3, 64, 64, generator=g), "depth": torch.randn(2, 1, 64, 64, generator=g),
+          "semseg": torch.randint(0, 133, (2, 16, 16), generator=g)}
+    torch.manual_seed(45)
+    with torch.no_grad():
+        preds_all, masks_all = model(x2, mask_inputs=False)
+    assert all(int(v.sum()) == 0 for v in masks_all.values())
+    torch.save({"config": dict(in_domains=["rgb", "depth", "semseg"], **kw),
+                "state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+                "x_fixed": x1, "task_masks": tm, "preds_fixed": {k: v.clone() for k, v in preds_fixed.items()},
+                "x_all": x2, "preds_all": {k: v.clone() for k, v in preds_all.items()}}, os.path.join(HERE, name))
+    print("wrote", name)
+
+
+def record_losses(R, name):
+    """Every criterion of multimae/criterion.py over its options (norm_pix, label_smoothing, mask / no mask / all-zero
+    mask / one sample without masked patches): loss value and gradient w.r.t. the prediction."""
+    g = torch.Generator().manual_seed(41)
+    B, S = 3, 32
+    mask = (torch.rand(B, (S // 16) ** 2, generator=g) > 0.4).long()
+    mask[2] = 0                                             # a sample without any masked patch (skipped by nanmean)
+    mask[0, 0] = 1
+    cases = {
+        "mse": (R.MSE(16, 1), torch.randn(B, 3, S, S, generator=g), torch.randn(B, 3, S, S, generator=g)),
+        "mse_norm_pix": (R.MSE(16, 1, norm_pix=True), torch.randn(B, 3, S, S, generator=g), torch.randn(B, 3, S, S, generator=g) * 2 + 1),
+        "l1": (R.L1(16, 1), torch.randn(B, 1, S, S, generator=g), torch.randn(B, 1, S, S, generator=g)),
+        "l1_norm_pix": (R.L1(16, 1, norm_pix=True), torch.randn(B, 1, S, S, generator=g), torch.randn(B, 1, S, S, generator=g) + 3),
+        "ce": (R.CE(16, 4), torch.randn(B, 133, S // 4, S // 4, generator=g) * 2, torch.randint(0, 133, (B, S // 4, S // 4), generator=g)),
+        "ce_smooth": (R.CE(16, 4, label_smoothing=0.1), torch.randn(B, 133, S // 4, S // 4, generator=g) * 2,
+                      torch.randint(0, 133, (B, S // 4, S // 4), generator=g)),
+    }
+    out = {"mask": mask, "cases": {}}
+    for key, (fn, pred, tgt) in cases.items():
+        rec = {"pred": pred, "target": tgt}
+        for mname, m in (("masked", mask), ("none", None), ("zero", torch.zeros_like(mask))):
+            pr = pred.clone().requires_grad_(True)
+            loss = fn(pr, tgt, mask=m)
+            rec["loss_" + mname] = loss.detach().clone().float()
+            if loss.requires_grad:
+                loss.backward()
+                rec["grad_" + mname] = pr.grad.clone()
+        out["cases"][key] = rec
+    torch.save(out, os.path.join(HERE, name))
+    print("wrote", name, {k: round(float(v["loss_masked"]), 6) for k, v in out["cases"].items()})
+
+
 def record_depth_standardize(name):
     """Executes the reference's OWN statements (the body of `if standardize_depth and 'depth' in tasks_dict:` in
     train_one_epoch, run_pretraining_multimae.py:487-492) on synthetic depth maps and records input and result."""
@@ -208,6 +271,12 @@ if __name__ == "__main__":
                                       use_task_queries=False, out_domains=("rgb", "depth", "semseg"), dim=128, depth=1,
                                       heads=2, dec_dim=128, dec_depth=1, dec_heads=4, image_size=64),
     )
+    if only == {"fixed_masks.pt"}:
+        record_fixed_masks(R, "fixed_masks.pt")
+        raise SystemExit(0)
+    if only == {"losses.pt"}:
+        record_losses(R, "losses.pt")
+        raise SystemExit(0)
     if only and only <= {k + ".pt" for k in xtask}:
         for k, fn in xtask.items():
             if k + ".pt" in only:
@@ -215,6 +284,8 @@ if __name__ == "__main__":
         raise SystemExit(0)
     for fn in xtask.values():
         fn()
+    record_losses(R, "losses.pt")
+    record_fixed_masks(R, "fixed_masks.pt")
     record_depth_standardize("depth_std.pt")
     record_sampler(R, "sampler_small.pt", B=16, tokens_per_task=[16, 16, 16], num_encoded=12, alphas=1.0, seed=3)
     record_sampler(R, "sampler_cfg2.pt", B=8, tokens_per_task=[196, 196, 196], num_encoded=98, alphas=1.0, seed=4)
