@@ -60,7 +60,12 @@ class TrainStep:
         return self.static_out
 
     def capture(self, example_x, warmup=3):
-        """Warm up eagerly (lazy kernel attributes, workspaces, arena) then capture the step into a CUDA graph."""
+        """Warm up eagerly (lazy kernel attributes, workspaces, arena) then capture the step into a CUDA graph.
+
+        The learning rate and the step count live on the device and follow the schedule across replays
+        (FlatAdamW.sync_hyperparams); betas, eps and the weight decay are launch arguments and therefore frozen at their
+        capture-time values - with a weight-decay schedule (run_pretraining_multimae.py:479-480, off by default:
+        --weight_decay_end is None) re-capture when the value changes or run the step eagerly."""
         dev = next(iter(example_x.values())).device
         n_tasks = len([d for d in example_x if d in self.model.input_adapters])
         B = next(iter(example_x.values())).shape[0]
