@@ -52,3 +52,82 @@ def test_reference_script_builds_our_model():
                          timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "DROPIN_OK 97917" in res.stdout.replace(",", ""), res.stdout[-500:]
+
+
+STEP_SCRIPT = r'''
+import ctypes, sys, types
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, %(root)r + "/tests")
+import torch
+from multimae_b200 import _lib as L
+from multimae_b200 import functional as Fn
+
+# ---- stand-ins for the GPU: a library stub that validates every call's arguments and computes nothing, zero-filled
+# "uninitialised" buffers so that the losses the unchanged script reads are finite, no device synchronisation
+class Stub:
+    calls = []
+    def __getattr__(self, name):
+        res, argtypes = L.SIGNATURES[name]
+        def fn(*args):
+            assert len(args) == len(argtypes), name
+            for a, t in zip(args, argtypes):
+                if not isinstance(a, type(ctypes.byref(ctypes.c_int()))):
+                    t.from_param(a)
+            Stub.calls.append(name)
+            return 4096 if name.endswith("_bytes") else (L.ABI_VERSION if name == "mmae_abi_version" else (b"" if name == "mmae_last_error" else 0))
+        return fn
+stub = Stub()
+L.lib = lambda: stub
+L.current_stream = lambda: 0
+Fn._require_cuda = lambda t, what: None
+_empty = torch.empty
+torch.empty = lambda *a, **k: _empty(*a, **k).zero_()
+torch.cuda.synchronize = lambda *a, **k: None
+
+from multimae_b200 import overlay
+overlay.install(%(ref)r)
+import run_pretraining_multimae as R            # the reference script, unmodified
+import utils
+
+args = types.SimpleNamespace(model="pretrain_multimae_base", in_domains=["rgb", "depth", "semseg"],
+                             out_domains=["rgb", "depth", "semseg"], patch_size=16, decoder_dim=256, decoder_depth=1,
+                             decoder_num_heads=8, decoder_use_task_queries=True, decoder_use_xattn=True,
+                             extra_norm_pix_loss=True, num_global_tokens=1, drop_path=0.0,
+                             opt="adamw", weight_decay=0.05, lr=1e-4, opt_eps=1e-8, opt_betas=[0.9, 0.95], momentum=0.9,
+                             balancer_lr_scale=1.0)
+model = R.get_model(args)
+loss_balancer = R.NoWeightingStrategy()
+optimizer = R.create_optimizer(args, {"model": model, "balancer": loss_balancer})
+loss_scaler = R.NativeScaler()                   # = multimae_b200.native_scaler.NativeScalerWithGradNormCount via the overlay
+tasks_loss_fn = {d: R.DOMAIN_CONF[d]["loss"](patch_size=16, stride=R.DOMAIN_CONF[d]["stride_level"]) for d in args.out_domains}
+tasks_loss_fn["norm_rgb"] = R.DOMAIN_CONF["rgb"]["loss"](patch_size=16, stride=1, norm_pix=True)
+g = torch.Generator().manual_seed(0)
+def batch():
+    return ({"rgb": torch.randn(2, 3, 224, 224, generator=g), "depth": torch.rand(2, 1, 224, 224, generator=g) + 0.5,
+             "semseg": torch.randint(0, 133, (2, 56, 56), generator=g)}, None)
+stats = R.train_one_epoch(model, [batch(), batch()], tasks_loss_fn, loss_balancer, optimizer, torch.device("cpu"), epoch=0,
+                          loss_scaler=loss_scaler, max_norm=None, max_skip_norm=None, start_steps=0,
+                          lr_schedule_values=[1e-4, 1e-4], wd_schedule_values=[0.05, 0.05], num_encoded_tokens=98,
+                          in_domains=args.in_domains, loss_on_unmasked=False, alphas=1.0, sample_tasks_uniformly=False,
+                          standardize_depth=True, extra_norm_pix_loss=True, fp32_output_adapters=["semseg"])
+for name in ("mmae_sample_masks", "mmae_embed_forward", "mmae_block_forward", "mmae_dechead_forward", "mmae_dectail_forward",
+             "mmae_masked_loss_forward", "mmae_masked_loss_backward", "mmae_dectail_backward", "mmae_dechead_backward",
+             "mmae_block_backward", "mmae_embed_backward"):
+    assert name in Stub.calls, name
+assert Stub.calls.count("mmae_block_forward") == 2 * (12 + 4 * 1) and Stub.calls.count("mmae_masked_loss_forward") == 2 * 4
+assert {"[Epoch] loss", "[Epoch] rgb_loss", "[Epoch] depth_loss", "[Epoch] semseg_loss", "[Epoch] norm_rgb_loss",
+        "[Epoch] grad_norm", "[Epoch] loss_scale", "[Epoch] lr"} <= set(stats), sorted(stats)
+print("STEP_OK", len(Stub.calls))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_reference_train_one_epoch_drives_our_modules():
+    """The reference's own, unmodified `train_one_epoch` (run_pretraining_multimae.py:458-574) - autocast context, depth
+    standardisation, `model(**kwargs)`, the four criteria, loss balancer, NativeScaler call, meters - runs two steps over
+    this package's modules with a library stub in place of the GPU: every module-level C-ABI entry point is reached with
+    well-formed arguments, in the counts the B model implies."""
+    res = subprocess.run([sys.executable, "-c", STEP_SCRIPT % {"root": ROOT, "ref": REF}], capture_output=True, text=True,
+                         timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-5000:]
+    assert "STEP_OK" in res.stdout, res.stdout[-500:]
