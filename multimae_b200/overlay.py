@@ -42,12 +42,34 @@ class _Wrapped:
         return getattr(self.__dict__["module"], name)
 
 
-def install(reference_root=None, replace_ddp=True):
+def _legacy_checkpoint_load():
+    """torch >= 2.6 made `torch.load` default to weights_only=True; the reference (pinned to torch 1.10) re-loads its OWN
+    checkpoints - model / optimizer / scaler state plus the argparse Namespace and numpy schedule scalars - with a bare
+    `torch.load(path, map_location='cpu')` (utils/checkpoint.py:124).  Restore the default the script was written against
+    for calls that do not say otherwise.  Like the `torch._six` stub this is a torch-version shim, not a change of the script."""
+    import functools
+    import torch
+    if getattr(torch.load, "_mmae_legacy_default", False):
+        return
+    original = torch.load
+
+    @functools.wraps(original)
+    def load(*args, **kwargs):
+        kwargs.setdefault("weights_only", False)
+        return original(*args, **kwargs)
+
+    load._mmae_legacy_default = True
+    torch.load = load
+
+
+def install(reference_root=None, replace_ddp=True, legacy_checkpoint_load=True):
     """Install the overlay into sys.modules.  `reference_root`: checkout of EPFL-VILAB/MultiMAE (for its `utils` package)."""
     if "torch._six" not in sys.modules:            # utils/native_scaler.py:11 imports a module removed in torch >= 2
         six = types.ModuleType("torch._six")
         six.inf = math.inf
         sys.modules["torch._six"] = six
+    if legacy_checkpoint_load:
+        _legacy_checkpoint_load()
     if reference_root is not None and reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     pkg = types.ModuleType("multimae")

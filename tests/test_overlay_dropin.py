@@ -131,3 +131,76 @@ def test_reference_train_one_epoch_drives_our_modules():
                          timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-5000:]
     assert "STEP_OK" in res.stdout, res.stdout[-500:]
+
+
+FULL_SCRIPT = r'''
+import ctypes, os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import torch
+from PIL import Image
+from multimae_b200 import _lib as L
+from multimae_b200 import functional as Fn
+
+class Stub:                                     # validates every C-ABI call, computes nothing (no GPU here)
+    calls = []
+    def __getattr__(self, name):
+        res, argtypes = L.SIGNATURES[name]
+        def fn(*args):
+            assert len(args) == len(argtypes), name
+            for a, t in zip(args, argtypes):
+                if not isinstance(a, type(ctypes.byref(ctypes.c_int()))):
+                    t.from_param(a)
+            Stub.calls.append(name)
+            return 4096 if name.endswith("_bytes") else (L.ABI_VERSION if name == "mmae_abi_version" else (b"" if name == "mmae_last_error" else 0))
+        return fn
+stub = Stub()
+L.lib = lambda: stub
+L.current_stream = lambda: 0
+Fn._require_cuda = lambda t, what: None
+_empty = torch.empty
+torch.empty = lambda *a, **k: _empty(*a, **k).zero_()
+torch.cuda.synchronize = lambda *a, **k: None
+
+# a tiny multi-task image folder: root/<task>/<class>/<name>.png (utils/dataset_folder.py MultiTaskImageFolder)
+root, out = %(data)r, %(out)r
+rng = np.random.default_rng(0)
+for i in range(4):
+    for task, arr in (("rgb", rng.integers(0, 255, (64, 64, 3), dtype=np.uint8)),
+                      ("depth", rng.integers(1000, 60000, (64, 64), dtype=np.uint16)),
+                      ("semseg", rng.integers(0, 133, (64, 64), dtype=np.uint8))):
+        os.makedirs(os.path.join(root, task, "scene"), exist_ok=True)
+        Image.fromarray(arr).save(os.path.join(root, task, "scene", "%%04d.png" %% i))
+
+from multimae_b200 import overlay
+argv = [os.path.join(%(ref)r, "run_pretraining_multimae.py"), "--data_path", root, "--output_dir", out, "--device", "cpu",
+        "--batch_size", "2", "--epochs", %(epochs)r, "--warmup_epochs", "0", "--save_ckpt_freq", "1", "--num_workers", "0",
+        "--no_pin_mem", "--decoder_depth", "1", "--standardize_depth", "--fp32_output_adapters", "semseg",
+        "--no_log_wandb", "--blr", "1e-4"]
+try:
+    overlay.main(argv)
+except SystemExit as e:
+    assert not e.code, e.code
+assert Stub.calls.count("mmae_embed_forward") == %(steps)d, Stub.calls.count("mmae_embed_forward")
+print("FULL_OK", sorted(f for f in os.listdir(out) if f.startswith("checkpoint")))
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_unmodified_script_end_to_end_with_checkpoint_resume(tmp_path):
+    """`python -m multimae_b200.overlay run_pretraining_multimae.py ...` in process: the reference's argument parser, data
+    pipeline (a 4-image multi-task folder written here), get_model, optimizer factory, LR/WD schedules, train_one_epoch,
+    log.txt and utils.save_model run unmodified over this package's modules (library stubbed: no GPU here).  The second
+    launch auto-resumes from the checkpoint the first one wrote (model, optimizer and scaler state through
+    utils/checkpoint.py:119-134) and trains one more epoch."""
+    data, out = str(tmp_path / "data"), str(tmp_path / "out")
+    os.makedirs(out)
+    for epochs, steps, expect in (("1", 2, ["checkpoint-0.pth"]), ("2", 2, ["checkpoint-0.pth", "checkpoint-1.pth"])):
+        res = subprocess.run([sys.executable, "-c", FULL_SCRIPT % {"root": ROOT, "ref": REF, "data": data, "out": out,
+                                                                   "epochs": epochs, "steps": steps}],
+                             capture_output=True, text=True, timeout=900)
+        assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-6000:]
+        assert "FULL_OK %s" % expect in res.stdout, res.stdout[-1500:]
+        if epochs == "2":
+            assert "Auto resume checkpoint" in res.stdout or "Resume checkpoint" in res.stdout, res.stdout[-3000:]
+    assert os.path.exists(os.path.join(out, "log.txt"))
