@@ -37,6 +37,23 @@ class Workspace:
         return buf
 
 
+_ARENAS = weakref.WeakSet()
+
+
+def find_arena_for(params):
+    """The live GradArena whose flat buffer holds EVERY gradient of `params` (each p.grad aliases one of its views), or
+    None.  Lets a caller that was handed only `model.parameters()` - NativeScalerWithGradNormCount inside the unchanged
+    train_one_epoch - reach the flat gradient buffer and the data-parallel reducer attached to it."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return None
+    for arena in list(_ARENAS):
+        base, end = arena.flat.data_ptr(), arena.flat.data_ptr() + arena.flat.numel() * arena.flat.element_size()
+        if all(g.device == arena.flat.device and base <= g.data_ptr() < end for g in grads):
+            return arena
+    return None
+
+
 class GradArena:
     """Flat fp32 gradient storage for a list of (name, parameter); views are 32-byte aligned."""
 
@@ -50,6 +67,8 @@ class GradArena:
         self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=device)
         self.views = {name: self.flat[o:o + n].view(shape) for name, (o, n, shape) in self.offsets.items()}
         self.owned = False     # True: p.grad aliases the views and backward returns None for parameters
+        self.reducer = None    # parallel.FlatGradReducer exchanging this arena between ranks (attach_data_parallel)
+        _ARENAS.add(self)
 
     def zero_(self):
         self.flat.zero_()

@@ -27,9 +27,13 @@ def get_grad_norm_(parameters, norm_type: float = 2.0) -> torch.Tensor:
 
 
 def _find_arena(optimizer, parameters):
+    """The flat gradient buffer behind the parameters: published by the optimizer (FlatAdamW), or - after backward - the
+    arena all p.grad alias (data-parallel models own their gradients: parallel.attach_data_parallel)."""
     arena = getattr(optimizer, "mmae_arena", None)
     if arena is not None:
         return arena
+    if parameters is not None:
+        return Fn.find_arena_for(parameters)
     return None
 
 
@@ -63,11 +67,16 @@ class NativeScalerWithGradNormCount:
     def __call__(self, loss, optimizer, clip_grad=None, skip_grad=None, parameters=None, create_graph=False,
                  update_grad=True):
         self._lazy_init(loss.device)
+        if parameters is not None and not isinstance(parameters, (list, tuple)):
+            parameters = list(parameters)            # the script passes the generator model.parameters()
         (loss * self._scale if self._enabled else loss).backward(create_graph=create_graph)
         if not update_grad:
             return None
         arena = self._arena or _find_arena(optimizer, parameters)
-        post = self._reducer.finish() if self._reducer is not None else 1.0
+        # the bucketed all-reduces started during backward are joined here; a reducer that was attached to the model
+        # behind the script's back (overlay: DistributedDataParallel -> identity wrapper) is found through its arena
+        reducer = self._reducer if self._reducer is not None else getattr(arena, "reducer", None)
+        post = reducer.finish() if reducer is not None else 1.0
         if arena is not None:
             inv = (1.0 / self._scale) if self._enabled else None
             norm, out2 = Fn.grad_unscale_norm(arena.flat, inv_scale=1.0, post_scale=post, inv_scale_tensor=inv)

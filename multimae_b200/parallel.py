@@ -88,6 +88,7 @@ def attach_data_parallel(model, scaler=None, process_group=None, bucket_bytes=48
     arena = model.own_gradients(True)
     names = [n for n, p in model.named_parameters() if p.requires_grad]
     reducer = FlatGradReducer(arena, names, process_group, bucket_bytes)
+    arena.reducer = reducer            # found again by a scaler that only ever sees model.parameters() (overlay launcher)
     model.set_grad_callback(reducer.on_grads_ready)
     if scaler is not None:
         scaler.attach_arena(arena)
