@@ -80,6 +80,7 @@ def install(reference_root=None, replace_ddp=True, legacy_checkpoint_load=True):
         sys.modules["multimae." + sub] = mod
         setattr(pkg, sub, mod)
     from . import multimae as mm
+    mm.AUTO_OWN_GRADIENTS = True                   # p.grad = views of the flat gradient arena (see multimae.py)
     # register the factories in the reference's registry if it only became importable now
     try:
         from utils.registry import _model_entrypoints, register_model  # type: ignore

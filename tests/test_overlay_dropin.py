@@ -115,6 +115,9 @@ for name in ("mmae_sample_masks", "mmae_embed_forward", "mmae_block_forward", "m
              "mmae_block_backward", "mmae_embed_backward"):
     assert name in Stub.calls, name
 assert Stub.calls.count("mmae_block_forward") == 2 * (12 + 4 * 1) and Stub.calls.count("mmae_masked_loss_forward") == 2 * 4
+assert Stub.calls.count("mmae_grad_unscale_norm") == 2                 # fused unscale + norm over the flat arena, per step
+assert all(p.grad is not None and p.grad.data_ptr() == model.grad_arena().view(n).data_ptr()
+           for n, p in model.named_parameters() if p.requires_grad)
 assert {"[Epoch] loss", "[Epoch] rgb_loss", "[Epoch] depth_loss", "[Epoch] semseg_loss", "[Epoch] norm_rgb_loss",
         "[Epoch] grad_norm", "[Epoch] loss_scale", "[Epoch] lr"} <= set(stats), sorted(stats)
 print("STEP_OK", len(Stub.calls))
@@ -182,6 +185,8 @@ try:
 except SystemExit as e:
     assert not e.code, e.code
 assert Stub.calls.count("mmae_embed_forward") == %(steps)d, Stub.calls.count("mmae_embed_forward")
+# the script's own NativeScaler call took the one-pass unscale / norm path over the flat gradient arena
+assert Stub.calls.count("mmae_grad_unscale_norm") == %(steps)d, Stub.calls.count("mmae_grad_unscale_norm")
 print("FULL_OK", sorted(f for f in os.listdir(out) if f.startswith("checkpoint")))
 '''
 
