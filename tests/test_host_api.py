@@ -154,3 +154,32 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert mine == int(value), "%s.%s: ctypes %d, C %s" % (cname, field, mine, value)
     assert L.MAX_TASKS == int(re.search(r"#define MMAE_MAX_TASKS (\d+)", open(header).read()).group(1))
     assert L.ABI_VERSION == int(re.search(r"#define MMAE_ABI_VERSION (\d+)", open(header).read()).group(1))
+
+
+def test_c_abi_rejects_bad_arguments_before_any_launch():
+    """Error behaviour of the C ABI (no GPU needed: every check fires before the first CUDA call): a non-zero code,
+    the message behind mmae_last_error(), and the Python stub's exception (MmaeError, a RuntimeError like the reference's
+    assertion failures, e.g. multimae/input_adapters.py:105-106)."""
+    import ctypes
+    from multimae_b200 import _lib as L
+    lib = L.lib()
+    ep = L.GemmEpilogue()
+    ARG, UNSUPPORTED = 1, 3
+    cases = [
+        (lib.mmae_gemm_bf16(None, 0, 0, None, 0, 0, 128, 128, 64, 1, ctypes.byref(ep), None), ARG, b"null operand"),
+        (lib.mmae_gemm_bf16(16, 64, 0, 16, 64, 0, 128, 100, 64, 1, ctypes.byref(ep), None), ARG, b"multiple of 8"),
+        (lib.mmae_standardize_depth(None, None, 1, 16, 1, 9, 1e-6, None, None), ARG, b"bad args"),
+        (lib.mmae_standardize_depth(16, 16, 1, 16, 9, 9, 1e-6, None, None), ARG, b"lo < hi"),
+        (lib.mmae_standardize_depth_set_variant(3), ARG, b"1 or 2"),
+        (lib.mmae_layernorm_forward(16, 100, 16, 16, 16, 100, None, 0, 16, 16, 4, 100, 1e-6, None), UNSUPPORTED, b"multiple of 128"),
+        (lib.mmae_attention_forward(16, 64, 16, 64, 16, 64, 16, 64, None, 1, 1, 8, 8, 48, 0.1, None), UNSUPPORTED, b"head_dim 48"),
+        (lib.mmae_masked_loss_forward(5, 0, 0.0, 16, 16, None, 1, 3, 32, 32, 16, 16, 16, None), UNSUPPORTED, b"kind"),
+    ]
+    # mmae_last_error() holds the message of the most recent failure: re-issue each call to read its own message
+    assert [rc for rc, _, _ in cases] == [want for _, want, _ in cases]
+    assert lib.mmae_gemm_bf16(16, 64, 0, 16, 64, 0, 128, 100, 64, 1, ctypes.byref(ep), None) == ARG
+    assert b"N=100 must be a multiple of 8" in lib.mmae_last_error()
+    with pytest.raises(L.MmaeError, match="multiple of 8"):
+        L.check(lib.mmae_gemm_bf16(16, 64, 0, 16, 64, 0, 128, 100, 64, 1, ctypes.byref(ep), None), "mmae_gemm_bf16")
+    assert issubclass(L.MmaeError, RuntimeError)
+    assert lib.mmae_standardize_depth_set_variant(1) == 0
