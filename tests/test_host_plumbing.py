@@ -159,3 +159,34 @@ def test_mask_token_queries_plumbing(stub):
         assert preds["depth"].shape == (2, 1, 64, 64)
     finally:
         Fn.DecoderHeadFunction.apply = real_apply
+
+
+def test_train_step_eager_and_sampling_options(stub):
+    """TrainStep._step (the body of train_one_epoch between the H2D copy and the optimizer step) through the stub: depth
+    standardisation first, `loss_sources` routing of norm_rgb, per-task alphas and uniform task sampling
+    (multimae/multimae.py:148-162,182-187)."""
+    from multimae_b200.criterion import MaskedCrossEntropyLoss, MaskedL1Loss, MaskedMSELoss
+    from multimae_b200.native_scaler import NativeScalerWithGradNormCount
+    from multimae_b200.optim import FlatAdamW
+    from multimae_b200.train_step import TrainStep
+    model = _build().train()
+    opt = FlatAdamW(model, lr=1e-3)
+    scaler = NativeScalerWithGradNormCount(enabled=False).attach_arena(model.grad_arena())
+    fns = {"rgb": MaskedMSELoss(16, 1), "depth": MaskedL1Loss(16, 1), "semseg": MaskedCrossEntropyLoss(16, 4),
+           "norm_rgb": MaskedMSELoss(16, 1, norm_pix=True)}
+    x = _inputs()
+    step = TrainStep(model, fns, opt, scaler, num_encoded_tokens=12, alphas=[0.5, 1.0, 2.0], loss_sources={"norm_rgb": "rgb"},
+                     standardize_depth=True)
+    loss, norm = step(x, use_graph=False)
+    assert loss.shape == () and norm is not None
+    assert stub.calls.count("mmae_standardize_depth") == 1 and stub.calls.index("mmae_standardize_depth") < stub.calls.index("mmae_embed_forward")
+    assert stub.calls.count("mmae_masked_loss_forward") == 4 and "mmae_adamw_step" in stub.calls
+    assert x["depth"].shape == (2, 1, 64, 64)               # the caller's batch dict still holds its own depth tensor
+    stub.calls.clear()
+    uniform = TrainStep(model, fns, opt, scaler, num_encoded_tokens=12, sample_tasks_uniformly=True,
+                        loss_sources={"norm_rgb": "rgb"})
+    torch.manual_seed(0)
+    uniform(x, use_graph=False)
+    assert "mmae_sample_masks" in stub.calls and "mmae_standardize_depth" not in stub.calls
+    a = model.sample_alphas(64, 3, alphas=[1.0, 1.0, 1.0])
+    assert a.shape == (64, 3) and bool(((a > 0.5).sum(1) >= 1).all())      # never the all-zero task subset (:150)
