@@ -563,6 +563,20 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// MMAE_GEMM_BALANCED_GRID=1 (experiment for round 2, default off, not yet measured): launch ceil(items / rounds) persistent
+// CTAs instead of min(items, SMs), rounds = ceil(items / SMs).  The makespan in rounds is unchanged (196 decoder tiles: 2
+// rounds on 148 or on 98 CTAs), but the SMs left free can host the persistent GEMM of another task decoder's stream, which
+// otherwise waits for a whole kernel: the four decoder streams only overlap their small-K GEMMs if those leave SMs free.
+static int g_gemm_balanced_grid = []() {
+  const char* e = getenv("MMAE_GEMM_BALANCED_GRID");
+  return e ? atoi(e) : 0;
+}();
+static int persistent_grid(int items, int slots) {
+  const int full = std::min(items, slots);
+  if (!g_gemm_balanced_grid || items <= 0) return full;
+  return ceil_div(items, ceil_div(items, slots));
+}
+
 template <int BN, bool A_MN, bool B_MN>
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int split_k,
                  cudaStream_t stream) {
@@ -578,7 +592,7 @@ int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   sc.tiles_n = ceil_div(p.N, BN);
   sc.splits = split_k;
   sc.total = sc.tiles_m * sc.tiles_n * split_k;
-  const int grid = std::min(sc.total, sm_count());
+  const int grid = persistent_grid(sc.total, sm_count());
   const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K, (A_MN ? 1 : 0) | (B_MN ? 2 : 0) | (split_k << 8));
   launch_k(kern, grid, C::THREADS, C::TOTAL, stream, tmA, tmB, tmC, p, sc);
   if (prof) gemm_profile_end(stream);
@@ -822,7 +836,7 @@ int launch_gemm3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorM
   sc.tiles_n = ceil_div(p.N, BN);
   sc.splits = split_k;
   sc.total = sc.tiles_m * sc.tiles_n * split_k;
-  const int clusters = std::min(sc.total, sm_count() / 2);
+  const int clusters = persistent_grid(sc.total, sm_count() / 2);
   const bool prof = gemm_profile_begin(stream, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K, (A_MN ? 1 : 0) | (B_MN ? 2 : 0) | (split_k << 8));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
