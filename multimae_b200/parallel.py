@@ -6,6 +6,8 @@ One process per GPU; parameters replicated; the arena is cut into contiguous buc
 kernels); `finish()` joins them before the fused unscale/norm kernel, which also applies the 1/world_size averaging.
 Replaces DistributedDataParallel's bucket copy-in/copy-out + unused-parameter bookkeeping
 (run_pretraining_multimae.py:380-383) — the kernels already write gradients in place in the buckets."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -83,8 +85,11 @@ class FlatGradReducer:
         return 1.0 / self.world
 
 
-def attach_data_parallel(model, scaler=None, process_group=None, bucket_bytes=48 << 20):
-    """Wire a MultiMAE model for data-parallel training with in-place bucketed all-reduce; returns the reducer."""
+def attach_data_parallel(model, scaler=None, process_group=None, bucket_bytes=None):
+    """Wire a MultiMAE model for data-parallel training with in-place bucketed all-reduce; returns the reducer.
+    `bucket_bytes`: default 48 MB (MMAE_BUCKET_MB overrides it for sweeps)."""
+    if bucket_bytes is None:
+        bucket_bytes = int(float(os.environ.get("MMAE_BUCKET_MB", "48")) * (1 << 20))
     arena = model.own_gradients(True)
     names = [n for n, p in model.named_parameters() if p.requires_grad]
     reducer = FlatGradReducer(arena, names, process_group, bucket_bytes)
