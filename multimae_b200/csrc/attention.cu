@@ -25,6 +25,8 @@ int attn_tc_backward_gen(const void* q, int64_t ldq, const void* k, int64_t ldk,
                          void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
 int attn_tc_forward_gen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                         int64_t ldo, float* lse, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
+int attn_tc_forward_persistent(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                               int64_t ldo, float* lse, int B, int H, int Nq, int Nk, float scale, cudaStream_t st);
 int attn_tc_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                     float* lse, int B, int H, int Nq, int Nk, float scale, cudaStream_t st);
 int attn_tc_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
@@ -547,8 +549,11 @@ extern "C" int mmae_attention_forward(const void* q, int64_t ldq, const void* k,
              MMAE_ERR_ARG, "mmae_attention_forward: 16-byte alignment / ld %% 8 required");
   dim3 grid(ceil_div(Nq, ATT_ROWS), H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim))
+  if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim)) {
+    if (g_attn_tc & 16)   // experimental persistent variant (attention_tc.cu), never on by default
+      return attn_tc_forward_persistent(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, scale, st);
     return attn_tc_forward(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, scale, st);
+  }
   // general tcgen05 forward: wins for up to 128 keys (26-29 us vs 33 us at 196 x 99 x 32, B*H = 1024); with a second key
   // box the mma.sync kernel with ldmatrix + cp.async double buffering is ahead (50 vs 63 us at 196 x 196 x 32); bit 3 of
   // the switch (8) forces the tcgen05 kernel for every supported shape

@@ -189,6 +189,180 @@ __global__ void __launch_bounds__(128) attn_tc_fwd_kernel(const __grid_constant_
 }
 
 // =====================================================================================================================
+// forward, persistent variant - EXPERIMENTAL, NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent).
+// Selected only by bit 4 of the switch (mmae_attention_set_tc(3 | 16) / MMAE_ATTN_TC=19); the default stays
+// attn_tc_fwd_kernel.  scripts/gpu_check_attention_v2.py compares and times the two.
+//
+// Same arithmetic as attn_tc_fwd_kernel.  What changes is the schedule: 2 CTAs per SM each loop over (batch, head) items
+// with a 2-stage Q/K/V ring, so the TMA of item i+1 is in flight while item i runs S -> softmax -> P V -> store, and the
+// per-CTA set-up (TMEM allocation, barrier init, tensor-map fetch) is paid once per CTA instead of once per item; 1536 items
+// are dealt over 296 CTAs instead of running as 2.6 waves of 592.  S / O share one 128-column TMEM accumulator, as before.
+// =====================================================================================================================
+constexpr int FWD2_STAGE_BYTES = 3 * TILE_BYTES;
+constexpr int FWD2_SMEM = 2 * FWD2_STAGE_BYTES + 128 + 1024;
+
+__global__ void __launch_bounds__(128) attn_tc_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                     const __grid_constant__ CUtensorMap tmK,
+                                                                     const __grid_constant__ CUtensorMap tmV,
+                                                                     const AttnTcParams p, const int items) {
+  pdl_prologue();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * FWD2_STAGE_BYTES);   // [0],[1] stage loaded, [2] S ready, [3] O ready
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nk16 = (p.Nk + 15) & ~15;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+
+  auto issue_loads = [&](int item, int stage) {
+    const int h = item % p.H, b = item / p.H;
+    uint8_t* base = smem + stage * FWD2_STAGE_BYTES;
+    mbar_expect_tx(&bars[stage], 3 * TILE_BYTES);
+    tma_load_3d(base, &tmQ, &bars[stage], h * DH, 0, b);
+    tma_load_3d(base + TILE_BYTES, &tmK, &bars[stage], h * DH, 0, b);
+    tma_load_3d(base + 2 * TILE_BYTES, &tmV, &bars[stage], h * DH, 0, b);
+  };
+  if (threadIdx.x == 0 && int(blockIdx.x) < items) issue_loads(blockIdx.x, 0);
+
+  const int row = warp * 32 + lane;
+  const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
+  const float sl2 = p.scale * LOG2E_F;
+
+  int it = 0;
+  for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    const int stage = it & 1;
+    const uint32_t ld_phase = uint32_t(it >> 1) & 1u;     // each stage barrier completes once per use of the stage
+    const uint32_t ph = uint32_t(it) & 1u;                // bars[2] / bars[3] complete once per item
+    const int h = item % p.H, b = item / p.H;
+    uint8_t* sQ = smem + stage * FWD2_STAGE_BYTES;
+    uint8_t* sK = sQ + TILE_BYTES;
+    uint8_t* sV = sQ + 2 * TILE_BYTES;
+    uint8_t* sP = sQ;                                     // P (two 64-key panels) aliases Q|K once S is complete
+
+    if (threadIdx.x == 0) {
+      // prefetch the next item into the other stage: its last readers (the P V MMAs of item it-1) completed before every
+      // thread passed the barrier that ended iteration it-1
+      const int next = item + int(gridDim.x);
+      if (next < items) issue_loads(next, stage ^ 1);
+      mbar_wait(&bars[stage], ld_phase);
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, nk16, 0, 0);
+#pragma unroll
+      for (int j = 0; j < DH / 16; ++j) {
+        const uint64_t da = umma_smem_desc_sw128(smem_u32(sQ) + j * 32, 16, 1024);
+        const uint64_t db = umma_smem_desc_sw128(smem_u32(sK) + j * 32, 16, 1024);
+        tc_mma_f16_ss(tmem, da, db, idesc, j != 0 ? 1u : 0u);
+      }
+      tc_commit(&bars[2]);
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- softmax: thread = query row
+    mbar_wait(&bars[2], ph);
+    tc_fence_after();
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < nk16; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + c0, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c0 + i < p.Nk) mx = fmaxf(mx, __uint_as_float(r[i]));
+    }
+    const float moff = mx * sl2;
+    float sum = 0.f;
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t pk[16];
+      if (c0 < nk16) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + c0, r);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = c0 + 2 * i < p.Nk ? fast_exp2(__uint_as_float(r[2 * i]) * sl2 - moff) : 0.f;
+          const float c = c0 + 2 * i + 1 < p.Nk ? fast_exp2(__uint_as_float(r[2 * i + 1]) * sl2 - moff) : 0.f;
+          sum += a + c;
+          pk[i] = pack_bf16x2(a, c);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = 0u;
+      }
+      store_row32(sP, row, c0, pk);                       // Q|K are dead: the S MMAs completed (bars[2])
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t idesc = umma_idesc_bf16(128, DH, 0, 1);
+      const int ksteps = nk16 / 16;
+      for (int j = 0; j < ksteps; ++j) {
+        const uint32_t a_addr = smem_u32(sP) + (j >> 2) * TILE_BYTES + (j & 3) * 32;
+        const uint64_t da = umma_smem_desc_sw128(a_addr, 16, 1024);
+        const uint64_t db = umma_smem_desc_sw128(smem_u32(sV) + j * (16 * 128), TILE_BYTES, 1024);
+        tc_mma_f16_ss(tmem, da, db, idesc, j != 0 ? 1u : 0u);
+      }
+      tc_commit(&bars[3]);
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- epilogue
+    mbar_wait(&bars[3], ph);
+    tc_fence_after();
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(trow + c0, r);
+      tc_wait_ld();
+      if (row < p.Nq) {
+        bf16* dst = p.O + (int64_t(b) * p.Nq + row) * p.ldo + h * DH + c0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]) * inv, __uint_as_float(r[8 * j + 1]) * inv);
+          v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * inv, __uint_as_float(r[8 * j + 3]) * inv);
+          v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * inv, __uint_as_float(r[8 * j + 5]) * inv);
+          v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * inv, __uint_as_float(r[8 * j + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 8 * j) = v;
+        }
+      }
+    }
+    if (p.lse != nullptr && row < p.Nq) p.lse[(int64_t(b) * p.H + h) * p.Nq + row] = mx * p.scale + logf(sum);
+    // every TMEM read of this item is done before the next item's S MMAs overwrite the accumulator, and this stage's
+    // shared memory may be refilled by the TMA issued at the top of the next-but-one iteration
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// =====================================================================================================================
 // backward
 // =====================================================================================================================
 struct AttnTcBwdParams {
@@ -956,6 +1130,32 @@ int attn_tc_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
     configured = true;
   }
   launch_k(attn_tc_fwd_kernel, dim3(H, B), 128, SMEM, st, tq, tk, tv, p);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+// experimental persistent forward (bit 4 of mmae_attention_set_tc), same contract as attn_tc_forward
+int attn_tc_forward_persistent(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                               int64_t ldo, float* lse, int B, int H, int Nq, int Nk, float scale, cudaStream_t st) {
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_maps(&tq, q, ldq, B, Nq, H * DH)) || (rc = make_maps(&tk, k, ldk, B, Nk, H * DH)) ||
+      (rc = make_maps(&tv, v, ldv, B, Nk, H * DH)))
+    return rc;
+  AttnTcParams p;
+  p.Nq = Nq; p.Nk = Nk; p.H = H; p.scale = scale;
+  p.O = reinterpret_cast<bf16*>(o);
+  p.ldo = ldo;
+  p.lse = lse;
+  static bool configured = false;
+  if (!configured) {
+    MMAE_CUDA_OK(cudaFuncSetAttribute(attn_tc_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD2_SMEM));
+    configured = true;
+  }
+  const int items = B * H;
+  const int grid = std::min(items, 2 * sm_count());
+  launch_k(attn_tc_fwd_persistent_kernel, grid, 128, FWD2_SMEM, st, tq, tk, tv, p, items);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

@@ -2,6 +2,7 @@
 # First GPU-box visit of the next round: everything that was prepared after round 1's GPU budget ran out, in one call.
 #   1. GPU suite + smoke (regression check of the committed state)
 #   2. experimental depth-standardisation variant 2 against the oracle and variant 1 (correctness + timing)
+#   2b. experimental persistent encoder-attention forward: bit-identity with the default kernel + timing
 #   3. A/B of MMAE_GEMM_BALANCED_GRID (persistent GEMM grid = ceil(items / rounds)) on the headline bench
 #   4. K-sweep diagnostic of the K = 256 decoder GEMM shapes
 # Logs land in gpurun_out/; copy what is kept into profiles/rNN_*.
@@ -10,6 +11,7 @@ mkdir -p gpurun_out
 timeout 150 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
 timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"
 timeout 90 python scripts/gpu_check_depth_standardize_v2.py > gpurun_out/depth_standardize_v2.log 2>&1; echo "depth v2 rc=$?"; tail -6 gpurun_out/depth_standardize_v2.log
+timeout 120 python scripts/gpu_check_attention_v2.py > gpurun_out/attention_v2.log 2>&1; echo "attention v2 rc=$? (124 = hang: barrier protocol bug)"; tail -10 gpurun_out/attention_v2.log
 for v in 0 1; do
   MMAE_GEMM_BALANCED_GRID=$v timeout 90 python bench.py --steps 20 --warmup 5 --cpu-baseline 0 \
       --gemm-shapes gpurun_out/gemm_shapes_balanced$v.txt > gpurun_out/bench_balanced$v.json 2> gpurun_out/bench_balanced$v.err
