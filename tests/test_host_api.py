@@ -183,3 +183,22 @@ def test_c_abi_rejects_bad_arguments_before_any_launch():
         L.check(lib.mmae_gemm_bf16(16, 64, 0, 16, 64, 0, 128, 100, 64, 1, ctypes.byref(ep), None), "mmae_gemm_bf16")
     assert issubclass(L.MmaeError, RuntimeError)
     assert lib.mmae_standardize_depth_set_variant(1) == 0
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: nothing under multimae_b200/ (Python or CUDA sources) may import, load or name it,
+    nor read /root/reference; importing the whole package must not pull `oracle` into sys.modules."""
+    import subprocess
+    import sys
+    pkg = os.path.join(ROOT, "multimae_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert "multimae_oracle" not in text and "/root/reference" not in text, f
+    code = ("import sys; sys.path.insert(0, %r); import multimae_b200.multimae, multimae_b200.criterion, multimae_b200.optim, "
+            "multimae_b200.parallel, multimae_b200.train_step, multimae_b200.native_scaler, multimae_b200.overlay, "
+            "multimae_b200.kernels; assert not [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]; print('ok')" % ROOT)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
