@@ -154,6 +154,9 @@ int mmae_layernorm_backward_ex(const void* dy, int dy_is_bf16, int64_t lddy, con
  * 32/64; used for <= 128 keys, with 8 also for <= 256 keys), 4 = general tcgen05 backward; 0 = warp-MMA (mma.sync +
  * ldmatrix + cp.async) kernels everywhere.  Default 3 (env MMAE_ATTN_TC). */
 int mmae_attention_set_tc(int enable);
+/* diagnostics for the warp-specialised kernels (attention_ws.cu): a device buffer of 64 x 16 int64 that CTA 0 of the next
+ * launches fills with clock64 stamps of its pipeline phases (slot 16 * item + phase); NULL switches it off. */
+int mmae_attention_ws_set_trace(long long* device_buffer);
 int mmae_attention_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                            void* o, int64_t ldo, float* lse, int B, int H, int Nq, int Nk, int head_dim,
                            float scale, void* stream);
@@ -320,7 +323,9 @@ int mmae_weight_mirror_register(const float* params_f32, void* mirror_bf16, int6
 int mmae_grad_unscale_norm(float* grads, int64_t n, const float* inv_scale_dev, float inv_scale, float post_scale,
                            float* out2, float* norm_out, void* stream);
 /* dyn_lr_step_dev (optional): device float[2] = {learning rate, step count}; when non-NULL it overrides the host
- * `lr` / `step` arguments so that a CUDA-graph replay picks up the current schedule values. */
+ * `lr` / `step` arguments so that a CUDA-graph replay picks up the current schedule values, and the call itself advances
+ * the step count by one on the device - unless found_inf_dev[0] != 0, in which case nothing is updated (GradScaler.step
+ * does not call optimizer.step() for a non-finite gradient, so skipped steps do not advance the bias correction). */
 int mmae_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, const float* found_inf_dev,
                     const float* dyn_lr_step_dev, void* stream);

@@ -135,6 +135,7 @@ SIGNATURES = {
                                            c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
                                            c_int, c_int, c_void_p]),
     "mmae_attention_set_tc": (c_int, [c_int]),
+    "mmae_attention_ws_set_trace": (c_int, [c_void_p]),
     "mmae_attention_forward": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p,
                                        c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "mmae_attention_backward": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p,

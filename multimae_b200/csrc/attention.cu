@@ -20,6 +20,20 @@ void count_launch();
 bool attn_tc_supported(int Nq, int Nk, int head_dim);
 bool attn_tc_fwd_gen_supported(int H, int Nq, int Nk, int head_dim);
 bool attn_tc_bwd_gen_supported(int H, int Nq, int Nk, int head_dim);
+bool attn_ws_fwd_supported(int H, int Nq, int Nk, int head_dim);
+bool attn_ws_bwd_supported(int H, int Nq, int Nk, int head_dim);
+int attn_ws_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                    float* lse, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
+int attn_ws_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+                     int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                     void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
+bool attn_ws_fwd_supported(int H, int Nq, int Nk, int head_dim);
+bool attn_ws_bwd_supported(int H, int Nq, int Nk, int head_dim);
+int attn_ws_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                    float* lse, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
+int attn_ws_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
+                     int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                     void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
 int attn_tc_backward_gen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
                          int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
                          void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
@@ -549,6 +563,9 @@ extern "C" int mmae_attention_forward(const void* q, int64_t ldq, const void* k,
              MMAE_ERR_ARG, "mmae_attention_forward: 16-byte alignment / ld %% 8 required");
   dim3 grid(ceil_div(Nq, ATT_ROWS), H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // bit 5 (32): warp-specialised persistent tcgen05 forward (attention_ws.cu) for every shape it supports
+  if ((g_attn_tc & 32) && attn_ws_fwd_supported(H, Nq, Nk, head_dim))
+    return attn_ws_forward(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, head_dim, scale, st);
   if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim)) {
     if (g_attn_tc & 16)   // experimental persistent variant (attention_tc.cu), never on by default
       return attn_tc_forward_persistent(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, scale, st);
@@ -590,6 +607,17 @@ extern "C" int mmae_attention_backward(const void* q, int64_t ldq, const void* k
   const bf16 *qp = (const bf16*)q, *kp = (const bf16*)k, *vp = (const bf16*)v, *op = (const bf16*)o,
              *dop = (const bf16*)d_o;
   dim3 gq(ceil_div(Nq, ATT_ROWS), H, B), gk(ceil_div(Nk, ATT_ROWS), H, B);
+  // bit 6 (64): warp-specialised persistent tcgen05 backward (attention_ws.cu): one kernel, dV / dK / dQ accumulate in TMEM
+  if ((g_attn_tc & 64) && attn_ws_bwd_supported(H, Nq, Nk, head_dim)) {
+    if (head_dim == 64)
+      launch_k(attn_delta_kernel<64>, delta_grid(B, Nq, H, 64), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
+    else
+      launch_k(attn_delta_kernel<32>, delta_grid(B, Nq, H, 32), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
+    count_launch();
+    MMAE_LAUNCH_OK();
+    return attn_ws_backward(q, ldq, k, ldk, v, ldv, d_o, lddo, lse, delta_ws, dq, lddq, dk, lddk, dv, lddv, B, H, Nq, Nk,
+                            head_dim, scale, st);
+  }
   if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim)) {
     launch_k(attn_delta_kernel<64>, delta_grid(B, Nq, H, 64), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
     count_launch();

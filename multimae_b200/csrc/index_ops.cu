@@ -54,7 +54,9 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(mmae_embed_layout L, 
       const int y = ph * P + py, x = pw * P + px;
       if (L.is_semseg[t]) {
         const int64_t label = reinterpret_cast<const int64_t*>(in.data[t])[(int64_t(b) * Ht + y) * Wt + x];
-        v = __float2bfloat16_rn(__ldg(in.class_emb[t] + label * C + c));
+        // a label outside [0, num_classes) (e.g. a 255 / -100 "ignore" label in a pseudo-label map) embeds as zeros instead
+        // of reading out of bounds (nn.Embedding would raise a device-side assert, multimae/input_adapters.py:229)
+        if (label >= 0 && label < L.num_classes[t]) v = __float2bfloat16_rn(__ldg(in.class_emb[t] + label * C + c));
       } else {
         v = __float2bfloat16_rn(__ldg(reinterpret_cast<const float*>(in.data[t]) + ((int64_t(b) * C + c) * Ht + y) * Wt + x));
       }
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(256) semseg_emb_bwd_kernel(const bf16* __restr
     for (int k = threadIdx.x; k < E * P * P; k += blockDim.x) {
       const int e = k / (P * P), py = (k / P) % P, px = k % P;
       const int64_t label = labels[(int64_t(b) * Ht + ph * P + py) * Wt + pw * P + px];
-      atomicAdd(&tab[label * E + e], __bfloat162float(dA[int64_t(r) * ld_dA + k]));
+      if (label >= 0 && label < num_classes) atomicAdd(&tab[label * E + e], __bfloat162float(dA[int64_t(r) * ld_dA + k]));
     }
   }
   __syncthreads();

@@ -22,6 +22,11 @@ void count_launch();
 // few cache lines serialise in one or two L2 slices (measured: 592 blocks x 256 columns = 45 us for a 13 MB column sum),
 // and the result is deterministic.
 float* colred_scratch(size_t floats, cudaStream_t st);   // nullptr + last error if it cannot be provided
+// the scratch buffers carry a zeroed header of ticket counters in front of the partial rows ("last block adds up")
+constexpr size_t COLRED_HEADER_FLOATS = 1024;
+inline unsigned int* colred_counters(float* partial) {
+  return partial ? reinterpret_cast<unsigned int*>(partial - COLRED_HEADER_FLOATS) : nullptr;
+}
 int colred_finalize(const float* partial, int Y, int ld, int seg, float* dst0, float* dst1, float* dst2, cudaStream_t st);
 
 // same with up to 9 destinations of `seg` columns each (null entries are skipped)

@@ -160,15 +160,18 @@ __global__ void __launch_bounds__(LOSS_THREADS) ce_loss_kernel(const float* __re
     }
     const float lse = m + logf(s);
     const int64_t tcls = target[int64_t(b) * HW + off];
+    // F.cross_entropy's ignore_index (-100 by default, multimae/criterion.py:52): a label outside [0, C) contributes no
+    // loss and no gradient (the pixel still counts in the mask denominator, as in the reference)
+    const bool ignored = tcls < 0 || tcls >= C;
     if constexpr (BWD) {
       const float inv = 1.0f / s;
 #pragma unroll 8
       for (int c = 0; c < C; ++c) {
         const float p = __expf(__ldg(lb + int64_t(c) * HW + off) - m) * inv;
         const float y = (c == tcls ? 1.f - smoothing : 0.f) + smoothing / C;
-        dlogits[int64_t(b) * C * HW + c * HW + off] = (p - y) * gscale;
+        dlogits[int64_t(b) * C * HW + c * HW + off] = ignored ? 0.f : (p - y) * gscale;
       }
-    } else {
+    } else if (!ignored) {
       const float nll = lse - lb[tcls * HW + off];
       acc += (1.f - smoothing) * nll + smoothing * (lse - sum_logits / C);
     }

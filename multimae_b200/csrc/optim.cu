@@ -63,6 +63,13 @@ __global__ void __launch_bounds__(256) unscale_norm_kernel(float* __restrict__ g
 __global__ void sqrt_kernel(const float* __restrict__ in, float* __restrict__ norm_out) {
   pdl_prologue(); norm_out[0] = sqrtf(in[0]); }
 
+// device-side step counter: dyn[1] advances by one unless the step is skipped (non-finite gradients), like GradScaler.step,
+// which does not call optimizer.step() at all in that case - the bias correction must not see skipped steps
+__global__ void adamw_advance_kernel(float* __restrict__ dyn, const float* __restrict__ found_inf) {
+  pdl_prologue();
+  if (found_inf == nullptr || found_inf[0] == 0.f) dyn[1] += 1.0f;
+}
+
 // decoupled weight decay AdamW, skipping the whole update when found_inf[0] != 0 (GradScaler.step semantics)
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                     float* __restrict__ v, int64_t n, float lr, float beta1, float beta2,
@@ -154,6 +161,11 @@ extern "C" int mmae_adamw_step(float* params, const float* grads, float* exp_avg
   const int64_t cap = int64_t(sm_count()) * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  if (dyn_lr_step_dev != nullptr) {
+    launch_k(adamw_advance_kernel, 1, 1, 0, reinterpret_cast<cudaStream_t>(stream), const_cast<float*>(dyn_lr_step_dev), found_inf_dev);
+    count_launch();
+    MMAE_LAUNCH_OK();
+  }
   launch_k(adamw_kernel, (unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream), params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, found_inf_dev, dyn_lr_step_dev,
       const_cast<bf16*>(mirror_lookup(params)));
   count_launch();

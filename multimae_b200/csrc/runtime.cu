@@ -146,6 +146,26 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
   return MMAE_OK;
 }
 
+// 3D bf16 store map [d2][d1][d0] (element strides s1, s2): box b0 x b1 x b2 with b0 * 2 bytes = the swizzle span
+// (128: SWIZZLE_128B, 64: SWIZZLE_64B); out-of-bounds parts of a stored box are clipped by the TMA unit
+int make_tmap_3d_bf16_store(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1,
+                            uint64_t s2, uint32_t b0, uint32_t b1, uint32_t b2) {
+  encode_tiled_fn fn = get_encode_fn();
+  if (!fn) return MMAE_ERR_CUDA;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1 * 2, s2 * 2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = b0 * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (b0 * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled(3d store) failed: %d", (int)r);
+    return MMAE_ERR_CUDA;
+  }
+  return MMAE_OK;
+}
+
 }  // namespace mmae
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -9,7 +9,6 @@ the model (zeroed once per forward), and the per-parameter views are what backwa
 """
 import ctypes
 import weakref
-import math
 
 import torch
 
@@ -67,11 +66,18 @@ class GradArena:
         self.flat = torch.zeros(max(off, 4), dtype=torch.float32, device=device)
         self.views = {name: self.flat[o:o + n].view(shape) for name, (o, n, shape) in self.offsets.items()}
         self.owned = False     # True: p.grad aliases the views and backward returns None for parameters
+        self.accumulating = False   # True between scaler(update_grad=False) calls: the next forward must not zero the arena
         self.reducer = None    # parallel.FlatGradReducer exchanging this arena between ranks (attach_data_parallel)
         _ARENAS.add(self)
 
     def zero_(self):
         self.flat.zero_()
+
+    def begin_step(self):
+        """Called by the model at the start of a training forward: one memset, unless a gradient accumulation over several
+        forward/backward passes is in progress (NativeScalerWithGradNormCount(..., update_grad=False))."""
+        if not self.accumulating:
+            self.flat.zero_()
 
     def view(self, name):
         return self.views[name]
@@ -491,5 +497,3 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, lr, betas, eps, weight_decay,
                                     float(weight_decay), max(int(step), 1), L.ptr(found_inf), L.ptr(dyn),
                                     L.current_stream()), "mmae_adamw_step")
 
-
-_ = math

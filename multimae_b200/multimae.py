@@ -324,7 +324,7 @@ class MultiMAE(nn.Module):
         if torch.is_grad_enabled() and self.training:
             if AUTO_OWN_GRADIENTS and not arena.owned:
                 self.own_gradients(True)
-            arena.zero_()
+            arena.begin_step()
         seq = _embed(adapters, x, ids_keep, self.global_tokens, arena, lambda d: "input_adapters.%s." % d,
                      self._grad_callback)
         encoder_tokens = self.encoder(seq)
@@ -388,7 +388,7 @@ class MultiViT(MultiMAE):
         ids = torch.arange(total, device=dev).unsqueeze(0).expand(B, -1).contiguous()
         arena = self.grad_arena(dev)
         if torch.is_grad_enabled() and self.training:
-            arena.zero_()
+            arena.begin_step()
         seq = _embed(adapters, x, ids, self.global_tokens, arena, lambda d: "input_adapters.%s." % d, self._grad_callback)
         return seq, input_info
 

@@ -46,6 +46,7 @@ class NativeScalerWithGradNormCount:
         self._growth_factor, self._backoff_factor, self._growth_interval = growth_factor, backoff_factor, growth_interval
         self._scale = None           # device tensors, created lazily on the loss's device
         self._growth_tracker = None
+        self._init_tracker = 0       # growth tracker restored by load_state_dict before the first step
         self._arena = None
         self._reducer = None
 
@@ -62,7 +63,7 @@ class NativeScalerWithGradNormCount:
     def _lazy_init(self, device):
         if self._scale is None:
             self._scale = torch.full((), self._init_scale if self._enabled else 1.0, dtype=torch.float32, device=device)
-            self._growth_tracker = torch.zeros((), dtype=torch.int32, device=device)
+            self._growth_tracker = torch.full((), int(self._init_tracker), dtype=torch.int32, device=device)
 
     def __call__(self, loss, optimizer, clip_grad=None, skip_grad=None, parameters=None, create_graph=False,
                  update_grad=True):
@@ -70,9 +71,12 @@ class NativeScalerWithGradNormCount:
         if parameters is not None and not isinstance(parameters, (list, tuple)):
             parameters = list(parameters)            # the script passes the generator model.parameters()
         (loss * self._scale if self._enabled else loss).backward(create_graph=create_graph)
-        if not update_grad:
-            return None
         arena = self._arena or _find_arena(optimizer, parameters)
+        if not update_grad:
+            # gradient accumulation (utils/native_scaler.py:25,39): keep what is in the flat buffer across the next forward
+            if arena is not None:
+                arena.accumulating = True
+            return None
         # the bucketed all-reduces started during backward are joined here; a reducer that was attached to the model
         # behind the script's back (overlay: DistributedDataParallel -> identity wrapper) is found through its arena
         reducer = self._reducer if self._reducer is not None else getattr(arena, "reducer", None)
@@ -94,6 +98,12 @@ class NativeScalerWithGradNormCount:
                     p.grad.mul_(inv)
             norm = get_grad_norm_(params)
             found_inf = (~torch.isfinite(norm)).float().reshape(1)
+        # GradScaler.unscale_(optimizer) (utils/native_scaler.py:34) covers EVERY parameter the optimizer holds, not only
+        # `parameters`: e.g. the uncertainty task balancer's log_vars sit in the optimizer but not in model.parameters().
+        # Unscale them too and fold their non-finite check into found_inf (they are not part of the returned norm, as in
+        # the reference, whose norm runs over `parameters` only).
+        if self._enabled:
+            found_inf = self._unscale_outside(optimizer, arena, None if arena is not None else params, inv, found_inf)
         if clip_grad is not None:
             assert parameters is not None or arena is not None
             coef = torch.clamp(clip_grad / (norm + 1e-6), max=1.0)
@@ -111,7 +121,46 @@ class NativeScalerWithGradNormCount:
         elif float(found_inf) == 0.0:    # host sync, as GradScaler.step does for stock optimizers
             optimizer.step()
         self._update(found_inf)
+        if arena is not None:
+            arena.accumulating = False
         return norm
+
+    def _unscale_outside(self, optimizer, arena, handled, inv, found_inf):
+        key = (id(optimizer), id(arena), sum(len(g["params"]) for g in getattr(optimizer, "param_groups", [])))
+        cached = getattr(self, "_outside_cache", None)
+        if arena is not None and arena.owned and cached is not None and cached[0] == key:
+            outside = cached[1]                            # owned arena: which gradients alias it never changes
+        else:
+            lo = hi = None
+            if arena is not None:
+                lo = arena.flat.data_ptr()
+                hi = lo + arena.flat.numel() * arena.flat.element_size()
+            seen = {id(p) for p in (handled or [])}
+            outside = []
+            for group in getattr(optimizer, "param_groups", []):
+                for p in group["params"]:
+                    g = p.grad
+                    if id(p) in seen or (g is None and not (arena is not None and arena.owned)):
+                        continue
+                    if g is not None and lo is not None and g.device == arena.flat.device and lo <= g.data_ptr() < hi:
+                        continue                           # lives in the flat buffer: already unscaled and checked
+                    seen.add(id(p))
+                    outside.append(p)
+            if arena is not None and arena.owned:
+                self._outside_cache = (key, outside)
+        bad = None
+        a_lo = arena.flat.data_ptr() if arena is not None else 0
+        a_hi = a_lo + (arena.flat.numel() * arena.flat.element_size() if arena is not None else 0)
+        for p in outside:
+            g = p.grad
+            if g is None or a_lo <= g.data_ptr() < a_hi:
+                continue
+            g.mul_(inv.to(g.device))
+            flag = (~torch.isfinite(g).all()).float().reshape(1)
+            bad = flag if bad is None else torch.maximum(bad, flag.to(bad.device))
+        if bad is None:
+            return found_inf
+        return torch.maximum(found_inf, bad.to(found_inf.device))
 
     def _update(self, found_inf):
         if not self._enabled:
@@ -138,6 +187,7 @@ class NativeScalerWithGradNormCount:
         self._growth_factor = state_dict.get("growth_factor", self._growth_factor)
         self._backoff_factor = state_dict.get("backoff_factor", self._backoff_factor)
         self._growth_interval = state_dict.get("growth_interval", self._growth_interval)
+        self._init_tracker = int(state_dict.get("_growth_tracker", 0))   # resume order: loaded before the first step
         if self._scale is not None:
             self._scale.fill_(self._init_scale)
-            self._growth_tracker.fill_(int(state_dict.get("_growth_tracker", 0)))
+            self._growth_tracker.fill_(self._init_tracker)

@@ -1,7 +1,12 @@
 """Flat-buffer AdamW: parameters live as views of one fp32 buffer, gradients in the model's
 GradArena, so the update of all ~98 M parameters is ONE kernel (mmae_adamw_step) instead of per-tensor loops, and a
 non-finite step is skipped on the device.  Same update rule / hyper-parameter semantics as torch.optim.AdamW as the
-reference builds it (utils/optim_factory.py:155-174; betas (0.9, 0.95), weight_decay 0.05 on every parameter)."""
+reference builds it (utils/optim_factory.py:155-174; betas (0.9, 0.95), weight_decay 0.05 on every parameter).
+
+Checkpoints: `state_dict()` / `load_state_dict()` use torch.optim.AdamW's per-parameter layout ({step, exp_avg,
+exp_avg_sq} per parameter index, sliced out of / copied into the flat moment buffers), so utils.save_model /
+auto_load_model (utils/checkpoint.py:85,124-133) resume this optimizer - and a checkpoint written by the stock AdamW over
+the same parameter order loads here, and vice versa."""
 import torch
 
 from . import _lib as L
@@ -10,7 +15,8 @@ from . import functional as Fn
 
 class FlatAdamW(torch.optim.Optimizer):
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05):
-        params = [p for p in model.parameters() if p.requires_grad]
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        params = [p for _, p in named]
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, lr_scale=1.0))
         arena = model.own_gradients(True)
         self.mmae_arena = arena
@@ -18,9 +24,7 @@ class FlatAdamW(torch.optim.Optimizer):
         # re-home the parameters into one flat buffer laid out exactly like the gradient arena
         self.flat_params = torch.zeros_like(arena.flat)
         with torch.no_grad():
-            for n, p in model.named_parameters():
-                if not p.requires_grad:
-                    continue
+            for n, p in named:
                 o, numel, shape = arena.offsets[n]
                 view = self.flat_params[o:o + numel].view(shape)
                 view.copy_(p.data.to(dev))
@@ -31,6 +35,7 @@ class FlatAdamW(torch.optim.Optimizer):
         self._mirror_version = None
         self._invalidations = 0
         self._flat_views = params
+        self._named = named
         if dev.type == "cuda":
             self.flat_bf16 = torch.empty(self.flat_params.numel(), dtype=torch.bfloat16, device=dev)
             L.check(L.lib().mmae_weight_mirror_register(self.flat_params.data_ptr(), self.flat_bf16.data_ptr(),
@@ -43,7 +48,42 @@ class FlatAdamW(torch.optim.Optimizer):
         self._dyn = torch.zeros(2, dtype=torch.float32, device=dev)
         self._lr_host = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(1)
         self._lr_synced = None
+        self._bind_state()
         self.sync_hyperparams()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # optimizer state in torch.optim.AdamW's layout, as views of the flat buffers (checkpoint / resume contract)
+    # ------------------------------------------------------------------------------------------------------------
+    def _bind_state(self):
+        arena = self.mmae_arena
+        step = self._dyn[1]                      # 0-dim view of the device-side step counter, shared by every entry
+        for n, p in self._named:
+            o, numel, shape = arena.offsets[n]
+            self.state[p] = {"step": step, "exp_avg": self.exp_avg[o:o + numel].view(shape),
+                             "exp_avg_sq": self.exp_avg_sq[o:o + numel].view(shape)}
+
+    def load_state_dict(self, state_dict):
+        """torch.optim.AdamW-layout state -> flat moment buffers + device step counter; hyper-parameters as usual."""
+        super().load_state_dict(state_dict)      # validates sizes, restores param_groups, materialises per-parameter state
+        loaded_step = None
+        with torch.no_grad():
+            for n, p in self._named:
+                st = self.state.get(p)
+                if not st:
+                    continue
+                o, numel, shape = self.mmae_arena.offsets[n]
+                if "exp_avg" in st:
+                    self.exp_avg[o:o + numel].view(shape).copy_(st["exp_avg"])
+                if "exp_avg_sq" in st:
+                    self.exp_avg_sq[o:o + numel].view(shape).copy_(st["exp_avg_sq"])
+                if "step" in st and loaded_step is None:
+                    loaded_step = float(st["step"])
+            if loaded_step is not None:
+                self._dyn[1].fill_(loaded_step)
+        self._bind_state()
+        self._lr_synced = None
+        self.sync_hyperparams()
+        self.invalidate_mirror()
 
     def _params_version(self):
         # in-place torch ops on a Parameter (copy_, load_state_dict, init) bump its counter; our kernels do not
@@ -89,10 +129,12 @@ class FlatAdamW(torch.optim.Optimizer):
 
     @torch.no_grad()
     def fused_step(self, found_inf=None):
+        """One kernel over the flat buffers.  The step counter lives on the device and is advanced by the call itself,
+        only when the step is taken (found_inf == 0): a skipped step leaves moments, parameters AND the bias correction
+        untouched, like GradScaler.step."""
         g = self.param_groups[0]
         if not (self._dyn.is_cuda and torch.cuda.is_current_stream_capturing()):
             self.sync_hyperparams()
-        self._dyn[1:2].add_(1.0)            # device-side step counter (captured and replayed with the graph)
         Fn.adamw_step(self.flat_params, self.mmae_arena.flat, self.exp_avg, self.exp_avg_sq, g["lr"] * g.get("lr_scale", 1.0),
                       g["betas"], g["eps"], g["weight_decay"], 1, found_inf, dyn=self._dyn)
 
@@ -101,5 +143,8 @@ class FlatAdamW(torch.optim.Optimizer):
         self.fused_step(None)
 
     def zero_grad(self, set_to_none=True):
-        """Gradients are zeroed by the model at the start of every forward (one memset of the arena)."""
+        """Gradients alias the model's arena, which the model zeroes (one memset) at the start of the next training
+        forward - unless an accumulation is in progress (NativeScalerWithGradNormCount(update_grad=False)); after a step the
+        accumulation is over."""
+        self.mmae_arena.accumulating = False
         return None

@@ -17,17 +17,27 @@ import types
 
 
 class _IdentityDDP:
-    """Stands in for DistributedDataParallel (run_pretraining_multimae.py:380-383): gradients are reduced in place by
-    multimae_b200.parallel.FlatGradReducer, so no wrapper logic is needed.  Exposes `.module` like DDP does."""
+    """Stands in for DistributedDataParallel (run_pretraining_multimae.py:380-383) around a MultiMAE: gradients are reduced
+    in place by multimae_b200.parallel.FlatGradReducer, so no wrapper logic is needed.  Exposes `.module` like DDP does.
+    Any OTHER module the script wraps (the task balancer, run_pretraining_multimae.py:384-386) keeps the real
+    DistributedDataParallel: its few parameters are outside the flat arena and must still be averaged across ranks."""
+
+    _real = None          # torch's own class, saved by install() before the substitution
 
     def __new__(cls, module, *args, **kwargs):
         import torch
         from .multimae import MultiMAE
         from .parallel import attach_data_parallel, broadcast_parameters
-        if isinstance(module, MultiMAE) and torch.distributed.is_initialized():
-            broadcast_parameters(module)
-            module._mmae_reducer = attach_data_parallel(module)
+        if isinstance(module, MultiMAE):
+            if torch.distributed.is_initialized():
+                broadcast_parameters(module)
+                module._mmae_reducer = attach_data_parallel(module)
             return _Wrapped(module)
+        trainable = any(p.requires_grad for p in module.parameters())
+        if cls._real is not None and trainable and torch.distributed.is_initialized():
+            if not any(p.is_cuda for p in module.parameters()):
+                kwargs.pop("device_ids", None)
+            return cls._real(module, *args, **kwargs)
         return _Wrapped(module)
 
 
@@ -99,6 +109,8 @@ def install(reference_root=None, replace_ddp=True, legacy_checkpoint_load=True):
         pass
     if replace_ddp:
         import torch
+        if torch.nn.parallel.DistributedDataParallel is not _IdentityDDP:
+            _IdentityDDP._real = torch.nn.parallel.DistributedDataParallel
         torch.nn.parallel.DistributedDataParallel = _IdentityDDP
     return pkg
 
