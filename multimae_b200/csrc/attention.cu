@@ -24,16 +24,18 @@ bool attn_ws_fwd_supported(int H, int Nq, int Nk, int head_dim);
 bool attn_ws_bwd_supported(int H, int Nq, int Nk, int head_dim);
 int attn_ws_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                     float* lse, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
-int attn_ws_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
-                     int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
-                     void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
+int attn_ws_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
+                     int64_t ldo, const void* d_o, int64_t lddo, const float* lse, void* dq, int64_t lddq, void* dk,
+                     int64_t lddk, void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale,
+                     cudaStream_t st);
 bool attn_ws_fwd_supported(int H, int Nq, int Nk, int head_dim);
 bool attn_ws_bwd_supported(int H, int Nq, int Nk, int head_dim);
 int attn_ws_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                     float* lse, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
-int attn_ws_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
-                     int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
-                     void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
+int attn_ws_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
+                     int64_t ldo, const void* d_o, int64_t lddo, const float* lse, void* dq, int64_t lddq, void* dk,
+                     int64_t lddk, void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale,
+                     cudaStream_t st);
 int attn_tc_backward_gen(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
                          int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
                          void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st);
@@ -542,14 +544,19 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 using namespace mmae;
 
 // bit 0: fused single-tile tcgen05 kernels (encoder shape) ; bit 1: general tcgen05 forward (query tiles, <= 256 keys,
-// head_dim 32/64) ; bit 2: general tcgen05 backward (measured slower than the warp-MMA backward at N = 196: off).
-// 0 = warp-MMA kernels everywhere.  Default 3.
+// head_dim 32/64) ; bit 2: general tcgen05 backward (measured slower than the warp-MMA backward at N = 196: off) ;
+// bit 5 (32) / bit 6 (64): warp-specialised persistent tcgen05 forward / backward (attention_ws.cu).
+// 0 = warp-MMA kernels everywhere.  Default 3 | 64: measured on B200 at bs 128 (scripts/gpu_check_attention_ws.py) the
+// warp-specialised backward takes 43.8 us (encoder 99 x 99 x 64; was 76.5 with the delta kernel), 77.7 us (decoder
+// 196 x 196 x 32; was 130.8 on mma.sync) and 44.3 us (196 x 99 x 32; was 77.7); the warp-specialised forward does not beat
+// the one-CTA-per-item kernels yet (32.8 vs 27.2 us encoder, 50.2 vs 52.3 us at 196 keys) and stays opt-in.
 static int g_attn_tc = []() {
   const char* e = getenv("MMAE_ATTN_TC");
-  return e ? atoi(e) : 3;
+  return e ? atoi(e) : (3 | 64);
 }();
+static const int g_attn_tc_default = g_attn_tc;
 extern "C" int mmae_attention_set_tc(int enable) {
-  g_attn_tc = enable;
+  g_attn_tc = enable < 0 ? g_attn_tc_default : enable;   // negative: back to the start-up default (MMAE_ATTN_TC or 3 | 64)
   return MMAE_OK;
 }
 
@@ -608,16 +615,10 @@ extern "C" int mmae_attention_backward(const void* q, int64_t ldq, const void* k
              *dop = (const bf16*)d_o;
   dim3 gq(ceil_div(Nq, ATT_ROWS), H, B), gk(ceil_div(Nk, ATT_ROWS), H, B);
   // bit 6 (64): warp-specialised persistent tcgen05 backward (attention_ws.cu): one kernel, dV / dK / dQ accumulate in TMEM
-  if ((g_attn_tc & 64) && attn_ws_bwd_supported(H, Nq, Nk, head_dim)) {
-    if (head_dim == 64)
-      launch_k(attn_delta_kernel<64>, delta_grid(B, Nq, H, 64), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
-    else
-      launch_k(attn_delta_kernel<32>, delta_grid(B, Nq, H, 32), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
-    count_launch();
-    MMAE_LAUNCH_OK();
-    return attn_ws_backward(q, ldq, k, ldk, v, ldv, d_o, lddo, lse, delta_ws, dq, lddq, dk, lddk, dv, lddv, B, H, Nq, Nk,
+  // (delta = rowsum(dO o O) is computed inside the kernel from the staged tiles: no delta launch)
+  if ((g_attn_tc & 64) && attn_ws_bwd_supported(H, Nq, Nk, head_dim))
+    return attn_ws_backward(q, ldq, k, ldk, v, ldv, o, ldo, d_o, lddo, lse, dq, lddq, dk, lddk, dv, lddv, B, H, Nq, Nk,
                             head_dim, scale, st);
-  }
   if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim)) {
     launch_k(attn_delta_kernel<64>, delta_grid(B, Nq, H, 64), 256, 0, st, op, ldo, dop, lddo, delta_ws, Nq, H, int64_t(B) * Nq);
     count_launch();

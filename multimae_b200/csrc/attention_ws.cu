@@ -378,10 +378,11 @@ struct WsBwdParams {
 
 struct WsBwdCfg {
   static constexpr int STAGES = 2;
-  static constexpr int STAGE_BYTES = 4 * TILE_BYTES;                   // Q | dO | K | V
+  static constexpr int STAGE_BYTES = 5 * TILE_BYTES;                   // Q | dO | K | V | O
   static constexpr int P_OFF = STAGES * STAGE_BYTES;                    // P : two 64-key panels
   static constexpr int DS_OFF = P_OFF + 2 * TILE_BYTES;                 // dS: two 64-key panels
-  static constexpr int BAR_OFF = DS_OFF + 2 * TILE_BYTES;
+  static constexpr int X_OFF = DS_OFF + 2 * TILE_BYTES;                 // delta exchange: 2 x 128 floats
+  static constexpr int BAR_OFF = X_OFF + 1024;
   static constexpr int SMEM = BAR_OFF + 256 + 1024;
   static_assert(SMEM <= 232448, "backward exceeds 227 KB of shared memory");
   // TMEM columns: S [0,128)  dP [128,256)  dV [256,320)  dK [320,384)  dQ of query tile t [384 + 64 t, +64), t < 2
@@ -393,6 +394,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attn_ws_bwd_kernel(const __grid
                                                                     const __grid_constant__ CUtensorMap tmK,
                                                                     const __grid_constant__ CUtensorMap tmV,
                                                                     const __grid_constant__ CUtensorMap tmdO,
+                                                                    const __grid_constant__ CUtensorMap tmO,
                                                                     const __grid_constant__ CUtensorMap tmdQ,
                                                                     const __grid_constant__ CUtensorMap tmdK,
                                                                     const __grid_constant__ CUtensorMap tmdV,
@@ -404,6 +406,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attn_ws_bwd_kernel(const __grid
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sP = smem + C::P_OFF;
   uint8_t* sdS = smem + C::DS_OFF;
+  float* xdel = reinterpret_cast<float*>(smem + C::X_OFF);       // [2][128]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
   uint64_t* empty = full + STAGES;
   uint64_t* sdp_full = empty + STAGES;
@@ -420,6 +423,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attn_ws_bwd_kernel(const __grid
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
       tma_prefetch_desc(&tmdO);
+      tma_prefetch_desc(&tmO);
       tma_prefetch_desc(&tmdQ);
       tma_prefetch_desc(&tmdK);
       tma_prefetch_desc(&tmdV);
@@ -464,6 +468,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attn_ws_bwd_kernel(const __grid
             tma_load_3d(st + TILE_BYTES, &tmdO, &full[s], tile_col, qt * TQ, b);
             tma_load_3d(st + 2 * TILE_BYTES, &tmK, &full[s], tile_col, kt * TQ, b);
             tma_load_3d(st + 3 * TILE_BYTES, &tmV, &full[s], tile_col, kt * TQ, b);
+            tma_load_3d(st + 4 * TILE_BYTES, &tmO, &full[s], tile_col, qt * TQ, b);
           }
       }
     }
@@ -530,6 +535,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attn_ws_bwd_kernel(const __grid
     const float sl2 = p.scale * LOG2E_F;
     const bool is_issuer = cw == 0 && lane == 0;    // the compute thread that issues the TMA stores
     bool staged = false;                            // the previous block left gradient tiles in the P / dS buffers
+    float lse_next = int(blockIdx.x) < p.items && row < p.Nq ? __ldg(p.lse + int64_t(blockIdx.x) * p.Nq + row) : 0.f;
     int it = 0;
     for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
       const int h = item % p.H, b = item / p.H;
@@ -539,19 +545,54 @@ __global__ void __launch_bounds__(WS_THREADS, 1) attn_ws_bwd_kernel(const __grid
         for (int qt = 0; qt < p.q_tiles; ++qt, ++it) {
           const int qrow = qt * TQ + row;
           const bool row_ok = qrow < p.Nq;
-          // issued before the wait: these two global loads fly while S / dP are computed
-          const float lse2 = row_ok ? __ldg(p.lse + (int64_t(b) * p.H + h) * p.Nq + qrow) * LOG2E_F : INFINITY;   // +inf: P = 0
-          const float del = row_ok ? __ldg(p.delta + (int64_t(b) * p.H + h) * p.Nq + qrow) : 0.f;
+          // log-sum-exp of this row: loaded one block ahead (below), so its DRAM latency hides behind the previous block
+          const float lse2 = row_ok ? lse_next * LOG2E_F : INFINITY;   // +inf: P = 0
+          {
+            int qt_n = qt + 1, kt_n = kt, item_n = item;
+            if (qt_n == p.q_tiles) {
+              qt_n = 0;
+              if (++kt_n == p.k_tiles) {
+                kt_n = 0;
+                item_n += int(gridDim.x);
+              }
+            }
+            const int qrow_n = qt_n * TQ + row;
+            lse_next = item_n < p.items && qrow_n < p.Nq ? __ldg(p.lse + int64_t(item_n) * p.Nq + qrow_n) : 0.f;
+          }
           if (cw == 0 && lane == 0) trace_stamp(p.trace, it, 4);
+          // ---- delta = rowsum(dO o O) from the staged dO / O tiles (each thread: its half of the head's columns), exchanged
+          //      between the two threads of a row.  Replaces the separate delta kernel and its re-read of O and dO.
+          const int s = it % STAGES;
+          mbar_wait(&full[s], uint32_t(it / STAGES) & 1u);      // the TMA writes of this stage are visible to this thread
+          {
+            const uint8_t* sdO_t = smem + s * C::STAGE_BYTES + TILE_BYTES;
+            const uint8_t* sO_t = smem + s * C::STAGE_BYTES + 4 * TILE_BYTES;
+            constexpr int NCH = HD == 64 ? 4 : 2;                // 16-byte chunks per thread
+            const int ch0 = HD == 64 ? hf * 4 : (h & 1) * 4 + hf * 2;
+            float part = 0.f;
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) {
+              const uint4 a = *reinterpret_cast<const uint4*>(sdO_t + swz128(row, ch0 + j));
+              const uint4 o4 = *reinterpret_cast<const uint4*>(sO_t + swz128(row, ch0 + j));
+              const uint32_t* au = reinterpret_cast<const uint32_t*>(&a);
+              const uint32_t* ou = reinterpret_cast<const uint32_t*>(&o4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 x = unpack_bf16x2(au[e]), y = unpack_bf16x2(ou[e]);
+                part = fmaf(x.x, y.x, part);
+                part = fmaf(x.y, y.y, part);
+              }
+            }
+            xdel[hf * 128 + row] = part;
+          }
+          // P / dS buffers: the previous block's gradient MMAs have completed (grads_done awaited at the end of the
+          // previous iteration by every compute thread); gradient tiles staged there have been read by their TMA stores
+          if (staged && is_issuer) bulk_wait_read_all();
+          compute_bar();
+          const float del = xdel[row] + xdel[128 + row];
           mbar_wait(sdp_full, uint32_t(it) & 1u);
           tc_fence_after();
           if (cw == 0 && lane == 0) trace_stamp(p.trace, it, 5);
-          // P / dS buffers: the previous block's gradient MMAs have completed (grads_done awaited at the end of the
-          // previous iteration by every compute thread); gradient tiles staged there have been read by their TMA stores
-          if (staged) {
-            if (is_issuer) bulk_wait_read_all();
-            compute_bar();
-          }
 #pragma unroll
           for (int c0 = 0; c0 < 64; c0 += 32) {
             const int col = hf * 64 + c0;
@@ -658,7 +699,7 @@ int launch_ws_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
 }
 
 template <int HD>
-int launch_ws_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+int launch_ws_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo, const CUtensorMap& to,
                   const CUtensorMap& tdq, const CUtensorMap& tdk, const CUtensorMap& tdv, const WsBwdParams& p, cudaStream_t st) {
   auto kern = attn_ws_bwd_kernel<HD>;
   static bool configured = false;
@@ -666,7 +707,7 @@ int launch_ws_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMa
     MMAE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WsBwdCfg::SMEM));
     configured = true;
   }
-  launch_k(kern, dim3(std::min(p.items, sm_count())), WS_THREADS, WsBwdCfg::SMEM, st, tq, tk, tv, tdo, tdq, tdk, tdv, p);
+  launch_k(kern, dim3(std::min(p.items, sm_count())), WS_THREADS, WsBwdCfg::SMEM, st, tq, tk, tv, tdo, to, tdq, tdk, tdv, p);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;
@@ -707,14 +748,15 @@ int attn_ws_forward(const void* q, int64_t ldq, const void* k, int64_t ldk, cons
   return two ? launch_ws_fwd<32, 2>(tq, tk, tv, to, p, st) : launch_ws_fwd<32, 1>(tq, tk, tv, to, p, st);
 }
 
-int attn_ws_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* d_o,
-                     int64_t lddo, const float* lse, const float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk,
+int attn_ws_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
+                     int64_t ldo, const void* d_o, int64_t lddo, const float* lse, void* dq, int64_t lddq, void* dk, int64_t lddk,
                      void* dv, int64_t lddv, int B, int H, int Nq, int Nk, int head_dim, float scale, cudaStream_t st) {
-  CUtensorMap tq, tk, tv, tdo, tdq, tdk, tdv;
+  CUtensorMap tq, tk, tv, tdo, to, tdq, tdk, tdv;
   int rc;
   const int width = H * head_dim;
   if ((rc = make_maps(&tq, q, ldq, B, Nq, width)) || (rc = make_maps(&tk, k, ldk, B, Nk, width)) ||
       (rc = make_maps(&tv, v, ldv, B, Nk, width)) || (rc = make_maps(&tdo, d_o, lddo, B, Nq, width)) ||
+      (rc = make_maps(&to, o, ldo, B, Nq, width)) ||
       (rc = make_store_map(&tdq, dq, lddq, B, Nq, width, head_dim)) ||
       (rc = make_store_map(&tdk, dk, lddk, B, Nk, width, head_dim)) ||
       (rc = make_store_map(&tdv, dv, lddv, B, Nk, width, head_dim)))
@@ -725,12 +767,12 @@ int attn_ws_backward(const void* q, int64_t ldq, const void* k, int64_t ldk, con
   p.k_tiles = ceil_div(Nk, TQ);
   p.items = B * H;
   p.scale = scale;
-  p.lse = lse; p.delta = delta;
+  p.lse = lse; p.delta = nullptr;
   p.dQ = reinterpret_cast<bf16*>(dq); p.dK = reinterpret_cast<bf16*>(dk); p.dV = reinterpret_cast<bf16*>(dv);
   p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
   p.trace = g_ws_trace;
-  return head_dim == 64 ? launch_ws_bwd<64>(tq, tk, tv, tdo, tdq, tdk, tdv, p, st)
-                        : launch_ws_bwd<32>(tq, tk, tv, tdo, tdq, tdk, tdv, p, st);
+  return head_dim == 64 ? launch_ws_bwd<64>(tq, tk, tv, tdo, to, tdq, tdk, tdv, p, st)
+                        : launch_ws_bwd<32>(tq, tk, tv, tdo, to, tdq, tdk, tdv, p, st);
 }
 
 }  // namespace mmae

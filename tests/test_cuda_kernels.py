@@ -28,7 +28,7 @@ def KN():
     yield kernels
     L.lib().mmae_gemm_set_variant(-1)
     L.lib().mmae_gemm_set_tma_store(1)
-    L.lib().mmae_attention_set_tc(3)
+    L.lib().mmae_attention_set_tc(-1)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
@@ -181,10 +181,12 @@ def test_layernorm(dev, KN, shape):
 
 ATTN_CASES = [(3, 12, 99, 99, 64, True), (2, 8, 196, 99, 32, False), (2, 8, 196, 196, 32, True), (1, 2, 393, 393, 64, True),
               (1, 2, 130, 70, 32, False), (2, 1, 17, 5, 64, False), (2, 16, 99, 99, 64, True), (2, 3, 128, 128, 64, True),
-              (1, 2, 100, 33, 64, False)]
+              (1, 2, 100, 33, 64, False), (1, 2, 256, 256, 64, True), (1, 4, 200, 129, 32, False), (5, 8, 196, 196, 32, True)]
 
 
-@pytest.mark.parametrize("tc", [0, 1, 3, 7, 15])     # 15: every tcgen05 kernel wherever it is supported
+# 15: every one-CTA-per-item tcgen05 kernel wherever it is supported; 67: the default (warp-specialised backward);
+# 99: warp-specialised forward AND backward wherever supported (attention_ws.cu); 19: the persistent encoder forward
+@pytest.mark.parametrize("tc", [0, 1, 3, 7, 15, 19, 67, 99])
 @pytest.mark.parametrize("case", ATTN_CASES)
 def test_attention_forward_backward(dev, KN, tc, case):
     from multimae_b200 import _lib as L
