@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MMAE_ABI_VERSION 2
+#define MMAE_ABI_VERSION 3
 
 int mmae_abi_version(void);
 const char* mmae_last_error(void);
@@ -82,9 +82,9 @@ int mmae_gemm_set_variant(int variant);
 /* 1 (default): bf16-only epilogues of the persistent kernels leave through shared memory + TMA tile stores;
  * 0: per-lane global stores (kept for A/B measurements and for epilogues with extra operands).  Env MMAE_GEMM_TMA_STORE. */
 int mmae_gemm_set_tma_store(int enable);
-/* 1 (default): kernels are launched with programmatic stream serialization and start with griddepcontrol
- * (launch_dependents + wait), so the next kernel's blocks are scheduled while the previous one drains; 0: plain
- * stream order.  Env MMAE_PDL. */
+/* 1: kernels are launched with programmatic stream serialization and start with griddepcontrol (launch_dependents +
+ * wait), so the next kernel's blocks are scheduled while the previous one drains; 0 (default): plain stream order - a
+ * programmatically launched dependent keeps stale L1 lines for non-coherent loads (see runtime.cu).  Env MMAE_PDL. */
 int mmae_set_pdl(int enable);
 /* 1: mmae_block_backward runs its four weight-gradient GEMMs on a library-owned side stream, forked behind the kernel
  * that produces their dY operand and joined before the call returns (the caller's stream order is unchanged);
@@ -297,6 +297,48 @@ int mmae_dectail_backward(const float* dpred, int B, int nh, int nw, int Dd, int
                           float* d_out_w, float* d_out_b, float* dx, const void* saved, void* ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * fp32 tier for `fp32_output_adapters` (multimae/multimae.py:367-377: the listed output adapters run outside autocast;
+ * the shipped pre-training config lists ['semseg']).  Every activation stays fp32; Linear layers run as ONE bf16 tcgen05
+ * GEMM over 3-way split, K-concatenated operands (x_hi W_hi + x_hi W_lo + x_lo W_hi, fp32 accumulation: ~2^-16 relative),
+ * attention and GELU as fp32 CUDA-core kernels.  Same argument meaning as the bf16-tier entry points of the same name;
+ * the parameter / gradient structs are shared.  head_dim 32 only (the decoders').
+ * ---------------------------------------------------------------------------------------------- */
+int64_t mmae_linear_f32_workspace_bytes(int M, int N, int K);
+/* y[M,N] = x[M,K] W[N,K]^T (+ bias[N]) (+ residual[M,N]); N, K multiples of 8 */
+int mmae_linear_f32_forward(const float* x, const float* W, const float* bias, const float* residual, float* y, int M, int N,
+                            int K, void* ws, void* stream);
+/* dx[M,K] = dy W (when dx != NULL); dW[N,K] += dy^T x, db[N] += colsum(dy) (when dW / db != NULL); M, N, K multiples of 8 */
+int mmae_linear_f32_backward(const float* x, const float* W, const float* dy, float* dx, float* dW, float* db, int M, int N, int K,
+                             void* ws, void* stream);
+/* io = gelu(z) (backward = 0) or io *= gelu'(z) (backward = 1); exact erf form, n multiple of 4 */
+int mmae_gelu_f32(const float* z, float* io, int64_t n, int backward, void* stream);
+int mmae_attention_f32_forward(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, float* o,
+                               int64_t ldo, float* lse, int B, int H, int Nq, int Nk, int head_dim, float scale, void* stream);
+int mmae_attention_f32_backward(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                const float* o, int64_t ldo, const float* d_o, int64_t lddo, const float* lse, float* delta_ws,
+                                float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv, int B, int H, int Nq,
+                                int Nk, int head_dim, float scale, void* stream);
+int64_t mmae_block_f32_saved_bytes(int B, int N, int D, int H, int hidden);
+int64_t mmae_block_f32_workspace_bytes(int B, int N, int D, int H, int hidden);
+int mmae_block_f32_forward(const float* x_in, float* x_out, int B, int N, int D, int H, int hidden, float eps,
+                           const mmae_block_params* prm, void* saved, void* ws, void* stream);
+int mmae_block_f32_backward(const float* x_in, const float* dx_out, float* dx_in, int B, int N, int D, int H, int hidden,
+                            const mmae_block_params* prm, const mmae_block_grads* grads, const void* saved, void* ws,
+                            void* stream);
+int64_t mmae_dechead_f32_saved_bytes(const mmae_decoder_index* ix, int D_enc, int H, int hidden);
+int64_t mmae_dechead_f32_workspace_bytes(const mmae_decoder_index* ix, int D_enc, int H, int hidden);
+int mmae_dechead_f32_forward(const float* enc, int D_enc, const mmae_decoder_index* ix, int H, int hidden, float eps,
+                             const mmae_dechead_params* prm, float* x_out, void* saved, void* ws, void* stream);
+int mmae_dechead_f32_backward(const float* enc, int D_enc, const mmae_decoder_index* ix, int H, int hidden,
+                              const mmae_dechead_params* prm, const mmae_dechead_grads* grads, const float* dx_out,
+                              float* denc, const void* saved, void* ws, void* stream);
+int64_t mmae_dectail_f32_workspace_bytes(int B, int nh, int nw, int Dd, int C, int P);
+int mmae_dectail_f32_forward(const float* x, int B, int nh, int nw, int Dd, int C, int P, const float* out_w,
+                             const float* out_b, float* pred, void* ws, void* stream);
+int mmae_dectail_f32_backward(const float* x, const float* dpred, int B, int nh, int nw, int Dd, int C, int P,
+                              const float* out_w, float* d_out_w, float* d_out_b, float* dx, void* ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Masked reconstruction losses (multimae/criterion.py:37-57, 84-114, 141-171).
  * kind: 0 = MSE, 1 = L1, 2 = cross-entropy (pred = logits [B,C,H,W], target = int64 [B,H,W]).
  * mask: int64 [B, (H/scale)*(W/scale)] (non-zero = contributes) or NULL (plain mean).  ws: 2*B floats kept until
@@ -335,6 +377,7 @@ int mmae_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
 /* image <-> token layout helpers ('b (nh nw) (c ph pw) <-> b c (nh ph) (nw pw)') */
 int mmae_unpatchify(const float* tokens, int64_t ld_tok, float* image, int B, int C, int nh, int nw, int P,
                     void* stream);
+int mmae_patchify(const float* image, float* tokens, int64_t ld_tok, int B, int C, int nh, int nw, int P, void* stream);
 int mmae_unpatchify_bf16(const void* tokens_bf16, int64_t ld_tok, float* image, int B, int C, int nh, int nw, int P,
                          void* stream);
 int mmae_patchify_bf16(const float* image, void* tokens_bf16, int64_t ld_tok, int B, int C, int nh, int nw, int P,

@@ -181,11 +181,42 @@ SIGNATURES = {
     "mmae_unpatchify": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mmae_unpatchify_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mmae_patchify_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mmae_patchify": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    # ---- fp32 tier (fp32_output_adapters)
+    "mmae_linear_f32_workspace_bytes": (c_i64, [c_int] * 3),
+    "mmae_linear_f32_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "mmae_linear_f32_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                         c_void_p, c_void_p]),
+    "mmae_gelu_f32": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "mmae_attention_f32_forward": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p,
+                                           c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "mmae_attention_f32_backward": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p,
+                                            c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64,
+                                            c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "mmae_block_f32_saved_bytes": (c_i64, [c_int] * 5),
+    "mmae_block_f32_workspace_bytes": (c_i64, [c_int] * 5),
+    "mmae_block_f32_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                       ctypes.POINTER(BlockParams), c_void_p, c_void_p, c_void_p]),
+    "mmae_block_f32_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        ctypes.POINTER(BlockParams), ctypes.POINTER(BlockGrads), c_void_p, c_void_p,
+                                        c_void_p]),
+    "mmae_dechead_f32_saved_bytes": (c_i64, [ctypes.POINTER(DecoderIndex), c_int, c_int, c_int]),
+    "mmae_dechead_f32_workspace_bytes": (c_i64, [ctypes.POINTER(DecoderIndex), c_int, c_int, c_int]),
+    "mmae_dechead_f32_forward": (c_int, [c_void_p, c_int, ctypes.POINTER(DecoderIndex), c_int, c_int, c_float,
+                                         ctypes.POINTER(DecHeadParams), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmae_dechead_f32_backward": (c_int, [c_void_p, c_int, ctypes.POINTER(DecoderIndex), c_int, c_int,
+                                          ctypes.POINTER(DecHeadParams), ctypes.POINTER(DecHeadGrads), c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p]),
+    "mmae_dectail_f32_workspace_bytes": (c_i64, [c_int] * 6),
+    "mmae_dectail_f32_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]),
+    "mmae_dectail_f32_backward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmae_standardize_depth_set_variant": (c_int, [c_int]),
     "mmae_standardize_depth": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
 }
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 def lib():

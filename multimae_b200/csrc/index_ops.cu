@@ -364,10 +364,14 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(TokT* __restrict__ tok,
       }
     } else {
       const float4 v = __ldg(reinterpret_cast<const float4*>(ip));
-      uint2 o;
-      o.x = pack_bf16x2(v.x, v.y);
-      o.y = pack_bf16x2(v.z, v.w);
-      *reinterpret_cast<uint2*>(tp) = o;
+      if constexpr (sizeof(TokT) == 4) {
+        *reinterpret_cast<float4*>(tp) = v;
+      } else {
+        uint2 o;
+        o.x = pack_bf16x2(v.x, v.y);
+        o.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(tp) = o;
+      }
     }
   }
 }
@@ -536,6 +540,16 @@ extern "C" int mmae_unpatchify(const float* tokens, int64_t ld_tok, float* image
   MMAE_CHECK(tokens && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG, "mmae_unpatchify: bad args");
   MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_unpatchify: P and ld must be multiples of 4");
   launch_k(unpatchify_kernel<true, const float>, B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream), tokens, ld_tok, image, B, C, nh, nw, P);
+  count_launch();
+  MMAE_LAUNCH_OK();
+  return MMAE_OK;
+}
+
+extern "C" int mmae_patchify(const float* image, float* tokens, int64_t ld_tok, int B, int C, int nh, int nw, int P, void* stream) {
+  MMAE_CHECK(tokens && image && B > 0 && C > 0 && nh > 0 && nw > 0 && P > 0, MMAE_ERR_ARG, "mmae_patchify: bad args");
+  MMAE_CHECK(P % 4 == 0 && ld_tok % 4 == 0, MMAE_ERR_UNSUPPORTED, "mmae_patchify: P and ld must be multiples of 4");
+  launch_k(unpatchify_kernel<false, float>, B * nh, 256, 0, reinterpret_cast<cudaStream_t>(stream), tokens, ld_tok,
+           const_cast<float*>(image), B, C, nh, nw, P);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

@@ -219,9 +219,16 @@ extern "C" int mmae_weight_mirror_register(const float* params_f32, void* mirror
 }
 
 namespace mmae {
+// Programmatic dependent launch is OFF by default (MMAE_PDL=1 / mmae_set_pdl(1) turns it on).  Found in round 2: after
+// griddepcontrol.wait a non-coherent load (ld.global.nc, i.e. __ldg / const __restrict__ / L1::no_allocate streaming loads,
+// which most kernels here use for their inputs) can still hit a stale L1 line of a buffer the PREVIOUS kernel has just
+// rewritten - the L1 invalidation of an ordinary kernel boundary does not happen for a programmatically launched
+// dependent.  At the training shapes the lines are evicted by the ~100 MB every kernel streams, at small shapes (tests) the
+// fp32 attention kernels read stale gradients.  Captured CUDA graphs never used PDL (train_step.py), so the measured step
+// is unaffected; eager launches lose the ~3.5 % PDL gave them.
 static int g_pdl = []() {
   const char* e = getenv("MMAE_PDL");
-  return e ? atoi(e) : 1;
+  return e ? atoi(e) : 0;
 }();
 bool pdl_enabled() { return g_pdl != 0; }
 }  // namespace mmae

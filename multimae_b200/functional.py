@@ -144,12 +144,16 @@ class BlockFunction(torch.autograd.Function):
         H, hidden, eps = meta["heads"], meta["hidden"], meta["eps"]
         x = x.contiguous().float()
         lib = L.lib()
-        saved = torch.empty(lib.mmae_block_saved_bytes(B, N, D, H, hidden), dtype=torch.uint8, device=x.device)
-        ws = Workspace.get(lib.mmae_block_workspace_bytes(B, N, D, H, hidden), x.device)
+        # meta["fp32"]: the fp32 tier of `fp32_output_adapters` (3 x bf16 split GEMMs, fp32 attention / GELU)
+        f32 = "_f32" if meta.get("fp32") else ""
+        saved = torch.empty(getattr(lib, "mmae_block%s_saved_bytes" % f32)(B, N, D, H, hidden), dtype=torch.uint8,
+                            device=x.device)
+        ws = Workspace.get(getattr(lib, "mmae_block%s_workspace_bytes" % f32)(B, N, D, H, hidden), x.device)
         out = torch.empty_like(x)
         prm = L.BlockParams(*[p.data_ptr() for p in params])
-        L.check(lib.mmae_block_forward(x.data_ptr(), out.data_ptr(), B, N, D, H, hidden, eps, ctypes.byref(prm),
-                                       saved.data_ptr(), ws.data_ptr(), L.current_stream()), "mmae_block_forward")
+        L.check(getattr(lib, "mmae_block%s_forward" % f32)(x.data_ptr(), out.data_ptr(), B, N, D, H, hidden, eps,
+                                                           ctypes.byref(prm), saved.data_ptr(), ws.data_ptr(),
+                                                           L.current_stream()), "mmae_block%s_forward" % f32)
         ctx.meta = meta
         ctx.params = params
         ctx.save_for_backward(x, saved)
@@ -164,14 +168,15 @@ class BlockFunction(torch.autograd.Function):
         arena, prefix = meta["arena"], meta["prefix"]
         names = [prefix + n for n in BLOCK_PARAM_NAMES]
         lib = L.lib()
-        ws = Workspace.get(lib.mmae_block_workspace_bytes(B, N, D, H, hidden), x.device)
+        f32 = "_f32" if meta.get("fp32") else ""
+        ws = Workspace.get(getattr(lib, "mmae_block%s_workspace_bytes" % f32)(B, N, D, H, hidden), x.device)
         dout = dout.contiguous().float()
         dx = torch.empty_like(x)
         prm = L.BlockParams(*[p.data_ptr() for p in params])
         grd = L.BlockGrads(*[_grad_ptr(arena, n) for n in names])
-        L.check(lib.mmae_block_backward(x.data_ptr(), dout.data_ptr(), dx.data_ptr(), B, N, D, H, hidden,
-                                        ctypes.byref(prm), ctypes.byref(grd), saved.data_ptr(), ws.data_ptr(),
-                                        L.current_stream()), "mmae_block_backward")
+        L.check(getattr(lib, "mmae_block%s_backward" % f32)(x.data_ptr(), dout.data_ptr(), dx.data_ptr(), B, N, D, H, hidden,
+                                                            ctypes.byref(prm), ctypes.byref(grd), saved.data_ptr(),
+                                                            ws.data_ptr(), L.current_stream()), "mmae_block%s_backward" % f32)
         if meta.get("on_grads_ready") is not None:
             meta["on_grads_ready"](names)
         return (dx, None) + tuple(_ret_grads(arena, names, params))
@@ -313,13 +318,15 @@ class DecoderHeadFunction(torch.autograd.Function):
         prm = L.DecHeadParams()
         _fill_head_struct(prm, [p.data_ptr() for p in main], [None if p is None else p.data_ptr() for p in task])
         prm.pos = meta["pos"].data_ptr()
-        saved = torch.empty(lib.mmae_dechead_saved_bytes(ctypes.byref(ix), De, H, hidden), dtype=torch.uint8,
-                            device=enc.device)
-        ws = Workspace.get(lib.mmae_dechead_workspace_bytes(ctypes.byref(ix), De, H, hidden), enc.device)
+        f32 = "_f32" if meta.get("fp32") else ""
+        saved = torch.empty(getattr(lib, "mmae_dechead%s_saved_bytes" % f32)(ctypes.byref(ix), De, H, hidden),
+                            dtype=torch.uint8, device=enc.device)
+        ws = Workspace.get(getattr(lib, "mmae_dechead%s_workspace_bytes" % f32)(ctypes.byref(ix), De, H, hidden), enc.device)
         out = torch.empty((B, ix.num_queries, ix.dim), dtype=torch.float32, device=enc.device)
-        L.check(lib.mmae_dechead_forward(enc.data_ptr(), De, ctypes.byref(ix), H, hidden, eps, ctypes.byref(prm),
-                                         out.data_ptr(), saved.data_ptr(), ws.data_ptr(), L.current_stream()),
-                "mmae_dechead_forward")
+        L.check(getattr(lib, "mmae_dechead%s_forward" % f32)(enc.data_ptr(), De, ctypes.byref(ix), H, hidden, eps,
+                                                             ctypes.byref(prm), out.data_ptr(), saved.data_ptr(),
+                                                             ws.data_ptr(), L.current_stream()),
+                "mmae_dechead%s_forward" % f32)
         ctx.meta, ctx.params, ctx.ix = meta, params, ix
         ctx.save_for_backward(enc, saved, ids_keep, ids_restore)
         return out
@@ -340,12 +347,14 @@ class DecoderHeadFunction(torch.autograd.Function):
         prm.pos = meta["pos"].data_ptr()
         _fill_head_struct(grd, [_grad_ptr(arena, n) for n in names],
                           [None if n is None else _grad_ptr(arena, n) for n in task_names])
-        ws = Workspace.get(lib.mmae_dechead_workspace_bytes(ctypes.byref(ix), De, H, hidden), enc.device)
+        f32 = "_f32" if meta.get("fp32") else ""
+        ws = Workspace.get(getattr(lib, "mmae_dechead%s_workspace_bytes" % f32)(ctypes.byref(ix), De, H, hidden), enc.device)
         dout = dout.contiguous().float()
         denc = torch.zeros_like(enc)
-        L.check(lib.mmae_dechead_backward(enc.data_ptr(), De, ctypes.byref(ix), H, hidden, ctypes.byref(prm),
-                                          ctypes.byref(grd), dout.data_ptr(), denc.data_ptr(), saved.data_ptr(),
-                                          ws.data_ptr(), L.current_stream()), "mmae_dechead_backward")
+        L.check(getattr(lib, "mmae_dechead%s_backward" % f32)(enc.data_ptr(), De, ctypes.byref(ix), H, hidden,
+                                                              ctypes.byref(prm), ctypes.byref(grd), dout.data_ptr(),
+                                                              denc.data_ptr(), saved.data_ptr(), ws.data_ptr(),
+                                                              L.current_stream()), "mmae_dechead%s_backward" % f32)
         all_names = names + [n for n in task_names if n is not None]
         if meta.get("on_grads_ready") is not None:
             meta["on_grads_ready"](all_names)
@@ -364,12 +373,18 @@ class DecoderTailFunction(torch.autograd.Function):
         x = x.contiguous().float()
         B, _, Dd = x.shape
         nh, nw, C, P = meta["nh"], meta["nw"], meta["channels"], meta["patch"]
-        saved = torch.empty(lib.mmae_dectail_saved_bytes(B, nh, nw, Dd, C, P), dtype=torch.uint8, device=x.device)
-        ws = Workspace.get(lib.mmae_dectail_workspace_bytes(B, nh, nw, Dd, C, P), x.device)
         pred = torch.empty((B, C, nh * P, nw * P), dtype=torch.float32, device=x.device)
-        L.check(lib.mmae_dectail_forward(x.data_ptr(), B, nh, nw, Dd, C, P, weight.data_ptr(), bias.data_ptr(),
-                                         pred.data_ptr(), saved.data_ptr(), ws.data_ptr(), L.current_stream()),
-                "mmae_dectail_forward")
+        if meta.get("fp32"):      # fp32 tier: the input itself is what backward needs
+            ws = Workspace.get(lib.mmae_dectail_f32_workspace_bytes(B, nh, nw, Dd, C, P), x.device)
+            L.check(lib.mmae_dectail_f32_forward(x.data_ptr(), B, nh, nw, Dd, C, P, weight.data_ptr(), bias.data_ptr(),
+                                                 pred.data_ptr(), ws.data_ptr(), L.current_stream()), "mmae_dectail_f32_forward")
+            saved = x
+        else:
+            saved = torch.empty(lib.mmae_dectail_saved_bytes(B, nh, nw, Dd, C, P), dtype=torch.uint8, device=x.device)
+            ws = Workspace.get(lib.mmae_dectail_workspace_bytes(B, nh, nw, Dd, C, P), x.device)
+            L.check(lib.mmae_dectail_forward(x.data_ptr(), B, nh, nw, Dd, C, P, weight.data_ptr(), bias.data_ptr(),
+                                             pred.data_ptr(), saved.data_ptr(), ws.data_ptr(), L.current_stream()),
+                    "mmae_dectail_forward")
         ctx.meta, ctx.dims, ctx.params = meta, (B, nh, nw, Dd, C, P), (weight, bias)
         ctx.save_for_backward(saved)
         return pred
@@ -383,12 +398,18 @@ class DecoderTailFunction(torch.autograd.Function):
         weight, bias = ctx.params
         arena, prefix = meta["arena"], meta["prefix"]
         names = [prefix + "out_proj.weight", prefix + "out_proj.bias"]
-        ws = Workspace.get(lib.mmae_dectail_workspace_bytes(B, nh, nw, Dd, C, P), dpred.device)
         dpred = dpred.contiguous().float()
         dx = torch.empty((B, nh * nw, Dd), dtype=torch.float32, device=dpred.device)
-        L.check(lib.mmae_dectail_backward(dpred.data_ptr(), B, nh, nw, Dd, C, P, weight.data_ptr(),
-                                          _grad_ptr(arena, names[0]), _grad_ptr(arena, names[1]), dx.data_ptr(),
-                                          saved.data_ptr(), ws.data_ptr(), L.current_stream()), "mmae_dectail_backward")
+        if meta.get("fp32"):
+            ws = Workspace.get(lib.mmae_dectail_f32_workspace_bytes(B, nh, nw, Dd, C, P), dpred.device)
+            L.check(lib.mmae_dectail_f32_backward(saved.data_ptr(), dpred.data_ptr(), B, nh, nw, Dd, C, P, weight.data_ptr(),
+                                                  _grad_ptr(arena, names[0]), _grad_ptr(arena, names[1]), dx.data_ptr(),
+                                                  ws.data_ptr(), L.current_stream()), "mmae_dectail_f32_backward")
+        else:
+            ws = Workspace.get(lib.mmae_dectail_workspace_bytes(B, nh, nw, Dd, C, P), dpred.device)
+            L.check(lib.mmae_dectail_backward(dpred.data_ptr(), B, nh, nw, Dd, C, P, weight.data_ptr(),
+                                              _grad_ptr(arena, names[0]), _grad_ptr(arena, names[1]), dx.data_ptr(),
+                                              saved.data_ptr(), ws.data_ptr(), L.current_stream()), "mmae_dectail_backward")
         if meta.get("on_grads_ready") is not None:
             meta["on_grads_ready"](names)
         gw, gb = _ret_grads(arena, names, [weight, bias])

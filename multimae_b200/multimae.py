@@ -8,7 +8,6 @@ fused transformer blocks, fused decoder head/tail, gradients accumulated into on
 import itertools
 import os
 import math
-import warnings
 from collections import OrderedDict
 from functools import partial
 from typing import Dict, List, Optional, Union
@@ -117,7 +116,6 @@ class MultiMAE(nn.Module):
         self._init_all_weights()
         self._arena = None
         self._grad_callback = None
-        self._warned_fp32 = False
         self.external_shares = None
         self.device_shares = False                 # draw the Dirichlet task shares on the device (graph capture)
         self._alphas_dev = None
@@ -331,22 +329,26 @@ class MultiMAE(nn.Module):
         if self.output_adapters is None:
             return encoder_tokens, task_masks
 
-        if fp32_output_adapters and not self._warned_fp32:
-            warnings.warn("multimae_b200: fp32_output_adapters=%s run with bf16 tensor-core operands and fp32 accumulate "
-                          "(bf16 has fp32's exponent range, which removes the fp16 overflow the flag works around)"
-                          % list(fp32_output_adapters))
-            self._warned_fp32 = True
-        preds = self._decode(encoder_tokens, input_info, ids_keep, ids_restore)
+        preds = self._decode(encoder_tokens, input_info, ids_keep, ids_restore, fp32_output_adapters)
         return preds, task_masks
 
-    def _decode(self, encoder_tokens, input_info, ids_keep, ids_restore):
+    def _decode(self, encoder_tokens, input_info, ids_keep, ids_restore, fp32_output_adapters=()):
         """The task decoders are independent of each other (multimae/multimae.py:372-381 runs them in a Python loop):
         on CUDA each runs on its own stream, forward and (through autograd's stream tracking) backward, so their
         1.3-wave GEMMs, phase-locked attention CTAs and element-wise tails fill each other's idle SMs."""
         domains = list(self.output_adapters)
         kw = dict(encoder_tokens=encoder_tokens, input_info=input_info, ids_keep=ids_keep, ids_restore=ids_restore)
+        # adapters listed in fp32_output_adapters run in the fp32 tier (the reference calls them outside autocast,
+        # multimae/multimae.py:367-377); custom adapter classes without the switch are called as the reference does
+        fp32 = {d for d in (fp32_output_adapters or ()) if d in self.output_adapters}
+
+        def run(d):
+            if d in fp32:
+                return self.output_adapters[d](fp32=True, **kw)
+            return self.output_adapters[d](**kw)
+
         if not (self.decoder_streams and encoder_tokens.is_cuda and len(domains) > 1):
-            return {d: self.output_adapters[d](**kw) for d in domains}
+            return {d: run(d) for d in domains}
         dev = encoder_tokens.device
         if self._dec_streams is None or len(self._dec_streams) != len(domains):
             self._dec_streams = [torch.cuda.Stream(device=dev) for _ in domains]
@@ -356,7 +358,7 @@ class MultiMAE(nn.Module):
         for d, st in zip(domains, self._dec_streams):
             st.wait_event(ready)
             with torch.cuda.stream(st):
-                preds[d] = self.output_adapters[d](**kw)
+                preds[d] = run(d)
         for d, st in zip(domains, self._dec_streams):
             main.wait_stream(st)
             preds[d].record_stream(main)              # allocated on the side stream, consumed (loss) on this one

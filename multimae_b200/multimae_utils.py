@@ -121,7 +121,8 @@ class Block(nn.Module):
                 self.attn.proj.bias, self.norm2.weight, self.norm2.bias, self.mlp.fc1.weight, self.mlp.fc1.bias,
                 self.mlp.fc2.weight, self.mlp.fc2.bias)
 
-    def forward(self, x):
+    def forward(self, x, fp32=False):
+        """`fp32`: run this block in the fp32 tier (a decoder block of an adapter listed in fp32_output_adapters)."""
         if isinstance(self.drop_path, DropPath):
             self.drop_path(x)  # raises in training when p > 0
         if self._meta is None or self._meta["arena"].flat.device != x.device:
@@ -130,4 +131,5 @@ class Block(nn.Module):
             self._own_arena = True
         if getattr(self, "_own_arena", False) and torch.is_grad_enabled():
             self._meta["arena"].zero_()
-        return Fn.BlockFunction.apply(x, self._meta, *self._params())
+        meta = dict(self._meta, fp32=True) if fp32 else self._meta
+        return Fn.BlockFunction.apply(x, meta, *self._params())

@@ -103,7 +103,10 @@ class SpatialOutputAdapter(nn.Module, _PosEmbCache):
                 self.decoder.kv.bias, self.decoder.proj.weight, self.decoder.proj.bias, self.mlp.fc1.weight,
                 self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias)
 
-    def forward(self, encoder_tokens: torch.Tensor, input_info: Dict, ids_keep: torch.Tensor, ids_restore: torch.Tensor):
+    def forward(self, encoder_tokens: torch.Tensor, input_info: Dict, ids_keep: torch.Tensor, ids_restore: torch.Tensor,
+                fp32: bool = False):
+        """`fp32` (beyond the reference signature): run the whole adapter in the fp32 tier - what the reference does for the
+        adapters listed in `fp32_output_adapters` by calling them outside autocast (multimae/multimae.py:367-377)."""
         assert self.dim_tokens_enc is not None, "Need to call init(dim_tokens_enc) function first"
         if not self.use_xattn:
             raise NotImplementedError("multimae_b200: use_xattn=False is outside the pre-training hot path")
@@ -144,9 +147,13 @@ class SpatialOutputAdapter(nn.Module, _PosEmbCache):
         head_meta = dict(self._bound, dim=self.dim_tokens, num_global=input_info.get("num_global_tokens", 0),
                          num_queries=nh * nw, tok_offset=tok_offset, own_task=own_task, query_mode=query_mode,
                          heads=self.num_heads, hidden=self.mlp_hidden, eps=self.query_norm.eps,
-                         pos=self._resized_pos(nh, nw, "bilinear"), task_names=task_names)
+                         pos=self._resized_pos(nh, nw, "bilinear"), task_names=task_names, fp32=bool(fp32))
         x = Fn.DecoderHeadFunction.apply(encoder_tokens, head_meta, ids_keep, ids_restore, *self._head_params(),
                                          *task_embs)
-        x = self.decoder_transformer(x)
-        tail_meta = dict(self._bound, nh=nh, nw=nw, channels=self.num_channels, patch=self.P_H)
+        if fp32 and isinstance(self.decoder_transformer, nn.Sequential):
+            for blk in self.decoder_transformer:
+                x = blk(x, fp32=True)
+        else:
+            x = self.decoder_transformer(x)
+        tail_meta = dict(self._bound, nh=nh, nw=nw, channels=self.num_channels, patch=self.P_H, fp32=bool(fp32))
         return Fn.DecoderTailFunction.apply(x, tail_meta, self.out_proj.weight, self.out_proj.bias)

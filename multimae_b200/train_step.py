@@ -19,7 +19,7 @@ class TrainStep:
         # truncated depth standardisation of the 'depth' entry before it is used as input AND as loss target
         # (run_pretraining_multimae.py:487-492; --standardize_depth): one radix-select kernel instead of a full sort
         self.standardize_depth = standardize_depth
-        self._pdl_default = os.environ.get("MMAE_PDL", "1") != "0"
+        self._pdl_default = os.environ.get("MMAE_PDL", "0") != "0"
         self.num_encoded_tokens, self.alphas, self.uniform = num_encoded_tokens, alphas, sample_tasks_uniformly
         self.loss_sources = loss_sources or {}          # output key -> input key holding its target / mask
         self.graph = None

@@ -280,3 +280,82 @@ def test_standardize_depth_against_oracle_and_golden(dev, golden_dir):
         assert same.data_ptr() == xd.data_ptr() and torch.equal(same, out), name
     with pytest.raises(TypeError):
         Fn.standardize_depth(torch.zeros(2, 1, 8, 8, device=dev, dtype=torch.float16))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp32 tier primitives (fp32_output_adapters): 3 x bf16 split Linear, fp32 attention, fp32 GELU
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(48, 2128, 128), (392, 256, 768), (1000, 1024, 256), (48, 128, 128)])
+def test_linear_f32_split_gemm(dev, shape):
+    from multimae_b200 import _lib as L
+    lib = L.lib()
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    res = torch.randn(M, N, generator=g).to(dev)
+    dy = torch.randn(M, N, generator=g).to(dev)
+    ws = torch.empty(lib.mmae_linear_f32_workspace_bytes(M, N, K), dtype=torch.uint8, device=dev)
+    y = torch.empty(M, N, device=dev)
+    L.check(lib.mmae_linear_f32_forward(x.data_ptr(), W.data_ptr(), b.data_ptr(), res.data_ptr(), y.data_ptr(), M, N, K,
+                                        ws.data_ptr(), L.current_stream()))
+    ref = (x.double() @ W.double().t() + b.double() + res.double())
+    assert rel_l2(y, ref.float()) < 2e-5, rel_l2(y, ref.float())
+    dx = torch.empty(M, K, device=dev)
+    dW = torch.full((N, K), 0.5, device=dev)          # accumulated into
+    db = torch.full((N,), 0.25, device=dev)
+    L.check(lib.mmae_linear_f32_backward(x.data_ptr(), W.data_ptr(), dy.data_ptr(), dx.data_ptr(), dW.data_ptr(), db.data_ptr(),
+                                         M, N, K, ws.data_ptr(), L.current_stream()))
+    assert rel_l2(dx, (dy.double() @ W.double()).float()) < 2e-5
+    assert rel_l2(dW - 0.5, (dy.double().t() @ x.double()).float()) < 2e-5
+    assert rel_l2(db - 0.25, dy.double().sum(0).float()) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(3, 4, 16, 13), (2, 8, 196, 99), (2, 8, 196, 196), (1, 2, 130, 70)])
+def test_attention_f32(dev, case):
+    from multimae_b200 import _lib as L
+    lib = L.lib()
+    B, H, Nq, Nk = case
+    dh, D = 32, H * 32
+    scale = dh ** -0.5
+    q = torch.randn(B * Nq, D, device=dev)
+    kv = torch.randn(B * Nk, 2 * D, device=dev)
+    k, v = kv[:, :D], kv[:, D:]
+    o = torch.empty(B * Nq, D, device=dev)
+    lse = torch.empty(B, H, Nq, device=dev)
+    L.check(lib.mmae_attention_f32_forward(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                           o.data_ptr(), o.stride(0), lse.data_ptr(), B, H, Nq, Nk, dh, scale, L.current_stream()))
+    qf = q.double().reshape(B, Nq, H, dh).transpose(1, 2).detach().requires_grad_(True)
+    kf = k.double().reshape(B, Nk, H, dh).transpose(1, 2).detach().requires_grad_(True)
+    vf = v.double().reshape(B, Nk, H, dh).transpose(1, 2).detach().requires_grad_(True)
+    s = (qf @ kf.transpose(-2, -1)) * scale
+    ref = (torch.softmax(s, -1) @ vf).transpose(1, 2).reshape(B * Nq, D)
+    assert rel_l2(o, ref.float()) < 1e-5 and rel_l2(lse, torch.logsumexp(s, -1).float()) < 1e-5
+    do = torch.randn(B * Nq, D, device=dev)
+    ref.backward(do.double())
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    delta = torch.empty(B, H, Nq, device=dev)
+    L.check(lib.mmae_attention_f32_backward(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0),
+                                            o.data_ptr(), o.stride(0), do.data_ptr(), do.stride(0), lse.data_ptr(),
+                                            delta.data_ptr(), dq.data_ptr(), dq.stride(0), dkv.data_ptr(), dkv.stride(0),
+                                            dkv[:, D:].data_ptr(), dkv.stride(0), B, H, Nq, Nk, dh, scale, L.current_stream()))
+    assert rel_l2(dq, qf.grad.transpose(1, 2).reshape(B * Nq, D).float()) < 1e-5
+    assert rel_l2(dkv[:, :D], kf.grad.transpose(1, 2).reshape(B * Nk, D).float()) < 1e-5
+    assert rel_l2(dkv[:, D:], vf.grad.transpose(1, 2).reshape(B * Nk, D).float()) < 1e-5
+
+
+def test_gelu_f32(dev):
+    from multimae_b200 import _lib as L
+    lib = L.lib()
+    z = (torch.randn(1000, 64, device=dev) * 2).requires_grad_(True)
+    a = torch.empty_like(z)
+    L.check(lib.mmae_gelu_f32(z.data_ptr(), a.data_ptr(), z.numel(), 0, L.current_stream()))
+    ref = torch.nn.functional.gelu(z)
+    assert rel_l2(a, ref.detach()) < 1e-6
+    g = torch.randn_like(z)
+    ref.backward(g)
+    gz = g.clone()
+    L.check(lib.mmae_gelu_f32(z.data_ptr(), gz.data_ptr(), z.numel(), 1, L.current_stream()))
+    assert rel_l2(gz, z.grad) < 1e-5

@@ -9,6 +9,7 @@ import pytest
 import torch
 
 from helpers import formula_fill_, rel_l2
+from multimae_b200 import _lib as L
 from oracle import multimae_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -174,6 +175,92 @@ def test_model_against_golden_and_oracle(golden_dir, dev, name):
         d = fx["grads"][k]
         fair = float(fx["grad_norm"]) * (named[k].numel() / sum(v.numel() for v in train.values())) ** 0.5
         assert abs(float(named[k].grad.float().norm()) - float(d["norm"])) < PER_TENSOR_TOL * max(float(d["norm"]), fair), k
+
+
+FP32_TOL = 1e-3          # north_star "1e-3 rel fp32": the fp32 tier of fp32_output_adapters against the fp32 oracle
+
+
+@pytest.mark.parametrize("task", ["semseg", "rgb"])
+def test_fp32_output_adapter_tier(golden_dir, dev, task):
+    """fp32_output_adapters (multimae/multimae.py:367-377): an adapter run in the fp32 tier - 3 x bf16 split tcgen05 GEMMs,
+    fp32 attention / GELU / LayerNorm - against the fp32 oracle's decode_task on the SAME encoder tokens: prediction, the
+    gradient w.r.t. the encoder tokens and every parameter gradient of the adapter to 1e-3."""
+    fx = _load(golden_dir, "cuda_small.pt")
+    c = fx["config"]
+    model = _build_model(c)
+    formula_fill_(list(model.named_parameters()))
+    model = model.to(dev).train()
+    cfg = _oracle_cfg(c)
+    p = O.init_params(cfg)
+    train = O.trainable(p)
+    formula_fill_(list(train.items()))
+    prefix = "output_adapters.%s." % task
+    keys = [k for k in train if k.startswith(prefix)]
+    for k in keys:
+        train[k].requires_grad_(True)
+    B, n_tok = c["B"], (c["image_size"] // 16) ** 2
+    g = torch.Generator().manual_seed(5)
+    enc = torch.randn(B, c["num_encoded"] + 1, c["dim"], generator=g) * 0.5
+    enc_o = enc.clone().requires_grad_(True)
+    counts = {d: n_tok for d in c["in_domains"]}
+    hw = (c["image_size"], c["image_size"])
+    ref = O.decode_task(enc_o, p, task, O.DOMAINS[task], cfg, counts, hw, fx["ids_keep"], fx["ids_restore"])
+    w = torch.randn(ref.shape, generator=g)
+    (ref * w).sum().backward()
+
+    info = model.generate_input_info({d: torch.empty(B, n_tok, 0) for d in c["in_domains"]}, hw)
+    model.grad_arena(dev).zero_()
+    enc_d = enc.to(dev).requires_grad_(True)
+    pred = model.output_adapters[task](enc_d, info, fx["ids_keep"].to(dev), fx["ids_restore"].to(dev), fp32=True)
+    (pred * w.to(dev)).sum().backward()
+    torch.cuda.synchronize()
+    assert pred.shape == ref.shape
+    named = dict(model.named_parameters())
+    total = sum(float(train[k].grad.norm()) ** 2 for k in keys) ** 0.5
+    numel = sum(train[k].numel() for k in keys)
+    worst = (0.0, None)
+    for k in keys:
+        r, got = train[k].grad, named[k].grad.detach().float().cpu()
+        fair = total * (r.numel() / numel) ** 0.5
+        e = float((got - r).norm()) / max(float(r.norm()), 0.05 * fair)
+        worst = max(worst, (e, k))
+        if e >= FP32_TOL:
+            print("  gradient off: %-60s %.3e (||ref|| %.3e)" % (k, e, float(r.norm())))
+    print("fp32 tier %s: pred %.2e, d_enc %.2e, worst parameter gradient %.2e (%s)" %
+          (task, rel_l2(pred, ref), rel_l2(enc_d.grad, enc_o.grad), worst[0], worst[1]))
+    assert rel_l2(pred, ref) < FP32_TOL, rel_l2(pred, ref)
+    assert rel_l2(enc_d.grad, enc_o.grad) < FP32_TOL, rel_l2(enc_d.grad, enc_o.grad)
+    assert worst[0] < FP32_TOL, worst
+
+
+def test_fp32_output_adapters_flag_in_model(golden_dir, dev):
+    """MultiMAE.forward(fp32_output_adapters=['semseg']) routes that adapter through the fp32 tier (no warning, no
+    downgrade) and the step still matches the fixture."""
+    import warnings
+    fx = _load(golden_dir, "cuda_small.pt")
+    c = fx["config"]
+    model = _build_model(c)
+    formula_fill_(list(model.named_parameters()))
+    model = model.to(dev).train()
+    triple = ({k: v.to(dev) for k, v in fx["task_masks"].items()}, fx["ids_keep"].to(dev), fx["ids_restore"].to(dev))
+    model.generate_random_masks = lambda *a, **k: triple
+    fed = {k: v.to(dev) for k, v in fx["inputs"].items()}
+    lib = L.lib()
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        before = lib.mmae_launch_count()
+        preds, _ = model(fed, num_encoded_tokens=c["num_encoded"], fp32_output_adapters=["semseg"])
+        n_fp32 = lib.mmae_launch_count() - before
+        before = lib.mmae_launch_count()
+        preds_b, _ = model(fed, num_encoded_tokens=c["num_encoded"])
+        n_bf16 = lib.mmae_launch_count() - before
+    assert n_fp32 > n_bf16                        # the split kernels of the fp32 tier ran
+    for k, ref in fx["preds"].items():
+        assert rel_l2(preds[k], ref) < BF16_TOL, (k, rel_l2(preds[k], ref))
+    assert rel_l2(preds["semseg"], fx["preds"]["semseg"]) <= rel_l2(preds_b["semseg"], fx["preds"]["semseg"]) * 1.05
+    sum(p.float().sum() for p in preds.values()).backward()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
 
 
 def _full_model_case(dev, size, image_size, n_visible, B):
