@@ -27,8 +27,14 @@ for r in reader:
     rows.append((name, ns))
 if not rows:
     sys.exit("no gpu__time_duration rows found")
-per_step = len(rows) // a.steps_in_log
-last = rows[-per_step:]
+# step boundaries: the mask sampler runs exactly once per step, first thing in the forward; use the last COMPLETE step
+marks = [i for i, (name, _) in enumerate(rows) if "mask_sampler_kernel" in name]
+if len(marks) >= 2:
+    last = rows[marks[-2]:marks[-1]]
+    per_step = len(last)
+else:
+    per_step = len(rows) // a.steps_in_log
+    last = rows[-per_step:]
 tot = sum(ns for _, ns in last)
 agg = collections.OrderedDict()
 for name, ns in last:

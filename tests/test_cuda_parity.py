@@ -263,9 +263,10 @@ def test_fp32_output_adapters_flag_in_model(golden_dir, dev):
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
 
 
-def _full_model_case(dev, size, image_size, n_visible, B):
+def _full_model_case(dev, size, image_size, n_visible, B, oracle_on=None, global_tol=None):
     """One full-size step (forward, 4 losses, backward) of the CUDA path against the fp32 oracle on the same weights,
-    synthetic inputs (SURVEY.md §8d generator) and oracle-sampled masks."""
+    synthetic inputs (SURVEY.md §8d generator) and oracle-sampled masks.  `oracle_on`: device the oracle runs on (fp32, TF32
+    off; default CPU) - the bench-sized batch needs the GPU to finish in seconds."""
     from test_host_api import _build
     dim, depth, heads = (768, 12, 12) if size == "base" else (1024, 24, 16)     # multimae/multimae.py:387-397, 405-415
     model = _build(("rgb", "depth", "semseg"), dim, depth, heads, 256, 2, 8, image_size)
@@ -284,12 +285,21 @@ def _full_model_case(dev, size, image_size, n_visible, B):
     m, ids_keep, ids_restore = O.sample_masks(shares, noises, noise_all, n_visible)
     tmask = {d.name: mm for d, mm in zip(cfg.in_domains, m)}
 
-    p = {k: v.clone() for k, v in sd.items()}
-    train = O.trainable(p)
-    for v in train.values():
-        v.requires_grad_(True)
-    o_losses, o_preds = O.step_losses(p, x, cfg, tmask, ids_keep, ids_restore)
-    sum(o_losses.values()).backward()
+    od = torch.device("cpu") if oracle_on is None else oracle_on
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False        # the oracle is fp32
+    try:
+        p = {k: v.clone().to(od) for k, v in sd.items()}
+        train = O.trainable(p)
+        for v in train.values():
+            v.requires_grad_(True)
+        o_losses, o_preds = O.step_losses(p, {k: v.to(od) for k, v in x.items()}, cfg, {k: v.to(od) for k, v in tmask.items()},
+                                          ids_keep.to(od), ids_restore.to(od))
+        sum(o_losses.values()).backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    o_preds = {k: v.detach().cpu() for k, v in o_preds.items()}
+    o_losses = {k: v.detach().cpu() for k, v in o_losses.items()}
 
     model = model.to(dev).train()
     triple = ({k: v.to(dev) for k, v in tmask.items()}, ids_keep.to(dev), ids_restore.to(dev))
@@ -300,6 +310,17 @@ def _full_model_case(dev, size, image_size, n_visible, B):
         assert abs(float(losses[k]) - float(o_losses[k])) < BF16_TOL * abs(float(o_losses[k])), k
     named = dict(model.named_parameters())
     _check_grads({k: named[k].grad for k in train}, {k: v.grad for k, v in train.items()})
+    if global_tol is not None:
+        got = torch.cat([named[k].grad.detach().float().cpu().flatten() for k in train])
+        ref = torch.cat([v.grad.detach().float().cpu().flatten() for v in train.values()])
+        assert rel_l2(got, ref) < global_tol, rel_l2(got, ref)
+
+
+def test_bench_batch_model_against_oracle_on_cuda(dev):
+    """BASELINE config 2 at a bench-sized batch (B = 64: encoder M = 6336 rows, decoder M = 12544 - the persistent / CTA-pair
+    GEMM variants, BN = 192 / 256 tiles, automatic split-K and the warp-specialised attention kernels run as in bench.py)
+    against the fp32 oracle evaluated on the same GPU in plain fp32 (TF32 off).  Global gradient error < 1e-2."""
+    _full_model_case(dev, "base", 224, 98, B=64, oracle_on=dev, global_tol=1e-2)
 
 
 def test_full_size_model_against_oracle(dev):

@@ -114,7 +114,10 @@ for name in ("mmae_sample_masks", "mmae_embed_forward", "mmae_block_forward", "m
              "mmae_masked_loss_forward", "mmae_masked_loss_backward", "mmae_dectail_backward", "mmae_dechead_backward",
              "mmae_block_backward", "mmae_embed_backward"):
     assert name in Stub.calls, name
-assert Stub.calls.count("mmae_block_forward") == 2 * (12 + 4 * 1) and Stub.calls.count("mmae_masked_loss_forward") == 2 * 4
+# fp32_output_adapters=["semseg"]: that adapter's head / block / tail run through the fp32-tier entry points
+assert Stub.calls.count("mmae_block_forward") == 2 * (12 + 3 * 1) and Stub.calls.count("mmae_block_f32_forward") == 2 * 1
+assert Stub.calls.count("mmae_dechead_f32_forward") == 2 and Stub.calls.count("mmae_dectail_f32_backward") == 2
+assert Stub.calls.count("mmae_masked_loss_forward") == 2 * 4
 assert Stub.calls.count("mmae_grad_unscale_norm") == 2                 # fused unscale + norm over the flat arena, per step
 assert all(p.grad is not None and p.grad.data_ptr() == model.grad_arena().view(n).data_ptr()
            for n, p in model.named_parameters() if p.requires_grad)
