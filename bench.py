@@ -125,12 +125,16 @@ def _note(msg):
     print("[bench %6.1fs] %s" % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant GEMM (encoder fc1 forward, 12672x3072x768 + bias,
-# L2 flushed before the launch) from the committed `ncu --set full` capture profiles/r01_ncu_full_hot_kernels.txt
-NCU_GEMM_DRAM_BYTES = 24.25e6 + 25.62e6
-NCU_GEMM_TRAFFIC_NOTE = ("fc1 forward GEMM 12672x3072x768: 24.3 MB read (= the 24.2 MB of operands: no re-reads) + 25.6 MB "
-                         "written inside the capture window; the remaining ~52 MB of the 77.9 MB result are still dirty in the "
-                         "126 MB L2 when the kernel ends (algorithmic bytes per launch: 102.1 MB)")
+def ncu_evidence():
+    """Figures that only a profiler can give (DRAM bytes of the dominant GEMM, tensor-pipe % of the attention kernels) are
+    READ from the committed summary of the `ncu --set full` capture - profiles/ncu_hot_kernels.json, written by
+    scripts/ncu_raw_table.py --json together with the commit it was taken at - never typed into this file."""
+    path = os.path.join(ROOT, "profiles", "ncu_hot_kernels.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def encoder_tc_from_table(agg, rows_enc, D_enc, peak_tf):
@@ -153,12 +157,14 @@ def encoder_tc_from_table(agg, rows_enc, D_enc, peak_tf):
     if ms_enc <= 0:
         return None
     tf_enc = fl_enc / (ms_enc * 1e-3) / 1e12
-    return {"encoder_gemm_tflops": round(tf_enc, 1), "launches_per_step": n_enc, "ms_per_step": round(ms_enc, 3),
-            "frac_of_measured_peak": round(tf_enc / peak_tf, 4), "frac_of_nominal_2250": round(tf_enc / 2250.0, 4),
-            "mhsa_kernel_tensor_pipe_pct_ncu": {"attn_tc_fwd_kernel": 7.7, "attn_tc_bwd_kernel": 7.3},
-            "note": "ncu sm__pipe_tensor figures of the big encoder GEMM kernels: 63-69 % "
-                    "(profiles/r01_ncu_full_hot_kernels.txt); the stand-alone MHSA kernel is HBM-bound (Q/K/V in + O out = "
-                    "78 MB -> 12 us floor -> <= 24 % tensor pipe), DESIGN.md section 7"}
+    out = {"encoder_gemm_tflops": round(tf_enc, 1), "launches_per_step": n_enc, "ms_per_step": round(ms_enc, 3),
+           "frac_of_measured_peak": round(tf_enc / peak_tf, 4), "frac_of_nominal_2250": round(tf_enc / 2250.0, 4)}
+    ev = ncu_evidence()
+    if ev is not None:
+        out["tensor_pipe_pct_ncu"] = {k: v.get("tensor_pct") for k, v in ev.get("kernels", {}).items()
+                                      if "attn" in k or "gemm" in k}
+        out["ncu_capture"] = {"file": "profiles/ncu_hot_kernels.json", "commit": ev.get("commit"), "when": ev.get("when")}
+    return out
 
 
 def synthetic_batch(B, seed, pin=False, image=224):
@@ -198,7 +204,15 @@ def run_ours(args, rank, world, local_rank):
     stepper = TrainStep(model, loss_fns, opt, scaler, num_encoded_tokens=wl["visible"], alphas=1.0,
                         loss_sources={"norm_rgb": "rgb"}, standardize_depth=bool(args.standardize_depth))
     mode = "eager"
-    if (args.graph and world == 1) or args.graph >= 2:
+    if world > 1:
+        # the first collectives build NCCL's channels / buffers: keep that out of every timed region
+        for _ in range(3):
+            dist.all_reduce(model.grad_arena().flat)
+        model.grad_arena().zero_()
+        torch.cuda.synchronize()
+        if args.sm_budget:
+            lib.mmae_set_sm_budget(args.sm_budget)
+    if args.graph:
         try:
             stepper.capture(resident[0], warmup=3)
             mode = "cuda-graph (whole step = one graph launch)"
@@ -383,6 +397,7 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": "dp%d" % world,
                    "l2": "two alternating input batches (212 MB) and a >9 GB per-step activation working set exceed the 126 MB L2",
                    "loss_scaling": "none (bf16)",
+                   "sm_budget": args.sm_budget or None,
                    "e2e_pipeline": "H2D of step i+1 prefetched on a copy stream during step i; every step's loss read on "
                                    "the host once, one step late (pinned D2H behind the step)", "final_loss": round(final_loss, 4), "launch_mode": mode},
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes,
@@ -391,19 +406,30 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05, all operand-major variants)",
                      "achieved": round(gemm_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": round(gemm_tf / peak_tf, 4), "traffic": NCU_GEMM_DRAM_BYTES,
-                     "traffic_note": NCU_GEMM_TRAFFIC_NOTE, "peak_source": peak_src + " (sustained bf16)",
+                     "frac": round(gemm_tf / peak_tf, 4), "traffic": None,
+                     "traffic_note": None, "peak_source": peak_src + " (sustained bf16)",
                      "launches_per_step": int(n_g.value), "kernel_ms_per_step": round(ms_g.value, 3),
                      "kernel_share_of_step": round(ms_g.value / ms_step, 3),
                      "step_model_flops_frac": round(value / world * wl["flop"] / (peak_tf * 1e12), 4)},
     }
     if encoder_tc is not None:
         out["encoder_tc"] = encoder_tc
-    if args.workload != "cfg2":
-        # the committed ncu traffic figure belongs to the cfg2 fc1 GEMM shape
-        out["roofline"]["traffic"], out["roofline"]["traffic_note"] = None, "no ncu capture for this workload's GEMM shapes"
+    ev = ncu_evidence() if args.workload == "cfg2" else None
+    gemm_ev = (ev or {}).get("dominant_gemm")
+    if gemm_ev:          # dram__bytes_read + dram__bytes_write of one launch of the dominant GEMM, from the committed capture
+        out["roofline"]["traffic"] = gemm_ev.get("dram_bytes")
+        out["roofline"]["traffic_note"] = "%s: %s (ncu --set full, commit %s, profiles/ncu_hot_kernels.json)" % (
+            gemm_ev.get("what"), gemm_ev.get("note"), ev.get("commit"))
+    else:
+        out["roofline"]["traffic_note"] = "no committed ncu capture for this workload's GEMM shapes"
+    if world == 1 and args.eager_baseline:
+        # free this process's ~10 GB of activations / graph memory pools first: the eager oracle needs room of its own
+        _note("GPU legs done (%.1f samples/s); timing torch eager (oracle port) on this GPU" % value)
+        out["torch_eager_same_gpu"] = gpu_eager_baseline_bounded(workload=args.workload)
+        if out["torch_eager_same_gpu"].get("bf16_autocast"):
+            out["torch_eager_same_gpu"]["speedup_vs_bf16_autocast"] = round(value / out["torch_eager_same_gpu"]["bf16_autocast"], 2)
     if world == 1 and args.cpu_baseline:
-        _note("GPU legs done (%.1f samples/s); timing the CPU baseline sample" % value)
+        _note("timing the CPU baseline sample")
         out["cpu_baseline"] = cpu_baseline_bounded(workload=args.workload)
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -466,6 +492,70 @@ def cpu_baseline(sample_steps=2, batch=4, workload="cfg2"):
                       "PyTorch path; no optimizer step; thread count chosen by a probe over 8/16/32/64)" % (sample_steps, batch)}
 
 
+def _gpu_eager_steps(workload, dtype, steps=5, warmup=2):
+    """The oracle port of the reference PyTorch path, eager, on THIS GPU under torch.autocast (fp16 as the reference ships
+    it, run_pretraining_multimae.py:500, or bf16): forward + 4 losses + backward at the workload's batch - the "kernel to
+    beat" of SURVEY.md section 8(d).  Test infrastructure timed as a baseline, like the CPU arm."""
+    from oracle import multimae_oracle as O
+    wl = WORKLOADS[workload]
+    dev = torch.device("cuda", 0)
+    cfg = O.make_config(size=wl["size"])
+    p = {k: v.to(dev) for k, v in O.init_params(cfg, seed=0).items()}
+    train = O.trainable(p)
+    for v in train.values():
+        v.requires_grad_(True)
+    B = wl["batch"]
+    x = {k: v.to(dev) for k, v in O.synthetic_inputs(cfg, B, wl["image"], seed=0).items()}
+    shares, noises, noise_all = O.synthetic_mask_draws(cfg, B, wl["image"], seed=1)
+    m, ids_keep, ids_restore = O.sample_masks(shares, noises, noise_all, wl["visible"])
+    tmask = {d.name: mm.to(dev) for d, mm in zip(cfg.in_domains, m)}
+    ids_keep, ids_restore = ids_keep.to(dev), ids_restore.to(dev)
+    times = []
+    for i in range(warmup + steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for v in train.values():
+            v.grad = None
+        if dtype is None:
+            losses, _ = O.step_losses(p, x, cfg, tmask, ids_keep, ids_restore)
+        else:
+            with torch.autocast("cuda", dtype=dtype):
+                losses, _ = O.step_losses(p, x, cfg, tmask, ids_keep, ids_restore)
+        (sum(losses.values()) * (65536.0 if dtype == torch.float16 else 1.0)).backward()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= warmup:
+            times.append(a.elapsed_time(b))
+    return B / (statistics.median(times) * 1e-3)
+
+
+def gpu_eager_baseline(workload="cfg2"):
+    out = {"unit": "samples/s", "what": "oracle port of the reference PyTorch path, eager on this GPU, fwd+4 losses+bwd at the "
+           "workload's batch (no optimizer step), median of 5 steps after 2 warm-ups, CUDA events"}
+    for name, dt in (("fp16_autocast", torch.float16), ("bf16_autocast", torch.bfloat16)):
+        try:
+            out[name] = round(_gpu_eager_steps(workload, dt), 1)
+        except Exception as e:  # noqa: BLE001
+            out[name] = None
+            out[name + "_error"] = str(e).splitlines()[0][:160] if str(e) else type(e).__name__
+        torch.cuda.empty_cache()
+    return out
+
+
+def gpu_eager_baseline_bounded(limit_s=150, workload="cfg2"):
+    """In a child process (its ~40 GB of eager activations are gone when it exits) with a hard time limit."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "gpu-eager", "--workload", workload],
+                           capture_output=True, text=True, timeout=limit_s)
+        for line in reversed(r.stdout.splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"fp16_autocast": None, "bf16_autocast": None,
+                "note": "failed: " + (r.stderr.strip().splitlines() or ["no output"])[-1][:200]}
+    except subprocess.TimeoutExpired:
+        return {"fp16_autocast": None, "bf16_autocast": None, "note": "exceeded %d s" % limit_s}
+
+
 def cpu_baseline_bounded(limit_s=150, workload="cfg2"):
     """The CPU sample in a child process with a hard time limit: a slow or oversubscribed host must not cost the GPU line."""
     try:
@@ -484,20 +574,25 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    batch = 8 if args.workload == "cfg2" else 2
-    threads = _best_thread_count(batch, args.workload)
-    times = _cpu_steps(batch, args.steps, max(1, min(args.warmup, 2)), threads=threads, workload=args.workload)
+    # the workload's own batch (cfg2: bs = 128, a few seconds per step on the host cores), so that the arm's config IS the
+    # GPU arm's; the thread count is probed at a small batch, the step count is bounded
+    batch = wl["batch"] if args.workload == "cfg2" else 2
+    threads = _best_thread_count(8 if args.workload == "cfg2" else 2, args.workload)
+    steps = min(args.steps, 3)
+    times = _cpu_steps(batch, steps, 1, threads=threads, workload=args.workload)
     ms_step = statistics.mean(times) * 1e3
     value = batch / (ms_step * 1e-3)
     base = {"value": round(value, 2), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "each step = fwd+4 losses+bwd of bs=%d on the host cores (bounded sample of the bs=%d workload)"
-                      % (batch, wl["batch"])}
+            "sample": "%d steps (after 1 warm-up) of fwd+4 losses+bwd+grad-norm at bs=%d on the host cores, fp32, no optimizer "
+                      "update (the oracle port of the reference path; bounded step count)" % (steps, batch)}
     print(json.dumps({
         "impl": "reference", "metric": wl["metric"], "value": round(value, 2), "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 1), "higher_is_better": True,
+        "steps": steps, "warmup": 1, "ms_per_step": round(ms_step, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "note": "CPU arm: oracle port of the reference path (the reference is pure "
-                   "PyTorch and /root/reference does not travel to the GPU box)"},
+        "config": {"workload": wl["name"], "global_batch": batch, "per_gpu_batch": batch,
+                   "note": "CPU arm: oracle port of the reference path (the reference is pure PyTorch and /root/reference "
+                           "does not travel to the GPU box); fp32 on the host cores, no optimizer update; with N > 1 it is "
+                           "still ONE host process - compare it with the N = 1 line only"},
         "cpu_baseline": base,
         "e2e": {"value": round(value, 2), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -514,9 +609,12 @@ def main():
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the bounded CPU sample (development runs only)")
     ap.add_argument("--standardize-depth", type=int, default=0,
                     help="1: truncated depth standardisation (run_pretraining_multimae.py:487-492) inside the step")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-baseline"])
-    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (single GPU); 2: also with data parallelism "
-                         "(NCCL all-reduces captured in the graph)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-baseline", "gpu-eager"])
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (data parallel: the bucketed NCCL "
+                         "all-reduces are captured in it); 0: eager launches")
+    ap.add_argument("--sm-budget", type=int, default=0, help="N>1: SMs the persistent kernels may claim (0 = all; the rest is "
+                         "left to NCCL's all-reduce CTAs)")
+    ap.add_argument("--eager-baseline", type=int, default=1, help="0: skip the torch-eager-on-this-GPU sample of the oracle port")
     ap.add_argument("--e2e-probe", action="store_true", help="extra timed loops that isolate the H2D / loss-read costs")
     ap.add_argument("--gemm-shapes", default=None, help="write a per-shape GEMM time table of one profiled step here")
     args = ap.parse_args()
@@ -529,9 +627,10 @@ def main():
         print(json.dumps(cpu_baseline(sample_steps=2, batch=4 if args.workload == "cfg2" else 2, workload=args.workload)),
               flush=True)
         return
+    if args.impl == "gpu-eager":
+        print(json.dumps(gpu_eager_baseline(args.workload)), flush=True)
+        return
     if args.impl == "reference":
-        if args.steps > 5:
-            args.steps = 5                                  # bounded CPU sample
         run_reference(args, rank, world)
         return
     args.warmup = max(args.warmup, 3)

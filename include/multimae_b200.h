@@ -86,6 +86,9 @@ int mmae_gemm_set_tma_store(int enable);
  * wait), so the next kernel's blocks are scheduled while the previous one drains; 0 (default): plain stream order - a
  * programmatically launched dependent keeps stale L1 lines for non-coherent loads (see runtime.cu).  Env MMAE_PDL. */
 int mmae_set_pdl(int enable);
+/* SM budget of the persistent kernels (GEMM, warp-specialised attention, one-wave element-wise grids): 0 = every SM
+ * (default), n = at most n.  Data-parallel runs leave NCCL's all-reduce CTAs their SMs.  Env MMAE_SM_BUDGET. */
+int mmae_set_sm_budget(int sms);
 /* 1: mmae_block_backward runs its four weight-gradient GEMMs on a library-owned side stream, forked behind the kernel
  * that produces their dY operand and joined before the call returns (the caller's stream order is unchanged);
  * 0 (default; no gain measured at the MultiMAE-B shapes): everything on the caller's stream.  Env MMAE_WGRAD_STREAM. */

@@ -134,6 +134,7 @@ SIGNATURES = {
     "mmae_layernorm_backward_ex": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_void_p,
                                            c_int, c_int, c_void_p]),
+    "mmae_set_sm_budget": (c_int, [c_int]),
     "mmae_attention_set_tc": (c_int, [c_int]),
     "mmae_attention_ws_set_trace": (c_int, [c_void_p]),
     "mmae_attention_forward": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p,

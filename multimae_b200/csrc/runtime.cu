@@ -56,6 +56,13 @@ void gemm_profile_end(cudaStream_t st) {
   g_prof.used++;
 }
 
+// SM budget of the persistent kernels: the physical SM count, or fewer (MMAE_SM_BUDGET / mmae_set_sm_budget).  Data-parallel
+// runs overlap NCCL's all-reduce CTAs with the backward: a persistent GEMM that claims every SM runs a second wave on the
+// SMs NCCL holds; sized to SMs - NCCL CTAs it finishes in one.
+static int g_sm_budget = []() {
+  const char* e = getenv("MMAE_SM_BUDGET");
+  return e ? atoi(e) : 0;
+}();
 int sm_count() {
   static int cached = 0;
   if (cached == 0) {
@@ -64,7 +71,7 @@ int sm_count() {
     cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
     if (cached <= 0) cached = 148;
   }
-  return cached;
+  return g_sm_budget > 0 && g_sm_budget < cached ? g_sm_budget : cached;
 }
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -232,6 +239,10 @@ static int g_pdl = []() {
 }();
 bool pdl_enabled() { return g_pdl != 0; }
 }  // namespace mmae
+extern "C" int mmae_set_sm_budget(int sms) {
+  mmae::g_sm_budget = sms;
+  return MMAE_OK;
+}
 extern "C" int mmae_set_pdl(int enable) {
   mmae::g_pdl = enable != 0;
   return MMAE_OK;

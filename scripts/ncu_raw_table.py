@@ -60,6 +60,7 @@ def main(path):
                 continue
             launches.append((r[kcol], {h: (num(v), u) for h, v, u in zip(header, r, units)}))
     print("%-80s %8s %8s %8s %8s %7s %7s %6s %8s" % ("kernel", "us", "MB rd", "MB wr", "tensor%", "dram%", "warps%", "regs", "grid"))
+    summary = {}
     for name, m in launches:
         def get(key, scale=None):
             for cand in WANT[key]:
@@ -69,7 +70,40 @@ def main(path):
             return float("nan")
         print("%-80s %8.1f %8.1f %8.1f %8.1f %7.1f %7.1f %6.0f %8.0f" % (short(name), get("us", TIME), get("rd", BYTES),
               get("wr", BYTES), get("tensor"), get("dram"), get("warps"), get("regs"), get("grid")))
+        key = short(name)
+        k = 2
+        while key in summary:                      # several launches of one kernel (different shapes): name, name#2, ...
+            key = "%s#%d" % (short(name), k)
+            k += 1
+        summary[key] = {"us": round(get("us", TIME), 2), "dram_read_mb": round(get("rd", BYTES), 2),
+                        "dram_write_mb": round(get("wr", BYTES), 2), "tensor_pct": round(get("tensor"), 2),
+                        "dram_pct": round(get("dram"), 2), "grid": int(get("grid"))}
+    return summary
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    # python scripts/ncu_raw_table.py raw.csv [--json profiles/ncu_hot_kernels.json --commit HASH --order "name; name; ..."]
+    import argparse
+    import datetime
+    import json
+    ap = argparse.ArgumentParser()
+    ap.add_argument("csv")
+    ap.add_argument("--json", default=None, help="also write the machine-readable summary bench.py reads")
+    ap.add_argument("--commit", default="unknown", help="git commit of the profiled code")
+    ap.add_argument("--gemm", default=None, help="summary key of the dominant GEMM launch (default: first gemm_* entry)")
+    ap.add_argument("--gemm-what", default="dominant GEMM launch")
+    a = ap.parse_args()
+    summ = main(a.csv)
+    if a.json:
+        gk = a.gemm or next((k for k in summ if k.startswith("gemm")), None)
+        out = {"commit": a.commit, "when": datetime.datetime.utcnow().strftime("%Y-%m-%dT%H:%MZ"),
+               "how": "ncu --set full --clock-control none, L2 flushed before each profiled launch (scripts/gpu_ncu_targets.py)",
+               "kernels": summ}
+        if gk:
+            g = summ[gk]
+            out["dominant_gemm"] = {"kernel": gk, "what": a.gemm_what,
+                                    "dram_bytes": round((g["dram_read_mb"] + g["dram_write_mb"]) * 1e6),
+                                    "note": "%.1f MB read + %.1f MB written to DRAM inside the capture window, %.1f us, tensor pipe "
+                                            "%.1f %%" % (g["dram_read_mb"], g["dram_write_mb"], g["us"], g["tensor_pct"])}
+        with open(a.json, "w") as fh:
+            json.dump(out, fh, indent=1)
