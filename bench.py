@@ -203,7 +203,6 @@ def run_ours(args, rank, world, local_rank):
     from multimae_b200.train_step import TrainStep
     stepper = TrainStep(model, loss_fns, opt, scaler, num_encoded_tokens=wl["visible"], alphas=1.0,
                         loss_sources={"norm_rgb": "rgb"}, standardize_depth=bool(args.standardize_depth))
-    mode = "eager"
     if world > 1:
         # the first collectives build NCCL's channels / buffers: keep that out of every timed region
         for _ in range(3):
@@ -212,6 +211,46 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         if args.sm_budget:
             lib.mmae_set_sm_budget(args.sm_budget)
+    # ------------------------------------------------------------------ roofline of the dominant kernel (tcgen05 GEMM): one
+    # eager step with CUDA events around every GEMM launch, taken BEFORE the step is captured (a captured graph cannot be
+    # profiled per launch, and eager collectives must not be mixed in behind captured ones)
+    for _ in range(2):
+        stepper._step(resident[0])
+    torch.cuda.synchronize()
+    peak_tf, peak_gbs, peak_src = peaks()
+    lib.mmae_profile_gemm(1)
+    l0 = lib.mmae_launch_count()
+    stepper._step(resident[0])                             # eager: per-launch events cannot be replayed from a graph
+    launches_per_step = lib.mmae_launch_count() - l0
+    torch.cuda.synchronize()
+    lib.mmae_profile_gemm(0)
+    fl, ms_g, n_g = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    lib.mmae_profile_gemm_read(ctypes.byref(fl), ctypes.byref(ms_g), ctypes.byref(n_g))
+    gemm_tf = fl.value / (ms_g.value * 1e-3) / 1e12 if ms_g.value > 0 else 0.0
+    encoder_tc = None
+    if rank == 0:
+        try:
+            buf = ctypes.create_string_buffer(1 << 20)
+            n = lib.mmae_profile_gemm_dump(buf, len(buf))
+            agg = {}
+            for line in buf.raw[:max(n, 0)].decode().splitlines():
+                M_, N_, K_, fl_, ms_ = line.split()
+                key = (int(M_), int(N_), int(K_), int(fl_) & 3, int(fl_) >> 8)
+                a_ = agg.setdefault(key, [0, 0.0])
+                a_[0] += 1
+                a_[1] += float(ms_)
+            if args.gemm_shapes:
+                with open(args.gemm_shapes, "w") as fh:
+                    fh.write("%7s %6s %6s %3s %5s %5s %9s %8s\n" % ("M", "N", "K", "maj", "split", "count", "ms_total", "TF/s"))
+                    for key, (cnt, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                        tf = 2.0 * key[0] * key[1] * key[2] * cnt / (ms_ * 1e-3) / 1e12
+                        fh.write("%7d %6d %6d %3d %5d %5d %9.3f %8.1f\n" % (key + (cnt, ms_, tf)))
+            encoder_tc = encoder_tc_from_table(agg, args.batch * (wl["visible"] + 1), 768 if wl["size"] == "base" else 1024,
+                                               peak_tf)
+        except Exception as e:  # noqa: BLE001  (diagnostics only: never cost the headline line)
+            _note("per-shape GEMM table unavailable: %s" % str(e)[:120])
+
+    mode = "eager"
     if args.graph:
         try:
             stepper.capture(resident[0], warmup=3)
@@ -254,6 +293,8 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.mmae_launch_count() - launches0
+    if stepper.graph is not None:
+        launches = launches_per_step * args.steps          # a replayed graph re-issues the captured launches
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(loss)
 
@@ -345,42 +386,11 @@ def run_ours(args, rank, world, local_rank):
                           ("H2D consumed, loss read", (True, True, True)),
                           ("H2D consumed, loss read, submit after launch", (True, True, True, True))):
             _note("probe %-46s %.3f ms/step" % (name, timed(*cfg)))
-    # ------------------------------------------------------------------ roofline of the dominant kernel (tcgen05 GEMM)
-    peak_tf, peak_gbs, peak_src = peaks()
-    lib.mmae_profile_gemm(1)
-    l0 = lib.mmae_launch_count()
-    stepper._step(resident[0])                             # eager: per-launch events cannot be replayed from a graph
-    launches_per_step = lib.mmae_launch_count() - l0
-    if stepper.graph is not None:
-        launches = launches_per_step * args.steps          # a replayed graph re-issues the captured launches
-    torch.cuda.synchronize()
-    lib.mmae_profile_gemm(0)
-    fl, ms_g, n_g = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
-    lib.mmae_profile_gemm_read(ctypes.byref(fl), ctypes.byref(ms_g), ctypes.byref(n_g))
-    gemm_tf = fl.value / (ms_g.value * 1e-3) / 1e12 if ms_g.value > 0 else 0.0
-    encoder_tc = None
-    if rank == 0:
-        try:
-            buf = ctypes.create_string_buffer(1 << 20)
-            n = lib.mmae_profile_gemm_dump(buf, len(buf))
-            agg = {}
-            for line in buf.raw[:max(n, 0)].decode().splitlines():
-                M_, N_, K_, fl_, ms_ = line.split()
-                key = (int(M_), int(N_), int(K_), int(fl_) & 3, int(fl_) >> 8)
-                a_ = agg.setdefault(key, [0, 0.0])
-                a_[0] += 1
-                a_[1] += float(ms_)
-            if args.gemm_shapes:
-                with open(args.gemm_shapes, "w") as fh:
-                    fh.write("%7s %6s %6s %3s %5s %5s %9s %8s\n" % ("M", "N", "K", "maj", "split", "count", "ms_total", "TF/s"))
-                    for key, (cnt, ms_) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-                        tf = 2.0 * key[0] * key[1] * key[2] * cnt / (ms_ * 1e-3) / 1e12
-                        fh.write("%7d %6d %6d %3d %5d %5d %9.3f %8.1f\n" % (key + (cnt, ms_, tf)))
-            encoder_tc = encoder_tc_from_table(agg, args.batch * (wl["visible"] + 1), 768 if wl["size"] == "base" else 1024,
-                                               peak_tf)
-        except Exception as e:  # noqa: BLE001  (diagnostics only: never cost the headline line)
-            _note("per-shape GEMM table unavailable: %s" % str(e)[:120])
-
+    if world > 1:
+        # the captured graph holds NCCL work: release it, drain the device, line the ranks up, then tear the group down
+        stepper.graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
