@@ -157,7 +157,8 @@ int mmae_layernorm_backward_ex(const void* dy, int dy_is_bf16, int64_t lddy, con
  * 32/64; used for <= 128 keys, with 8 also for <= 256 keys), 4 = general tcgen05 backward; 0 = warp-MMA (mma.sync +
  * ldmatrix + cp.async) kernels everywhere; 32 / 64 = warp-specialised persistent tcgen05 forward / backward (TMA warp, MMA
  * warp, 8 compute warps; attention_ws.cu) for every shape they support (forward: <= 256 keys; backward: <= 256 queries).
- * Default 3 | 64 (env MMAE_ATTN_TC); a negative value restores the start-up default. */
+ * 128 = the warp-specialised forward only where the alternative is the mma.sync kernel (129..256 keys).
+ * Default 3 | 64 | 128 (env MMAE_ATTN_TC); a negative value restores the start-up default. */
 int mmae_attention_set_tc(int enable);
 /* diagnostics for the warp-specialised kernels (attention_ws.cu): a device buffer of 64 x 16 int64 that CTA 0 of the next
  * launches fills with clock64 stamps of its pipeline phases (slot 16 * item + phase); NULL switches it off. */

@@ -546,13 +546,16 @@ using namespace mmae;
 // bit 0: fused single-tile tcgen05 kernels (encoder shape) ; bit 1: general tcgen05 forward (query tiles, <= 256 keys,
 // head_dim 32/64) ; bit 2: general tcgen05 backward (measured slower than the warp-MMA backward at N = 196: off) ;
 // bit 5 (32) / bit 6 (64): warp-specialised persistent tcgen05 forward / backward (attention_ws.cu).
-// 0 = warp-MMA kernels everywhere.  Default 3 | 64: measured on B200 at bs 128 (scripts/gpu_check_attention_ws.py) the
+// bit 7 (128): the warp-specialised forward for > 128 keys only (where the alternative is the mma.sync kernel).
+// 0 = warp-MMA kernels everywhere.  Default 3 | 64 | 128: measured on B200 at bs 128 (scripts/gpu_check_attention_ws.py) the
 // warp-specialised backward takes 43.8 us (encoder 99 x 99 x 64; was 76.5 with the delta kernel), 77.7 us (decoder
 // 196 x 196 x 32; was 130.8 on mma.sync) and 44.3 us (196 x 99 x 32; was 77.7); the warp-specialised forward does not beat
-// the one-CTA-per-item kernels yet (32.8 vs 27.2 us encoder, 50.2 vs 52.3 us at 196 keys) and stays opt-in.
+// the one-CTA-per-item tcgen05 kernels at <= 128 keys yet (32.8 vs 27.2 us encoder, 36.6 vs 25.5 us at 99 keys) and is used
+// where it ties with / beats the mma.sync kernel: 196 keys (50.2 vs 52.3 us) - with it no mma.sync kernel is left on the
+// MultiMAE-B 224^2 path.
 static int g_attn_tc = []() {
   const char* e = getenv("MMAE_ATTN_TC");
-  return e ? atoi(e) : (3 | 64);
+  return e ? atoi(e) : (3 | 64 | 128);
 }();
 static const int g_attn_tc_default = g_attn_tc;
 extern "C" int mmae_attention_set_tc(int enable) {
@@ -571,7 +574,7 @@ extern "C" int mmae_attention_forward(const void* q, int64_t ldq, const void* k,
   dim3 grid(ceil_div(Nq, ATT_ROWS), H, B);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // bit 5 (32): warp-specialised persistent tcgen05 forward (attention_ws.cu) for every shape it supports
-  if ((g_attn_tc & 32) && attn_ws_fwd_supported(H, Nq, Nk, head_dim))
+  if (((g_attn_tc & 32) || ((g_attn_tc & 128) && Nk > 128)) && attn_ws_fwd_supported(H, Nq, Nk, head_dim))
     return attn_ws_forward(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Nq, Nk, head_dim, scale, st);
   if ((g_attn_tc & 1) && attn_tc_supported(Nq, Nk, head_dim)) {
     if (g_attn_tc & 16)   // experimental persistent variant (attention_tc.cu), never on by default

@@ -184,9 +184,10 @@ ATTN_CASES = [(3, 12, 99, 99, 64, True), (2, 8, 196, 99, 32, False), (2, 8, 196,
               (1, 2, 100, 33, 64, False), (1, 2, 256, 256, 64, True), (1, 4, 200, 129, 32, False), (5, 8, 196, 196, 32, True)]
 
 
-# 15: every one-CTA-per-item tcgen05 kernel wherever it is supported; 67: the default (warp-specialised backward);
-# 99: warp-specialised forward AND backward wherever supported (attention_ws.cu); 19: the persistent encoder forward
-@pytest.mark.parametrize("tc", [0, 1, 3, 7, 15, 19, 67, 99])
+# 15: every one-CTA-per-item tcgen05 kernel wherever it is supported; 195: the default (warp-specialised backward, and
+# forward for > 128 keys); 99: warp-specialised forward AND backward wherever supported (attention_ws.cu); 19: the
+# persistent encoder forward
+@pytest.mark.parametrize("tc", [0, 1, 3, 7, 15, 19, 195, 99])
 @pytest.mark.parametrize("case", ATTN_CASES)
 def test_attention_forward_backward(dev, KN, tc, case):
     from multimae_b200 import _lib as L
@@ -253,7 +254,8 @@ def _depth_cases():
     yield "tiny", torch.tensor([[3.0, 1.0, 2.0, 2.0, 5.0, -1.0, 0.0, -0.0, 4.0, 2.0]]).reshape(1, 1, 2, 5)
 
 
-def test_standardize_depth_against_oracle_and_golden(dev, golden_dir):
+@pytest.mark.parametrize("variant", [2, 1])     # 2: the default (histogram copies + cluster split), 1: the single-CTA kernel
+def test_standardize_depth_against_oracle_and_golden(dev, golden_dir, variant):
     """mmae_standardize_depth (radix select of the two cut values) against the sort-based oracle
     (run_pretraining_multimae.py:487-492): fp32, differences only from the summation order -> 2e-5 absolute on O(1)
     outputs, 1e-5 relative on mean / variance; in-place operation; fixture recorded from the reference's own lines."""
@@ -261,6 +263,7 @@ def test_standardize_depth_against_oracle_and_golden(dev, golden_dir):
     from multimae_b200 import functional as Fn
     from oracle import multimae_oracle as O
     fx = torch.load(os.path.join(golden_dir, "depth_std.pt"), map_location="cpu", weights_only=False)
+    Fn.L.check(Fn.L.lib().mmae_standardize_depth_set_variant(variant))
     got = Fn.standardize_depth(fx["depth"].to(dev))
     assert got.shape == fx["standardized"].shape
     assert float((got.cpu() - fx["standardized"]).abs().max()) < 2e-5
@@ -280,6 +283,7 @@ def test_standardize_depth_against_oracle_and_golden(dev, golden_dir):
         assert same.data_ptr() == xd.data_ptr() and torch.equal(same, out), name
     with pytest.raises(TypeError):
         Fn.standardize_depth(torch.zeros(2, 1, 8, 8, device=dev, dtype=torch.float16))
+    Fn.L.check(Fn.L.lib().mmae_standardize_depth_set_variant(2))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
