@@ -3,6 +3,7 @@ as one fused forward kernel + one fused backward kernel with no host synchronisa
 import torch.nn as nn
 
 from . import functional as Fn
+from .lazy_meters import DeferredScalar
 
 
 class _MaskedLoss(nn.Module):
@@ -20,8 +21,9 @@ class _MaskedLoss(nn.Module):
         self.label_smoothing = label_smoothing
 
     def forward(self, input, target, mask=None):
-        return Fn.MaskedLossFunction.apply(input, target, mask, self.kind, bool(self.norm_pix), self.scale_factor,
+        loss = Fn.MaskedLossFunction.apply(input, target, mask, self.kind, bool(self.norm_pix), self.scale_factor,
                                            float(self.label_smoothing))
+        return DeferredScalar.wrap(loss)       # plain tensor unless the overlay's lazy meters are on (lazy_meters.py)
 
 
 class MaskedCrossEntropyLoss(_MaskedLoss):

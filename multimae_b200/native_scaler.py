@@ -8,6 +8,7 @@ The loss scale lives on the device; state_dict() has GradScaler's keys so checkp
 import torch
 
 from . import functional as Fn
+from .lazy_meters import METERS, DeferredScalar
 
 inf = float("inf")
 
@@ -35,6 +36,53 @@ def _find_arena(optimizer, parameters):
     if parameters is not None:
         return Fn.find_arena_for(parameters)
     return None
+
+
+class _LazyScalerState(dict):
+    """state_dict() under lazy meters: `["scale"]` - what train_one_epoch reads every step
+    (run_pretraining_multimae.py:538) - answers one step late without a host sync; every other use (iteration, pickling by
+    utils.save_model, load_state_dict) sees the exact, synchronously read state."""
+
+    def __init__(self, scaler):
+        super().__init__()
+        self._scaler = scaler
+
+    def _exact(self):
+        s = self._scaler
+        return {"scale": float(s._scale), "growth_factor": s._growth_factor, "backoff_factor": s._backoff_factor,
+                "growth_interval": s._growth_interval, "_growth_tracker": int(s._growth_tracker)}
+
+    def __getitem__(self, key):
+        if key == "scale":
+            return METERS.read(self._scaler._scale)
+        return self._exact()[key]
+
+    def get(self, key, default=None):
+        return self._exact().get(key, default)
+
+    def keys(self):
+        return self._exact().keys()
+
+    def values(self):
+        return self._exact().values()
+
+    def items(self):
+        return self._exact().items()
+
+    def __iter__(self):
+        return iter(self._exact())
+
+    def __len__(self):
+        return 5
+
+    def __contains__(self, key):
+        return key in self._exact()
+
+    def __bool__(self):
+        return True
+
+    def __reduce__(self):
+        return (dict, (self._exact(),))
 
 
 class NativeScalerWithGradNormCount:
@@ -123,7 +171,7 @@ class NativeScalerWithGradNormCount:
         self._update(found_inf)
         if arena is not None:
             arena.accumulating = False
-        return norm
+        return DeferredScalar.wrap(norm)
 
     def _unscale_outside(self, optimizer, arena, handled, inv, found_inf):
         key = (id(optimizer), id(arena), sum(len(g["params"]) for g in getattr(optimizer, "param_groups", [])))
@@ -175,6 +223,8 @@ class NativeScalerWithGradNormCount:
     def state_dict(self):
         if not self._enabled:
             return {"scale": 1.0}
+        if METERS.enabled and self._scale is not None and self._scale.is_cuda:
+            return _LazyScalerState(self)
         scale = float(self._scale) if self._scale is not None else self._init_scale
         tracker = int(self._growth_tracker) if self._growth_tracker is not None else 0
         return {"scale": scale, "growth_factor": self._growth_factor, "backoff_factor": self._backoff_factor,

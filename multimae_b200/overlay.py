@@ -107,6 +107,10 @@ def install(reference_root=None, replace_ddp=True, legacy_checkpoint_load=True):
         utils.native_scaler.get_grad_norm_ = get_grad_norm_
     except Exception:  # noqa: BLE001
         pass
+    from . import lazy_meters
+    lazy_meters.install()                          # MMAE_LAZY_METERS=1: the script's ~10 .item() per step answer one step late
+    from . import data
+    data.install()                                 # MMAE_DEVICE_FEED=1 / MMAE_SYNTHETIC_DATA=N: see data.py
     if replace_ddp:
         import torch
         if torch.nn.parallel.DistributedDataParallel is not _IdentityDDP:

@@ -185,3 +185,69 @@ def test_flat_adamw_state_dict_round_trip(golden_dir):
     stock = torch.optim.AdamW([p for p in model2.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.05)
     stock.load_state_dict(ck["optimizer"])
     assert float(next(iter(stock.state.values()))["step"]) == 2.0
+
+
+def test_lazy_meters_read_one_step_late(golden_dir):
+    """MMAE_LAZY_METERS (n3): the `.item()` reads of train_one_epoch (:525-538) and its per-step `torch.cuda.synchronize()`
+    stop draining the device - every call site returns the value it read in the previous step; checkpoints still see the
+    exact scaler state."""
+    import pickle
+    from multimae_b200 import lazy_meters
+    from multimae_b200.native_scaler import NativeScalerWithGradNormCount
+    from multimae_b200.optim import FlatAdamW
+    dev = torch.device("cuda:0")
+    model, fx = _model(golden_dir)
+    model = model.to(dev).train()
+    opt = FlatAdamW(model, lr=1e-3)
+    scaler = NativeScalerWithGradNormCount(enabled=True).attach_arena(model.grad_arena())
+    fns = _losses()
+    x = {k: v.to(dev) for k, v in fx["inputs"].items()}
+    real_sync = torch.cuda.synchronize
+    assert lazy_meters.install(True)
+    try:
+        assert torch.cuda.synchronize is not real_sync
+        read, true = [], []
+        for step in range(4):
+            torch.manual_seed(step)
+            preds, masks = model(x, num_encoded_tokens=fx["config"]["num_encoded"])
+            task_losses = {t: fns[t](preds[t].float(), x["rgb" if t == "norm_rgb" else t], mask=masks.get("rgb" if t == "norm_rgb" else t))
+                           for t in preds}
+            loss = sum(task_losses.values())
+            assert isinstance(loss, lazy_meters.DeferredScalar)
+            loss_value = sum(task_losses.values()).item()                          # :525
+            per_task = {t: l.item() for t, l in task_losses.items()}               # :526
+            grad_norm = scaler(loss, opt, parameters=None)
+            scale = scaler.state_dict()["scale"]                                   # :538
+            torch.cuda.synchronize()                                               # :540 -> step boundary, no device sync
+            read.append((loss_value, per_task["semseg"], grad_norm.item(), scale))
+            true.append((loss.detach().clone(), task_losses["semseg"].detach().clone(), grad_norm.detach().clone()))
+        real_sync()
+        true = [tuple(float(t.as_subclass(torch.Tensor)) for t in row) for row in true]
+        assert read[0][:3] == pytest.approx(true[0], rel=1e-6)                     # first step: the real values
+        for i in range(1, 4):
+            assert read[i][:3] == pytest.approx(true[i - 1], rel=1e-6), i          # afterwards: one step late
+        assert all(r[3] == 65536.0 for r in read)
+        state = pickle.loads(pickle.dumps(scaler.state_dict()))                    # what utils.save_model stores: exact
+        assert type(state) is dict and state["scale"] == 65536.0 and state["_growth_tracker"] == 4
+    finally:
+        lazy_meters.uninstall()
+    assert torch.cuda.synchronize is real_sync
+
+
+def test_device_feed_hands_out_gpu_batches():
+    """MMAE_DEVICE_FEED / MMAE_SYNTHETIC_DATA (n4): a DataLoader wrapped in DeviceFeed yields batches that already live on
+    the GPU (copied on a side stream one batch ahead), equal to the host batches."""
+    from torch.utils.data import DataLoader
+    from multimae_b200.data import DeviceFeed, SyntheticMultiTaskDataset
+    ds = SyntheticMultiTaskDataset(40, input_size=64, pool=16)
+    host = list(DataLoader(ds, batch_size=8, drop_last=True))
+    feed = DeviceFeed(DataLoader(ds, batch_size=8, drop_last=True), device="cuda:0")
+    assert len(feed) == len(host) == 5
+    n = 0
+    for (xd, _), (xh, _) in zip(feed, host):
+        for k in xh:
+            assert xd[k].is_cuda and torch.equal(xd[k].cpu(), xh[k]), k
+            y = xd[k].to("cuda:0", non_blocking=True)                              # the script's own .to(device): a no-op
+            assert y.data_ptr() == xd[k].data_ptr()
+        n += 1
+    assert n == 5
