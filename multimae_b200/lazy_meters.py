@@ -13,6 +13,7 @@ starts on an empty GPU queue.  Opt-in (MMAE_LAZY_METERS=1, overlay only) the val
 What the logger prints (and the `math.isfinite(loss_value)` divergence check, run_pretraining_multimae.py:529-531) therefore
 lags the computation by exactly one step; nothing else changes.  Off by default: the reference semantics are the default."""
 import os
+import sys
 
 import torch
 
@@ -24,21 +25,23 @@ class _Meters:
 
     def reset(self):
         self.step = 0
-        self.call = 0            # index of the .item() call inside the current step
-        self.slots = []          # per call site: [pinned buffer of 2 floats, [event, event]]
-        self.scale_cache = None
+        self.seen = {}           # call site -> how often it has read inside the current step window
+        self.slots = {}          # (call site, occurrence) -> [pinned buffer of 2 floats, [event, event], [valid, valid]]
 
-    def _slot(self, k):
-        while len(self.slots) <= k:
-            self.slots.append([torch.zeros(2, dtype=torch.float32).pin_memory(), [torch.cuda.Event(), torch.cuda.Event()],
-                               [False, False]])
-        return self.slots[k]
+    def _slot(self, key):
+        slot = self.slots.get(key)
+        if slot is None:
+            slot = self.slots[key] = [torch.zeros(2, dtype=torch.float32).pin_memory(),
+                                      [torch.cuda.Event(), torch.cuda.Event()], [False, False]]
+        return slot
 
-    def read(self, value):
-        """value: 0-dim CUDA tensor.  Returns a float: this call site's value of the previous step."""
-        k, cur = self.call, self.step & 1
-        self.call += 1
-        buf, events, valid = self._slot(k)
+    def read(self, value, site):
+        """value: 0-dim CUDA tensor; site: the reading call site (source file + line, or a name).  Returns a float: what the
+        same call site (and occurrence, for a line that reads several tensors per step) read in the previous step."""
+        occ = self.seen.get(site, 0)
+        self.seen[site] = occ + 1
+        cur = self.step & 1
+        buf, events, valid = self._slot((site, occ))
         buf[cur:cur + 1].copy_(value.detach().reshape(1).float(), non_blocking=True)
         events[cur].record()
         valid[cur] = True
@@ -51,7 +54,7 @@ class _Meters:
 
     def end_step(self):
         self.step += 1
-        self.call = 0
+        self.seen = {}
 
 
 METERS = _Meters()
@@ -68,7 +71,8 @@ class DeferredScalar(torch.Tensor):
 
     def item(self):
         if METERS.enabled and self.is_cuda and self.numel() == 1:
-            return METERS.read(self.as_subclass(torch.Tensor))
+            f = sys._getframe(1)                                   # the line of the script / logger that reads the value
+            return METERS.read(self.as_subclass(torch.Tensor), (f.f_code.co_filename, f.f_lineno))
         return self.as_subclass(torch.Tensor).item()
 
 

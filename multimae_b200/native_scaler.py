@@ -54,7 +54,7 @@ class _LazyScalerState(dict):
 
     def __getitem__(self, key):
         if key == "scale":
-            return METERS.read(self._scaler._scale)
+            return METERS.read(self._scaler._scale, "loss_scale")
         return self._exact()[key]
 
     def get(self, key, default=None):
