@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MMAE_ABI_VERSION 3
+#define MMAE_ABI_VERSION 4
 
 int mmae_abi_version(void);
 const char* mmae_last_error(void);
@@ -291,6 +291,41 @@ int mmae_dechead_forward(const float* enc, int D_enc, const mmae_decoder_index* 
 int mmae_dechead_backward(const float* enc, int D_enc, const mmae_decoder_index* ix, int H, int hidden,
                           const mmae_dechead_params* prm, const mmae_dechead_grads* grads, const float* dx_out,
                           float* denc, const void* saved, void* ws, void* stream);
+
+/* Shared context projection.  MultiMAE.forward passes the SAME encoder output to every output adapter
+ * (multimae/multimae.py:357-366) and each adapter begins with its own proj_context Linear
+ * (multimae/output_adapters.py:258): n Linears [rows, D_enc] -> [rows, Dd_i] on one input.  mmae_ctxproj_forward runs them
+ * as ONE GEMM with N = sum_i Dd_i (one bf16 cast of enc, ctx = enc W_cat^T + b_cat, fp32 [rows, dim_total], adapter i owns
+ * the column segment starting at sum(dim[0..i))); the heads then run through mmae_dechead_forward_ctx /
+ * mmae_dechead_backward_ctx, which read their segment, write their bf16 context gradient into the matching segment of one
+ * [rows, dim_total] matrix and produce the proj_context BIAS gradient; mmae_ctxproj_backward finishes with one weight
+ * gradient GEMM (K = rows) and one input-gradient GEMM (K = dim_total) that WRITES denc.  Parameters, their bf16 mirror and
+ * their gradient slots are used in place when the n tensors lie back to back in memory, gathered otherwise.
+ * For the *_ctx heads, mmae_dechead_saved_bytes / _workspace_bytes are queried with D_enc = 0. */
+typedef struct mmae_ctxproj_params {
+  int num;                              /* adapters sharing the projection, 1..MMAE_MAX_TASKS */
+  int dim[MMAE_MAX_TASKS];              /* dim_tokens of each adapter (multiples of 8) */
+  const float* weight[MMAE_MAX_TASKS];  /* proj_context.weight [dim_i, D_enc] */
+  const float* bias[MMAE_MAX_TASKS];    /* proj_context.bias [dim_i] */
+} mmae_ctxproj_params;
+typedef struct mmae_ctxproj_grads {     /* accumulated (+=) */
+  float* weight[MMAE_MAX_TASKS];
+} mmae_ctxproj_grads;
+int64_t mmae_ctxproj_saved_bytes(int rows, int D_enc, int dim_total);
+/* enc: [rows, D_enc] fp32 -> ctx: [rows, dim_total] fp32 */
+int mmae_ctxproj_forward(const float* enc, int rows, int D_enc, const mmae_ctxproj_params* prm, float* ctx, void* saved,
+                         void* stream);
+/* dctx_bf16: [rows, dim_total] bf16 (every segment written by its head); denc: [rows, D_enc] fp32, WRITTEN */
+int mmae_ctxproj_backward(int rows, int D_enc, const mmae_ctxproj_params* prm, const mmae_ctxproj_grads* grads,
+                          const void* dctx_bf16, float* denc, const void* saved, void* stream);
+/* ctx: this adapter's segment of the shared projection (row stride ld_ctx floats); prm->proj_context_w / _b are unused */
+int mmae_dechead_forward_ctx(const float* ctx, int64_t ld_ctx, const mmae_decoder_index* ix, int H, int hidden, float eps,
+                             const mmae_dechead_params* prm, float* x_out, void* saved, void* ws, void* stream);
+/* dctx_bf16: this adapter's segment of the shared gradient matrix (row stride ld_dctx bf16 elements, WRITTEN);
+ * grads->proj_context_b is accumulated, grads->proj_context_w is left to mmae_ctxproj_backward */
+int mmae_dechead_backward_ctx(const mmae_decoder_index* ix, int H, int hidden, const mmae_dechead_params* prm,
+                              const mmae_dechead_grads* grads, const float* dx_out, void* dctx_bf16, int64_t ld_dctx,
+                              const void* saved, void* ws, void* stream);
 
 int64_t mmae_dectail_saved_bytes(int B, int nh, int nw, int Dd, int C, int P);
 int64_t mmae_dectail_workspace_bytes(int B, int nh, int nw, int Dd, int C, int P);

@@ -96,6 +96,14 @@ class DecHeadGrads(ctypes.Structure):
                  ("task_emb", c_void_p * MAX_TASKS)] + [(n, c_void_p) for n in HEAD_TAIL_FIELDS])
 
 
+class CtxProjParams(ctypes.Structure):
+    _fields_ = [("num", c_int), ("dim", c_int * MAX_TASKS), ("weight", c_void_p * MAX_TASKS), ("bias", c_void_p * MAX_TASKS)]
+
+
+class CtxProjGrads(ctypes.Structure):
+    _fields_ = [("weight", c_void_p * MAX_TASKS)]
+
+
 class MmaeError(RuntimeError):
     pass
 
@@ -165,6 +173,15 @@ SIGNATURES = {
     "mmae_dechead_backward": (c_int, [c_void_p, c_int, ctypes.POINTER(DecoderIndex), c_int, c_int,
                                       ctypes.POINTER(DecHeadParams), ctypes.POINTER(DecHeadGrads), c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
+    "mmae_ctxproj_saved_bytes": (c_i64, [c_int] * 3),
+    "mmae_ctxproj_forward": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(CtxProjParams), c_void_p, c_void_p, c_void_p]),
+    "mmae_ctxproj_backward": (c_int, [c_int, c_int, ctypes.POINTER(CtxProjParams), ctypes.POINTER(CtxProjGrads), c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
+    "mmae_dechead_forward_ctx": (c_int, [c_void_p, c_i64, ctypes.POINTER(DecoderIndex), c_int, c_int, c_float,
+                                         ctypes.POINTER(DecHeadParams), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mmae_dechead_backward_ctx": (c_int, [ctypes.POINTER(DecoderIndex), c_int, c_int, ctypes.POINTER(DecHeadParams),
+                                          ctypes.POINTER(DecHeadGrads), c_void_p, c_void_p, c_i64, c_void_p, c_void_p,
+                                          c_void_p]),
     "mmae_dectail_saved_bytes": (c_i64, [c_int] * 6),
     "mmae_dectail_workspace_bytes": (c_i64, [c_int] * 6),
     "mmae_dectail_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
@@ -217,7 +234,7 @@ SIGNATURES = {
     "mmae_standardize_depth": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
 }
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 def lib():

@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(256) semseg_emb_bwd_kernel(const bf16* __restr
 // One CTA row per output row; rows [0, B*P) are queries, rows [B*P, B*P + B*(T+G)) are context.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int DBF_ROWS = 16;   // rows per block: 4 row lanes x 4 rows in flight per thread
-__global__ void __launch_bounds__(256) dec_build_kernel(const float* __restrict__ ctx, mmae_decoder_index ix,
+__global__ void __launch_bounds__(256) dec_build_kernel(const float* __restrict__ ctx, int64_t ld_ctx,  // row stride of ctx
+                                                        mmae_decoder_index ix,
                                                         const float* __restrict__ mask_token, TaskEmbPtrs task_emb,
                                                         const float* __restrict__ pos,  // [P, Dd]
                                                         float* __restrict__ queries, float* __restrict__ context) {
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(256) dec_build_kernel(const float* __restrict_
         const int g = ix.tok_offset[ix.own_task] + j;
         rank = (int)ix.ids_restore[int64_t(b) * ix.total_tokens + g];
       }
-      base[u] = rank < T ? reinterpret_cast<const float4*>(ctx + (int64_t(b) * (T + G) + rank) * Dd)
+      base[u] = rank < T ? reinterpret_cast<const float4*>(ctx + (int64_t(b) * (T + G) + rank) * ld_ctx)
                          : reinterpret_cast<const float4*>(mask_token);
       te[u] = ix.own_task >= 0 ? reinterpret_cast<const float4*>(task_emb.p[ix.own_task]) : nullptr;
       pe[u] = reinterpret_cast<const float4*>(pos + int64_t(j) * Dd);
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(256) dec_build_kernel(const float* __restrict_
     } else {
       const int cr = row - nq_rows;
       const int b = cr / (T + G), i = cr % (T + G);
-      base[u] = reinterpret_cast<const float4*>(ctx + int64_t(cr) * Dd);
+      base[u] = reinterpret_cast<const float4*>(ctx + int64_t(cr) * ld_ctx);
       dst[u] = reinterpret_cast<float4*>(context + int64_t(cr) * Dd);
       if (i < T) {
         const int g = (int)ix.ids_keep[int64_t(b) * T + i];
@@ -492,10 +493,10 @@ int launch_semseg_emb_bwd(const bf16* dA, int64_t ld_dA, const int64_t* labels, 
   return MMAE_OK;
 }
 
-int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float* mask_token, const TaskEmbPtrs& task_emb,
-                     const float* pos, float* queries, float* context, cudaStream_t st) {
+int launch_dec_build(const float* ctx, int64_t ld_ctx, const mmae_decoder_index& ix, const float* mask_token,
+                     const TaskEmbPtrs& task_emb, const float* pos, float* queries, float* context, cudaStream_t st) {
   const int rows = ix.batch * ix.num_queries + ix.batch * (ix.num_visible + ix.num_global);
-  launch_k(dec_build_kernel, ceil_div(rows, DBF_ROWS), 256, 0, st, ctx, ix, mask_token, task_emb, pos, queries, context);
+  launch_k(dec_build_kernel, ceil_div(rows, DBF_ROWS), 256, 0, st, ctx, ld_ctx, ix, mask_token, task_emb, pos, queries, context);
   count_launch();
   MMAE_LAUNCH_OK();
   return MMAE_OK;

@@ -47,8 +47,8 @@ int launch_embed_assemble_bwd(const float* dx, int B, int T, int G, int D, const
 int launch_semseg_emb_bwd(const bf16* dA, int64_t ld_dA, const int64_t* labels, const int64_t* ids_keep,
                           const int* row_task, const int* row_patch, int task, int T, int rows, int grid_w, int grid_h,
                           int P, int E, int num_classes, float* dtable, cudaStream_t st);
-int launch_dec_build(const float* ctx, const mmae_decoder_index& ix, const float* mask_token, const TaskEmbPtrs& task_emb,
-                     const float* pos, float* queries, float* context, cudaStream_t st);
+int launch_dec_build(const float* ctx, int64_t ld_ctx, const mmae_decoder_index& ix, const float* mask_token,
+                     const TaskEmbPtrs& task_emb, const float* pos, float* queries, float* context, cudaStream_t st);
 int launch_dec_build_bwd(const float* dqueries, const float* dcontext, const mmae_decoder_index& ix, float* dctx,
                          float* dmask_token, const TaskEmbGradPtrs& dtask_emb, cudaStream_t st);
 // depth_standardize_v2.cu (experimental variant 2); MMAE_ERR_UNSUPPORTED when the map exceeds 8 CTAs' shared memory

@@ -416,9 +416,14 @@ extern "C" int64_t mmae_dechead_workspace_bytes(const mmae_decoder_index* ix, in
   return (int64_t)head_ws(nullptr, *ix, D_enc, H, hidden).bytes;
 }
 
-extern "C" int mmae_dechead_forward(const float* enc, int De, const mmae_decoder_index* ixp, int H, int hidden, float eps,
-                                    const mmae_dechead_params* p, float* x_out, void* saved, void* ws, void* st) {
-  MMAE_CHECK(enc && ixp && p && x_out && saved && ws, MMAE_ERR_ARG, "mmae_dechead_forward: bad args");
+// `ctx_ext` != null: the context projection was done by mmae_ctxproj_forward for all adapters at once; this head reads
+// its [Mc, Dd] column segment (row stride ld_ctx floats) and De is 0 (no enc_b / proj_context operand slots in `saved`).
+static int dechead_forward_impl(const float* enc, const float* ctx_ext, int64_t ld_ctx, int De,
+                                const mmae_decoder_index* ixp, int H, int hidden, float eps, const mmae_dechead_params* p,
+                                float* x_out, void* saved, void* ws, void* st) {
+  MMAE_CHECK((enc || ctx_ext) && ixp && p && x_out && saved && ws, MMAE_ERR_ARG, "mmae_dechead_forward: bad args");
+  MMAE_CHECK(!ctx_ext || (ld_ctx % 4 == 0 && (reinterpret_cast<uintptr_t>(ctx_ext) & 15) == 0), MMAE_ERR_ARG,
+             "mmae_dechead_forward_ctx: the context segment must be 16-byte aligned with a row stride that is a multiple of 4");
   const mmae_decoder_index& ix = *ixp;
   const int Dd = ix.dim, B = ix.batch, P = ix.num_queries, Nc = ix.num_visible + ix.num_global;
   MMAE_CHECK(Dd % H == 0 && ix.num_tasks <= MMAE_MAX_TASKS &&
@@ -431,19 +436,22 @@ extern "C" int mmae_dechead_forward(const float* enc, int De, const mmae_decoder
   HeadSaved s = head_saved(saved, ix, De, H, hidden);
   HeadWs w = head_ws(ws, ix, De, H, hidden);
   cudaStream_t cst = reinterpret_cast<cudaStream_t>(st);
-  RUN(mmae_cast_f32_to_bf16(enc, s.enc_b, int64_t(Mc) * De, st));
-  RUN(weight_operand(p->proj_context_w, &s.wpc, int64_t(Dd) * De, true, st));
+  if (!ctx_ext) {
+    RUN(mmae_cast_f32_to_bf16(enc, s.enc_b, int64_t(Mc) * De, st));
+    RUN(weight_operand(p->proj_context_w, &s.wpc, int64_t(Dd) * De, true, st));
+  }
   RUN(weight_operand(p->q_w, &s.wq, int64_t(Dd) * Dd, true, st));
   RUN(weight_operand(p->kv_w, &s.wkv, int64_t(2) * Dd * Dd, true, st));
   RUN(weight_operand(p->proj_w, &s.wproj, int64_t(Dd) * Dd, true, st));
   RUN(weight_operand(p->fc1_w, &s.w1, int64_t(hidden) * Dd, true, st));
   RUN(weight_operand(p->fc2_w, &s.w2, int64_t(Dd) * hidden, true, st));
   // proj_context                                                   output_adapters.py:258
-  RUN(linear_f32(s.enc_b, s.wpc, p->proj_context_b, nullptr, w.ctx, Mc, Dd, De, st));
+  if (!ctx_ext) RUN(linear_f32(s.enc_b, s.wpc, p->proj_context_b, nullptr, w.ctx, Mc, Dd, De, st));
   // queries / context                                              output_adapters.py:183-234
   TaskEmbPtrs te;
   for (int t = 0; t < MMAE_MAX_TASKS; ++t) te.p[t] = p->task_emb[t];
-  RUN(launch_dec_build(w.ctx, ix, p->mask_token, te, p->pos, s.queries, s.context, cst));
+  RUN(launch_dec_build(ctx_ext ? ctx_ext : w.ctx, ctx_ext ? ld_ctx : int64_t(Dd), ix, p->mask_token, te, p->pos, s.queries,
+                       s.context, cst));
   // decoder(query_norm(q), context_norm(c))                        output_adapters.py:265
   RUN(mmae_layernorm_forward(s.queries, Dd, p->query_norm_w, p->query_norm_b, s.qn, Dd, nullptr, 0, s.qmean, s.qrstd, Mq,
                              Dd, eps, st));
@@ -463,16 +471,31 @@ extern "C" int mmae_dechead_forward(const float* enc, int De, const mmae_decoder
   return MMAE_OK;
 }
 
-extern "C" int mmae_dechead_backward(const float* enc, int De, const mmae_decoder_index* ixp, int H, int hidden,
-                                     const mmae_dechead_params* p, const mmae_dechead_grads* g, const float* dx_out,
-                                     float* denc, const void* saved, void* ws, void* st) {
-  (void)enc;
-  MMAE_CHECK(ixp && p && g && dx_out && denc && saved && ws, MMAE_ERR_ARG, "mmae_dechead_backward: bad args");
+extern "C" int mmae_dechead_forward(const float* enc, int De, const mmae_decoder_index* ixp, int H, int hidden, float eps,
+                                    const mmae_dechead_params* p, float* x_out, void* saved, void* ws, void* st) {
+  MMAE_CHECK(enc && De > 0, MMAE_ERR_ARG, "mmae_dechead_forward: bad args");
+  return dechead_forward_impl(enc, nullptr, 0, De, ixp, H, hidden, eps, p, x_out, saved, ws, st);
+}
+extern "C" int mmae_dechead_forward_ctx(const float* ctx, int64_t ld_ctx, const mmae_decoder_index* ixp, int H, int hidden,
+                                        float eps, const mmae_dechead_params* p, float* x_out, void* saved, void* ws,
+                                        void* st) {
+  MMAE_CHECK(ctx, MMAE_ERR_ARG, "mmae_dechead_forward_ctx: bad args");
+  return dechead_forward_impl(nullptr, ctx, ld_ctx, 0, ixp, H, hidden, eps, p, x_out, saved, ws, st);
+}
+
+// `dctx_ext` != null: the bf16 context gradient goes to the adapter's column segment of the shared [Mc, sum Dd] matrix
+// (row stride ld_dctx) and the proj_context weight / encoder-output gradients are left to mmae_ctxproj_backward.
+static int dechead_backward_impl(int De, const mmae_decoder_index* ixp, int H, int hidden, const mmae_dechead_params* p,
+                                 const mmae_dechead_grads* g, const float* dx_out, float* denc, void* dctx_ext,
+                                 int64_t ld_dctx, const void* saved, void* ws, void* st) {
+  MMAE_CHECK(ixp && p && g && dx_out && (denc || dctx_ext) && saved && ws, MMAE_ERR_ARG, "mmae_dechead_backward: bad args");
+  MMAE_CHECK(!dctx_ext || (ld_dctx % 8 == 0 && (reinterpret_cast<uintptr_t>(dctx_ext) & 15) == 0), MMAE_ERR_ARG,
+             "mmae_dechead_backward_ctx: the gradient segment must be 16-byte aligned with a row stride that is a multiple of 8");
   const mmae_decoder_index& ix = *ixp;
   const int Dd = ix.dim, B = ix.batch, P = ix.num_queries, Nc = ix.num_visible + ix.num_global;
   const int Mq = B * P, Mc = B * Nc, dh = Dd / H;
   HeadSaved s = head_saved(const_cast<void*>(saved), ix, De, H, hidden);
-  RUN(weight_operand(p->proj_context_w, &s.wpc, 0, false, st));
+  if (!dctx_ext) RUN(weight_operand(p->proj_context_w, &s.wpc, 0, false, st));
   RUN(weight_operand(p->q_w, &s.wq, 0, false, st));
   RUN(weight_operand(p->kv_w, &s.wkv, 0, false, st));
   RUN(weight_operand(p->proj_w, &s.wproj, 0, false, st));
@@ -508,6 +531,8 @@ extern "C" int mmae_dechead_backward(const float* enc, int De, const mmae_decode
   for (int t = 0; t < MMAE_MAX_TASKS; ++t) dte.p[t] = g->task_emb[t];
   RUN(launch_dec_build_bwd(w.dqueries, w.dcontext, ix, w.dctx, g->mask_token, dte, cst));
   // ---- proj_context
+  if (dctx_ext)   // bf16 cast into the shared matrix + the bias gradient; weight / encoder gradients: mmae_ctxproj_backward
+    return mmae_cast_colsum_f32(w.dctx, Dd, dctx_ext, ld_dctx, g->proj_context_b, Mc, Dd, st);
   RUN(mmae_cast_colsum_f32(w.dctx, Dd, w.dctx_b, Dd, g->proj_context_b, Mc, Dd, st));
   RUN(wgrad(w.dctx_b, Dd, s.enc_b, De, g->proj_context_w, Mc, Dd, De, st));
   {
@@ -518,6 +543,146 @@ extern "C" int mmae_dechead_backward(const float* enc, int De, const mmae_decode
     RUN(mmae_gemm_bf16(w.dctx_b, Dd, 0, s.wpc, De, 1, Mc, De, Dd, 1, &ep, st));
   }
   return MMAE_OK;
+}
+
+extern "C" int mmae_dechead_backward(const float* enc, int De, const mmae_decoder_index* ixp, int H, int hidden,
+                                     const mmae_dechead_params* p, const mmae_dechead_grads* g, const float* dx_out,
+                                     float* denc, const void* saved, void* ws, void* st) {
+  (void)enc;
+  MMAE_CHECK(denc && De > 0, MMAE_ERR_ARG, "mmae_dechead_backward: bad args");
+  return dechead_backward_impl(De, ixp, H, hidden, p, g, dx_out, denc, nullptr, 0, saved, ws, st);
+}
+extern "C" int mmae_dechead_backward_ctx(const mmae_decoder_index* ixp, int H, int hidden, const mmae_dechead_params* p,
+                                         const mmae_dechead_grads* g, const float* dx_out, void* dctx_bf16,
+                                         int64_t ld_dctx, const void* saved, void* ws, void* st) {
+  MMAE_CHECK(dctx_bf16, MMAE_ERR_ARG, "mmae_dechead_backward_ctx: bad args");
+  return dechead_backward_impl(0, ixp, H, hidden, p, g, dx_out, nullptr, dctx_bf16, ld_dctx, saved, ws, st);
+}
+
+// ============================================================================== shared context projection
+// MultiMAE.forward hands the SAME encoder output to every output adapter (multimae/multimae.py:357-366) and each adapter
+// starts with its own proj_context Linear (multimae/output_adapters.py:258).  Here the n Linears are one GEMM
+//   ctx[rows, sum_i Dd_i] = bf16(enc)[rows, De] x Wcat[sum_i Dd_i, De]^T + bcat
+// (one bf16 cast of enc instead of n; N = 1024 instead of four 256-column problems), and in backward
+//   dWcat += dctx^T enc_b  (one K = rows GEMM)      denc = dctx Wcat  (one K = sum Dd GEMM, written - not n accumulated
+// fp32 read-modify-write passes plus n zero fills and n-1 adds on the autograd side).
+// Wcat / bcat / dWcat are used IN PLACE when the adapters' parameters (and their bf16 mirror, and their gradient slots)
+// lie back to back - the flat arena orders them that way (functional.GradArena) - and are gathered otherwise.
+namespace {
+struct CtxSaved {
+  bf16 *enc_b, *wcat;
+  float* bcat;
+  size_t bytes;
+};
+CtxSaved ctx_saved(void* base, int rows, int De, int Dsum) {
+  Carver c(base);
+  CtxSaved s;
+  s.enc_b = c.take<bf16>(size_t(rows) * De);
+  s.wcat = c.take<bf16>(size_t(Dsum) * De);
+  s.bcat = c.take<float>(Dsum);
+  s.bytes = align_up(c.off, 256);
+  return s;
+}
+int ctx_dims_ok(const mmae_ctxproj_params* p, int* dsum) {
+  if (!p || p->num < 1 || p->num > MMAE_MAX_TASKS) return 0;
+  int tot = 0;
+  for (int i = 0; i < p->num; ++i) {
+    if (p->dim[i] <= 0 || p->dim[i] % 8 != 0 || !p->weight[i] || !p->bias[i]) return 0;
+    tot += p->dim[i];
+  }
+  *dsum = tot;
+  return 1;
+}
+// bf16 [Dsum, De] operand: the mirror in place when the n twins are adjacent, else gathered into s.wcat (fill = forward)
+int ctx_weight_operand(const mmae_ctxproj_params* p, int De, const CtxSaved& s, bool fill, const bf16** out, void* st) {
+  const bf16* m0 = mirror_lookup(p->weight[0]);
+  bool inplace = m0 != nullptr;
+  int64_t off = 0;
+  for (int i = 0; i < p->num && inplace; ++i) {
+    inplace = mirror_lookup(p->weight[i]) == m0 + off * De;
+    off += p->dim[i];
+  }
+  if (inplace) {
+    *out = m0;
+    return MMAE_OK;
+  }
+  *out = s.wcat;
+  if (!fill) return MMAE_OK;
+  off = 0;
+  for (int i = 0; i < p->num; ++i) {
+    const int64_t n = int64_t(p->dim[i]) * De;
+    if (const bf16* m = mirror_lookup(p->weight[i]))
+      MMAE_CUDA_OK(cudaMemcpyAsync(s.wcat + off * De, m, n * sizeof(bf16), cudaMemcpyDeviceToDevice,
+                                   reinterpret_cast<cudaStream_t>(st)));
+    else
+      RUN(mmae_cast_f32_to_bf16(p->weight[i], s.wcat + off * De, n, st));
+    off += p->dim[i];
+  }
+  return MMAE_OK;
+}
+}  // namespace
+
+extern "C" int64_t mmae_ctxproj_saved_bytes(int rows, int D_enc, int dim_total) {
+  return (int64_t)ctx_saved(nullptr, rows, D_enc, dim_total).bytes;
+}
+
+extern "C" int mmae_ctxproj_forward(const float* enc, int rows, int De, const mmae_ctxproj_params* p, float* ctx,
+                                    void* saved, void* st) {
+  int Dsum = 0;
+  MMAE_CHECK(enc && ctx && saved && rows > 0 && De > 0 && De % 8 == 0 && ctx_dims_ok(p, &Dsum), MMAE_ERR_ARG,
+             "mmae_ctxproj_forward: bad args (1..%d adapters, dims multiples of 8)", MMAE_MAX_TASKS);
+  CtxSaved s = ctx_saved(saved, rows, De, Dsum);
+  RUN(mmae_cast_f32_to_bf16(enc, s.enc_b, int64_t(rows) * De, st));
+  const bf16* W = nullptr;
+  RUN(ctx_weight_operand(p, De, s, true, &W, st));
+  const float* bias = p->bias[0];
+  bool adjacent = true;
+  int64_t off = 0;
+  for (int i = 0; i < p->num; ++i) {
+    adjacent = adjacent && p->bias[i] == p->bias[0] + off;
+    off += p->dim[i];
+  }
+  if (!adjacent) {
+    off = 0;
+    for (int i = 0; i < p->num; ++i) {
+      MMAE_CUDA_OK(cudaMemcpyAsync(s.bcat + off, p->bias[i], size_t(p->dim[i]) * sizeof(float), cudaMemcpyDeviceToDevice,
+                                   reinterpret_cast<cudaStream_t>(st)));
+      off += p->dim[i];
+    }
+    bias = s.bcat;
+  }
+  return linear_f32(s.enc_b, W, bias, nullptr, ctx, rows, Dsum, De, st);
+}
+
+extern "C" int mmae_ctxproj_backward(int rows, int De, const mmae_ctxproj_params* p, const mmae_ctxproj_grads* g,
+                                     const void* dctx_bf16, float* denc, const void* saved, void* st) {
+  int Dsum = 0;
+  MMAE_CHECK(g && dctx_bf16 && denc && saved && rows > 0 && De > 0 && ctx_dims_ok(p, &Dsum), MMAE_ERR_ARG,
+             "mmae_ctxproj_backward: bad args");
+  for (int i = 0; i < p->num; ++i) MMAE_CHECK(g->weight[i], MMAE_ERR_ARG, "mmae_ctxproj_backward: null gradient slot %d", i);
+  CtxSaved s = ctx_saved(const_cast<void*>(saved), rows, De, Dsum);
+  const bf16* W = nullptr;
+  RUN(ctx_weight_operand(p, De, s, false, &W, st));
+  const bf16* dctx = reinterpret_cast<const bf16*>(dctx_bf16);
+  bool adjacent = true;
+  int64_t off = 0;
+  for (int i = 0; i < p->num; ++i) {
+    adjacent = adjacent && g->weight[i] == g->weight[0] + off * De;
+    off += p->dim[i];
+  }
+  if (adjacent) {
+    RUN(wgrad(dctx, Dsum, s.enc_b, De, g->weight[0], rows, Dsum, De, st));
+  } else {
+    off = 0;
+    for (int i = 0; i < p->num; ++i) {
+      RUN(wgrad(dctx + off, Dsum, s.enc_b, De, g->weight[i], rows, p->dim[i], De, st));
+      off += p->dim[i];
+    }
+  }
+  mmae_gemm_epilogue ep = ep_zero();
+  ep.out_f32 = denc;
+  ep.ld_out_f32 = De;
+  return mmae_gemm_bf16(dctx, Dsum, 0, W, De, 1, rows, De, Dsum, 1, &ep, st);
 }
 
 // ================================================================================================ decoder tail

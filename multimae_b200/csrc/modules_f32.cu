@@ -245,7 +245,7 @@ extern "C" int mmae_dechead_f32_forward(const float* enc, int De, const mmae_dec
   RUN(linear_f32x3_forward(enc, p->proj_context_w, p->proj_context_b, nullptr, w.ctx, Mc, Dd, De, w.sp.A, w.sp.B, st));   // output_adapters.py:258
   TaskEmbPtrs te;
   for (int t = 0; t < MMAE_MAX_TASKS; ++t) te.p[t] = p->task_emb[t];
-  RUN(launch_dec_build(w.ctx, ix, p->mask_token, te, p->pos, s.queries, s.context, cst));                               // :183-234
+  RUN(launch_dec_build(w.ctx, ix.dim, ix, p->mask_token, te, p->pos, s.queries, s.context, cst));                               // :183-234
   RUN(mmae_layernorm_forward(s.queries, Dd, p->query_norm_w, p->query_norm_b, nullptr, 0, s.qn, Dd, s.qmean, s.qrstd, Mq, Dd, eps, st));
   RUN(mmae_layernorm_forward(s.context, Dd, p->context_norm_w, p->context_norm_b, nullptr, 0, s.cn, Dd, s.cmean, s.crstd, Mc, Dd, eps, st));
   RUN(linear_f32x3_forward(s.qn, p->q_w, p->q_b, nullptr, s.q, Mq, Dd, Dd, w.sp.A, w.sp.B, st));

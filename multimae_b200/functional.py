@@ -281,6 +281,75 @@ HEAD_PARAM_NAMES = ["proj_context.weight", "proj_context.bias", "mask_token", "c
                     "decoder.proj.bias", "mlp.fc1.weight", "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias"]
 
 
+class SharedContextFunction(torch.autograd.Function):
+    """proj_context (multimae/output_adapters.py:258) of every half-precision output adapter as ONE GEMM on the encoder
+    output they all receive (multimae/multimae.py:357-366): enc [B, Nc, De] -> ctx [B*Nc, sum_i Dd_i] fp32; adapter i reads
+    its column segment through DecoderHeadFunction (meta["shared"]).
+
+    args: enc, meta, then (proj_context.weight, proj_context.bias) per adapter.  meta: arena, weight_names (arena names of
+    the weights), on_grads_ready, state (dict shared with the heads).  Backward protocol: each head writes its bf16 context
+    gradient into its segment of state["dctx"] and appends a completion event to state["events"] (the heads run on their
+    own streams); it returns no gradient for `ctx`, so autograd calls this backward - after all heads - with None, and the
+    weight-gradient GEMM and the ONE input-gradient GEMM run here.  The bias gradients are produced by the heads."""
+
+    @staticmethod
+    def forward(ctx, enc, meta, *wb):
+        _require_cuda(enc, "proj_context")
+        ctx.set_materialize_grads(False)
+        lib = L.lib()
+        enc = enc.contiguous().float()
+        B, Nc, De = enc.shape
+        rows = B * Nc
+        weights = wb[0::2]
+        prm = L.CtxProjParams()
+        prm.num = len(weights)
+        for i, (w, b) in enumerate(zip(weights, wb[1::2])):
+            prm.dim[i], prm.weight[i], prm.bias[i] = w.shape[0], w.data_ptr(), b.data_ptr()
+        dsum = sum(w.shape[0] for w in weights)
+        saved = torch.empty(lib.mmae_ctxproj_saved_bytes(rows, De, dsum), dtype=torch.uint8, device=enc.device)
+        out = torch.empty((rows, dsum), dtype=torch.float32, device=enc.device)
+        L.check(lib.mmae_ctxproj_forward(enc.data_ptr(), rows, De, ctypes.byref(prm), out.data_ptr(), saved.data_ptr(),
+                                         L.current_stream()), "mmae_ctxproj_forward")
+        state = meta["state"]
+        state["events"] = []
+        # zero-filled: the segment of an adapter whose prediction does not reach the loss is never written
+        state["dctx"] = (torch.zeros((rows, dsum), dtype=torch.bfloat16, device=enc.device)
+                         if any(ctx.needs_input_grad) else None)
+        ctx.meta, ctx.wb, ctx.dims = meta, wb, (B, Nc, De, dsum)
+        ctx.save_for_backward(saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, _unused):
+        lib = L.lib()
+        (saved,) = ctx.saved_tensors
+        meta, wb = ctx.meta, ctx.wb
+        B, Nc, De, dsum = ctx.dims
+        state, arena, names = meta["state"], meta["arena"], meta["weight_names"]
+        weights = wb[0::2]
+        if saved.is_cuda:                          # the heads ran their backward on the task decoders' streams
+            cur = torch.cuda.current_stream()
+            for ev in state["events"]:
+                cur.wait_event(ev)
+        state["events"] = []
+        prm, grd = L.CtxProjParams(), L.CtxProjGrads()
+        prm.num = len(weights)
+        for i, (w, b) in enumerate(zip(weights, wb[1::2])):
+            prm.dim[i], prm.weight[i], prm.bias[i] = w.shape[0], w.data_ptr(), b.data_ptr()
+            grd.weight[i] = _grad_ptr(arena, names[i])
+        denc = torch.empty((B, Nc, De), dtype=torch.float32, device=saved.device)
+        L.check(lib.mmae_ctxproj_backward(B * Nc, De, ctypes.byref(prm), ctypes.byref(grd), state["dctx"].data_ptr(),
+                                          denc.data_ptr(), saved.data_ptr(), L.current_stream()), "mmae_ctxproj_backward")
+        state["dctx"] = None
+        if meta.get("on_grads_ready") is not None:
+            meta["on_grads_ready"](list(names))
+        gw = _ret_grads(arena, names, weights)
+        out = []
+        for g in gw:
+            out += [g, None]                       # bias gradients: DecoderHeadFunction
+        return (denc, None) + tuple(out)
+
+
 def _fill_head_struct(st, vals, task_vals):
     """vals follow HEAD_PARAM_NAMES order; task_vals is the per-context-task pointer list."""
     (st.proj_context_w, st.proj_context_b, st.mask_token, st.context_norm_w, st.context_norm_b, st.query_norm_w,
@@ -294,14 +363,21 @@ class DecoderHeadFunction(torch.autograd.Function):
     """proj_context .. x + mlp(out_norm(x)) of SpatialOutputAdapter.forward (multimae/output_adapters.py:258-266).
 
     args: enc, meta, ids_keep, ids_restore, then the 19 HEAD_PARAM_NAMES tensors, then one task embedding (or None)
-    per context task."""
+    per context task.  With meta["shared"] (dict: offset, ld, state, enc_shape) `enc` is the output of
+    SharedContextFunction instead, proj_context.weight is passed as None, and the head starts / ends at its column
+    segment of the shared projection / gradient matrix."""
 
     @staticmethod
     def forward(ctx, enc, meta, ids_keep, ids_restore, *params):
         _require_cuda(enc, "SpatialOutputAdapter")
         lib = L.lib()
-        enc = enc.contiguous().float()
-        B, Nc, De = enc.shape
+        shared = meta.get("shared")
+        if shared is None:
+            enc = enc.contiguous().float()
+            B, Nc, De = enc.shape
+        else:
+            assert not meta.get("fp32") and enc.dtype == torch.float32 and enc.is_contiguous()
+            B, Nc, De = shared["enc_shape"]
         ix = L.DecoderIndex()
         ix.batch, ix.dim, ix.num_global = B, meta["dim"], meta["num_global"]
         ix.num_visible = Nc - meta["num_global"]
@@ -316,19 +392,26 @@ class DecoderHeadFunction(torch.autograd.Function):
         H, hidden, eps = meta["heads"], meta["hidden"], meta["eps"]
         main, task = params[:len(HEAD_PARAM_NAMES)], params[len(HEAD_PARAM_NAMES):]
         prm = L.DecHeadParams()
-        _fill_head_struct(prm, [p.data_ptr() for p in main], [None if p is None else p.data_ptr() for p in task])
+        _fill_head_struct(prm, [L.ptr(p) for p in main], [None if p is None else p.data_ptr() for p in task])
         prm.pos = meta["pos"].data_ptr()
         f32 = "_f32" if meta.get("fp32") else ""
-        saved = torch.empty(getattr(lib, "mmae_dechead%s_saved_bytes" % f32)(ctypes.byref(ix), De, H, hidden),
+        De_q = De if shared is None else 0            # *_ctx heads hold no encoder copy / proj_context operand
+        saved = torch.empty(getattr(lib, "mmae_dechead%s_saved_bytes" % f32)(ctypes.byref(ix), De_q, H, hidden),
                             dtype=torch.uint8, device=enc.device)
-        ws = Workspace.get(getattr(lib, "mmae_dechead%s_workspace_bytes" % f32)(ctypes.byref(ix), De, H, hidden), enc.device)
+        ws = Workspace.get(getattr(lib, "mmae_dechead%s_workspace_bytes" % f32)(ctypes.byref(ix), De_q, H, hidden), enc.device)
         out = torch.empty((B, ix.num_queries, ix.dim), dtype=torch.float32, device=enc.device)
-        L.check(getattr(lib, "mmae_dechead%s_forward" % f32)(enc.data_ptr(), De, ctypes.byref(ix), H, hidden, eps,
-                                                             ctypes.byref(prm), out.data_ptr(), saved.data_ptr(),
-                                                             ws.data_ptr(), L.current_stream()),
-                "mmae_dechead%s_forward" % f32)
-        ctx.meta, ctx.params, ctx.ix = meta, params, ix
-        ctx.save_for_backward(enc, saved, ids_keep, ids_restore)
+        if shared is None:
+            L.check(getattr(lib, "mmae_dechead%s_forward" % f32)(enc.data_ptr(), De, ctypes.byref(ix), H, hidden, eps,
+                                                                 ctypes.byref(prm), out.data_ptr(), saved.data_ptr(),
+                                                                 ws.data_ptr(), L.current_stream()),
+                    "mmae_dechead%s_forward" % f32)
+        else:
+            L.check(lib.mmae_dechead_forward_ctx(enc.data_ptr() + 4 * shared["offset"], shared["ld"], ctypes.byref(ix), H,
+                                                 hidden, eps, ctypes.byref(prm), out.data_ptr(), saved.data_ptr(),
+                                                 ws.data_ptr(), L.current_stream()), "mmae_dechead_forward_ctx")
+        ctx.meta, ctx.params, ctx.ix, ctx.enc_shape = meta, params, ix, (B, Nc, De)
+        # the shared projection is not needed again: queries / context are in `saved`
+        ctx.save_for_backward(enc if shared is None else enc.new_empty(0), saved, ids_keep, ids_restore)
         return out
 
     @staticmethod
@@ -336,29 +419,45 @@ class DecoderHeadFunction(torch.autograd.Function):
         lib = L.lib()
         enc, saved, ids_keep, ids_restore = ctx.saved_tensors
         meta, params, ix = ctx.meta, ctx.params, ctx.ix
-        B, Nc, De = enc.shape
+        B, Nc, De = ctx.enc_shape
+        shared = meta.get("shared")
         H, hidden = meta["heads"], meta["hidden"]
         arena, prefix = meta["arena"], meta["prefix"]
         main, task = params[:len(HEAD_PARAM_NAMES)], params[len(HEAD_PARAM_NAMES):]
         names = [prefix + n for n in HEAD_PARAM_NAMES]
         task_names = [None if p is None else prefix + "task_embeddings." + tn for p, tn in zip(task, meta["task_names"])]
         prm, grd = L.DecHeadParams(), L.DecHeadGrads()
-        _fill_head_struct(prm, [p.data_ptr() for p in main], [None if p is None else p.data_ptr() for p in task])
+        _fill_head_struct(prm, [L.ptr(p) for p in main], [None if p is None else p.data_ptr() for p in task])
         prm.pos = meta["pos"].data_ptr()
-        _fill_head_struct(grd, [_grad_ptr(arena, n) for n in names],
+        # main[0] (proj_context.weight) is None under the shared projection: its gradient belongs to SharedContextFunction
+        _fill_head_struct(grd, [None if p is None else _grad_ptr(arena, n) for n, p in zip(names, main)],
                           [None if n is None else _grad_ptr(arena, n) for n in task_names])
         f32 = "_f32" if meta.get("fp32") else ""
-        ws = Workspace.get(getattr(lib, "mmae_dechead%s_workspace_bytes" % f32)(ctypes.byref(ix), De, H, hidden), enc.device)
+        De_q = De if shared is None else 0
+        ws = Workspace.get(getattr(lib, "mmae_dechead%s_workspace_bytes" % f32)(ctypes.byref(ix), De_q, H, hidden), dout.device)
         dout = dout.contiguous().float()
-        denc = torch.zeros_like(enc)
-        L.check(getattr(lib, "mmae_dechead%s_backward" % f32)(enc.data_ptr(), De, ctypes.byref(ix), H, hidden,
-                                                              ctypes.byref(prm), ctypes.byref(grd), dout.data_ptr(),
-                                                              denc.data_ptr(), saved.data_ptr(), ws.data_ptr(),
-                                                              L.current_stream()), "mmae_dechead%s_backward" % f32)
+        if shared is None:
+            denc = torch.zeros_like(enc)
+            L.check(getattr(lib, "mmae_dechead%s_backward" % f32)(enc.data_ptr(), De, ctypes.byref(ix), H, hidden,
+                                                                  ctypes.byref(prm), ctypes.byref(grd), dout.data_ptr(),
+                                                                  denc.data_ptr(), saved.data_ptr(), ws.data_ptr(),
+                                                                  L.current_stream()), "mmae_dechead%s_backward" % f32)
+        else:
+            denc, state = None, shared["state"]
+            L.check(lib.mmae_dechead_backward_ctx(ctypes.byref(ix), H, hidden, ctypes.byref(prm), ctypes.byref(grd),
+                                                  dout.data_ptr(), state["dctx"].data_ptr() + 2 * shared["offset"],
+                                                  shared["ld"], saved.data_ptr(), ws.data_ptr(), L.current_stream()),
+                    "mmae_dechead_backward_ctx")
+            if dout.is_cuda:
+                state["events"].append(torch.cuda.current_stream().record_event())
+            names = [n for n, p in zip(names, main) if p is not None]
+            main = tuple(p for p in main if p is not None)
         all_names = names + [n for n in task_names if n is not None]
         if meta.get("on_grads_ready") is not None:
             meta["on_grads_ready"](all_names)
         g_main = _ret_grads(arena, names, main)
+        if shared is not None:
+            g_main = [None] + list(g_main)             # the slot of proj_context.weight (passed as None)
         g_task = [None if n is None else _ret_grads(arena, [n], [p])[0] for n, p in zip(task_names, task)]
         return (denc, None, None, None) + tuple(g_main) + tuple(g_task)
 

@@ -19,6 +19,7 @@ from torch.distributions.dirichlet import Dirichlet
 from . import _lib as L
 from . import functional as Fn
 from .multimae_utils import Block, trunc_normal_
+from .output_adapters import SpatialOutputAdapter
 
 try:  # the reference's timm-style registry, when the reference tree is importable (drop-in overlay); else a local one
     from utils.registry import register_model  # type: ignore
@@ -35,6 +36,8 @@ __all__ = ["pretrain_multimae_base", "pretrain_multimae_large", "multivit_base",
 # gradient arena on its first training forward, so that the script's scaler (which only sees model.parameters()) takes the
 # one-pass unscale / norm path instead of ~344 per-tensor launches, and autograd does not clone 98 M gradients per step.
 AUTO_OWN_GRADIENTS = False
+# one GEMM for the proj_context Linears of all half-precision output adapters (MultiMAE._project_contexts); 0: one per adapter
+SHARED_CONTEXT_PROJECTION = os.environ.get("MMAE_SHARED_CTX", "1") != "0"
 
 
 def _build_layout(adapters, x):
@@ -171,6 +174,15 @@ class MultiMAE(nn.Module):
         device = device if device is not None else self.global_tokens.device
         if self._arena is None or self._arena.flat.device != device:
             named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+            # proj_context weights (then biases) of the output adapters back to back: their gradient slots - and, once
+            # FlatAdamW lays parameters / moments / the bf16 mirror out like the arena, the operands themselves - form ONE
+            # [sum Dd, D_enc] matrix that the shared context projection (SharedContextFunction) uses in place
+            for suffix in (".proj_context.weight", ".proj_context.bias"):
+                pc = [i for i, (n, _) in enumerate(named) if n.startswith("output_adapters.") and n.endswith(suffix)]
+                if len(pc) > 1:
+                    moved = [named[i] for i in pc]
+                    rest = [e for i, e in enumerate(named) if i not in set(pc)]
+                    named = rest[:pc[0]] + moved + rest[pc[0]:]
             self._arena = Fn.GradArena(named, device)
             self._bind()
         return self._arena
@@ -332,6 +344,35 @@ class MultiMAE(nn.Module):
         preds = self._decode(encoder_tokens, input_info, ids_keep, ids_restore, fp32_output_adapters)
         return preds, task_masks
 
+    def _project_contexts(self, encoder_tokens, domains):
+        """One GEMM for the proj_context Linears (multimae/output_adapters.py:258) of the half-precision spatial adapters -
+        they all project the same encoder output (multimae/multimae.py:357-366).  Returns {domain: shared_ctx dict} (empty
+        when fewer than two adapters qualify or MMAE_SHARED_CTX=0)."""
+        if not SHARED_CONTEXT_PROJECTION or self._arena is None:
+            return {}
+        group = []
+        for d in domains:
+            ad = self.output_adapters[d]
+            if (isinstance(ad, SpatialOutputAdapter) and ad.use_xattn and ad.dim_tokens % 8 == 0
+                    and ad.dim_tokens_enc == encoder_tokens.shape[-1] and ad._bound is not None
+                    and ad._bound["arena"] is self._arena):
+                group.append(d)
+        if not 2 <= len(group) <= L.MAX_TASKS:
+            return {}
+        adapters = [self.output_adapters[d] for d in group]
+        wb = []
+        for ad in adapters:
+            wb += [ad.proj_context.weight, ad.proj_context.bias]
+        state = {}
+        meta = dict(arena=self._arena, weight_names=["output_adapters.%s.proj_context.weight" % d for d in group],
+                    on_grads_ready=self._grad_callback, state=state)
+        ctx = Fn.SharedContextFunction.apply(encoder_tokens, meta, *wb)
+        out, off = {}, 0
+        for d, ad in zip(group, adapters):
+            out[d] = dict(ctx=ctx, offset=off, ld=ctx.shape[1], state=state, enc_shape=tuple(encoder_tokens.shape))
+            off += ad.dim_tokens
+        return out
+
     def _decode(self, encoder_tokens, input_info, ids_keep, ids_restore, fp32_output_adapters=()):
         """The task decoders are independent of each other (multimae/multimae.py:372-381 runs them in a Python loop):
         on CUDA each runs on its own stream, forward and (through autograd's stream tracking) backward, so their
@@ -342,9 +383,13 @@ class MultiMAE(nn.Module):
         # multimae/multimae.py:367-377); custom adapter classes without the switch are called as the reference does
         fp32 = {d for d in (fp32_output_adapters or ()) if d in self.output_adapters}
 
+        shared = self._project_contexts(encoder_tokens, [d for d in domains if d not in fp32])
+
         def run(d):
             if d in fp32:
                 return self.output_adapters[d](fp32=True, **kw)
+            if d in shared:
+                return self.output_adapters[d](shared_ctx=shared[d], **kw)
             return self.output_adapters[d](**kw)
 
         if not (self.decoder_streams and encoder_tokens.is_cuda and len(domains) > 1):
@@ -354,6 +399,11 @@ class MultiMAE(nn.Module):
             self._dec_streams = [torch.cuda.Stream(device=dev) for _ in domains]
         main = torch.cuda.current_stream(dev)
         ready = main.record_event()
+        for sh in list(shared.values())[:1]:          # allocated on this stream, read / written on the decoders' streams
+            for st in self._dec_streams:
+                sh["ctx"].record_stream(st)
+                if sh["state"].get("dctx") is not None:
+                    sh["state"]["dctx"].record_stream(st)
         preds = {}
         for d, st in zip(domains, self._dec_streams):
             st.wait_event(ready)

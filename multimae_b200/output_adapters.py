@@ -104,9 +104,11 @@ class SpatialOutputAdapter(nn.Module, _PosEmbCache):
                 self.mlp.fc1.bias, self.mlp.fc2.weight, self.mlp.fc2.bias)
 
     def forward(self, encoder_tokens: torch.Tensor, input_info: Dict, ids_keep: torch.Tensor, ids_restore: torch.Tensor,
-                fp32: bool = False):
+                fp32: bool = False, shared_ctx: Dict = None):
         """`fp32` (beyond the reference signature): run the whole adapter in the fp32 tier - what the reference does for the
-        adapters listed in `fp32_output_adapters` by calling them outside autocast (multimae/multimae.py:367-377)."""
+        adapters listed in `fp32_output_adapters` by calling them outside autocast (multimae/multimae.py:367-377).
+        `shared_ctx` (set by MultiMAE._decode): proj_context was already applied for all adapters in one GEMM
+        (functional.SharedContextFunction); dict(ctx=[B*Nc, sum Dd] tensor, offset, ld, state, enc_shape)."""
         assert self.dim_tokens_enc is not None, "Need to call init(dim_tokens_enc) function first"
         if not self.use_xattn:
             raise NotImplementedError("multimae_b200: use_xattn=False is outside the pre-training hot path")
@@ -148,8 +150,14 @@ class SpatialOutputAdapter(nn.Module, _PosEmbCache):
                          num_queries=nh * nw, tok_offset=tok_offset, own_task=own_task, query_mode=query_mode,
                          heads=self.num_heads, hidden=self.mlp_hidden, eps=self.query_norm.eps,
                          pos=self._resized_pos(nh, nw, "bilinear"), task_names=task_names, fp32=bool(fp32))
-        x = Fn.DecoderHeadFunction.apply(encoder_tokens, head_meta, ids_keep, ids_restore, *self._head_params(),
-                                         *task_embs)
+        head_params = self._head_params()
+        head_in = encoder_tokens
+        if shared_ctx is not None:
+            assert not fp32, "the shared context projection is the half-precision tier"
+            head_meta["shared"] = {k: shared_ctx[k] for k in ("offset", "ld", "state", "enc_shape")}
+            head_in = shared_ctx["ctx"]
+            head_params = (None,) + head_params[1:]          # proj_context.weight: used and differentiated by the shared GEMM
+        x = Fn.DecoderHeadFunction.apply(head_in, head_meta, ids_keep, ids_restore, *head_params, *task_embs)
         if fp32 and isinstance(self.decoder_transformer, nn.Sequential):
             for blk in self.decoder_transformer:
                 x = blk(x, fp32=True)

@@ -91,7 +91,7 @@ def attach_data_parallel(model, scaler=None, process_group=None, bucket_bytes=No
     if bucket_bytes is None:
         bucket_bytes = int(float(os.environ.get("MMAE_BUCKET_MB", "48")) * (1 << 20))
     arena = model.own_gradients(True)
-    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    names = list(arena.offsets)      # the arena's own order (registration order, proj_context tensors grouped): contiguous buckets
     reducer = FlatGradReducer(arena, names, process_group, bucket_bytes)
     arena.reducer = reducer            # found again by a scaler that only ever sees model.parameters() (overlay launcher)
     model.set_grad_callback(reducer.on_grads_ready)

@@ -177,6 +177,57 @@ def test_model_against_golden_and_oracle(golden_dir, dev, name):
         assert abs(float(named[k].grad.float().norm()) - float(d["norm"])) < PER_TENSOR_TOL * max(float(d["norm"]), fair), k
 
 
+@pytest.mark.parametrize("flat_optimizer", [False, True])
+@pytest.mark.parametrize("leave_out", [None, "depth"])
+def test_shared_context_projection_matches_per_adapter(golden_dir, dev, monkeypatch, flat_optimizer, leave_out):
+    """The proj_context Linears of the four output adapters as ONE GEMM on the shared encoder output (the default,
+    mmae_ctxproj_* + mmae_dechead_*_ctx) against one GEMM per adapter (MMAE_SHARED_CTX=0, multimae/output_adapters.py:258 as
+    the reference runs it): same bf16 operands and K order forward -> equal predictions; backward sums the four context
+    gradients inside one K = sum Dd GEMM instead of four accumulated passes -> gradients equal to fp32 reassociation carried
+    through the bf16 encoder backward.  `flat_optimizer`: parameters / bf16 mirror / gradient slots of the four Linears lie
+    back to back and are used in place (FlatAdamW) vs gathered.  `leave_out`: a prediction that does not reach the loss -
+    its head's backward never runs, its segment of the shared gradient matrix must count as zero."""
+    from multimae_b200 import multimae as MM
+    from multimae_b200.optim import FlatAdamW
+    fx = _load(golden_dir, "cuda_small.pt")
+    c = fx["config"]
+    triple = ({k: v.to(dev) for k, v in fx["task_masks"].items()}, fx["ids_keep"].to(dev), fx["ids_restore"].to(dev))
+
+    def run(shared):
+        monkeypatch.setattr(MM, "SHARED_CONTEXT_PROJECTION", shared)
+        model = _build_model(c)
+        formula_fill_(list(model.named_parameters()))
+        model = model.to(dev).train()
+        model.generate_random_masks = lambda *a, **k: triple
+        if flat_optimizer:
+            opt = FlatAdamW(model, lr=1e-3)      # noqa: F841  (keeps the bf16 mirror registered)
+        before = L.lib().mmae_launch_count()
+        preds, masks = model({k: v.to(dev) for k, v in fx["inputs"].items()}, num_encoded_tokens=12, alphas=1.0)
+        fns = _loss_modules()
+        loss = sum(fns[t](preds[t].float(), fx["inputs"]["rgb" if t == "norm_rgb" else t].to(dev),
+                          mask=masks.get("rgb" if t == "norm_rgb" else t)) for t in preds if t != leave_out)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in model.named_parameters() if p.requires_grad}
+        return {k: v.detach().clone() for k, v in preds.items()}, grads, L.lib().mmae_launch_count() - before
+
+    p_shared, g_shared, n_shared = run(True)
+    p_each, g_each, n_each = run(False)
+    assert n_shared < n_each                       # 3 casts of the encoder output, 3 forward and >= 6 backward GEMMs fewer
+    for k in p_each:
+        assert rel_l2(p_shared[k], p_each[k]) < 1e-5, (k, rel_l2(p_shared[k], p_each[k]))
+    names = [n for n in g_each if g_each[n] is not None and float(g_each[n].abs().sum()) > 0]
+    for n in g_each:
+        if n not in names:                         # e.g. the left-out adapter: no gradient either way
+            assert g_shared[n] is None or float(g_shared[n].abs().sum()) == 0.0, n
+    flat_s = torch.cat([g_shared[n].flatten() for n in names])
+    flat_e = torch.cat([g_each[n].flatten() for n in names])
+    assert rel_l2(flat_s, flat_e) < 5e-3, rel_l2(flat_s, flat_e)
+    for n in names:
+        if ".proj_context." in n:                  # same bf16 operands on both paths: fp32 summation order only
+            assert rel_l2(g_shared[n], g_each[n]) < 1e-4, (n, rel_l2(g_shared[n], g_each[n]))
+
+
 FP32_TOL = 1e-3          # north_star "1e-3 rel fp32": the fp32 tier of fp32_output_adapters against the fp32 oracle
 
 

@@ -132,7 +132,7 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     pairs = {"mmae_gemm_epilogue": L.GemmEpilogue, "mmae_embed_layout": L.EmbedLayout, "mmae_embed_inputs": L.EmbedInputs,
              "mmae_embed_params": L.EmbedParams, "mmae_embed_grads": L.EmbedGrads, "mmae_block_params": L.BlockParams,
              "mmae_block_grads": L.BlockGrads, "mmae_decoder_index": L.DecoderIndex, "mmae_dechead_params": L.DecHeadParams,
-             "mmae_dechead_grads": L.DecHeadGrads}
+             "mmae_dechead_grads": L.DecHeadGrads, "mmae_ctxproj_params": L.CtxProjParams, "mmae_ctxproj_grads": L.CtxProjGrads}
     header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "multimae_b200.h")
     declared = set(re.findall(r"^\} (mmae_\w+);", open(header).read(), re.M))
     assert declared == set(pairs), declared ^ set(pairs)

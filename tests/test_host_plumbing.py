@@ -52,8 +52,12 @@ def _inputs(B=2, size=64):
             "semseg": torch.randint(0, 133, (B, size // 4, size // 4))}
 
 
-def test_forward_backward_plumbing(stub):
+@pytest.mark.parametrize("shared_ctx", [True, False])
+def test_forward_backward_plumbing(stub, monkeypatch, shared_ctx):
+    """shared_ctx: the four adapters' proj_context Linears as one GEMM (the default) or one per adapter (MMAE_SHARED_CTX=0)."""
+    from multimae_b200 import multimae as MM
     from multimae_b200.criterion import MaskedCrossEntropyLoss, MaskedL1Loss, MaskedMSELoss
+    monkeypatch.setattr(MM, "SHARED_CONTEXT_PROJECTION", shared_ctx)
     model = _build().train()
     x = _inputs()
     preds, masks = model(x, num_encoded_tokens=12, alphas=1.0)
@@ -72,11 +76,21 @@ def test_forward_backward_plumbing(stub):
         else:
             assert p.grad is None, n
     # every module-level entry point was reached
+    head_f, head_b = ("mmae_dechead_forward_ctx", "mmae_dechead_backward_ctx") if shared_ctx else \
+        ("mmae_dechead_forward", "mmae_dechead_backward")
     for name in ("mmae_sample_masks", "mmae_embed_forward", "mmae_embed_backward", "mmae_block_forward",
-                 "mmae_block_backward", "mmae_dechead_forward", "mmae_dechead_backward", "mmae_dectail_forward",
+                 "mmae_block_backward", head_f, head_b, "mmae_dectail_forward",
                  "mmae_dectail_backward", "mmae_masked_loss_forward", "mmae_masked_loss_backward"):
         assert name in stub.calls, name
-    assert stub.calls.count("mmae_block_forward") == 2 + 4 * 1 and stub.calls.count("mmae_dechead_backward") == 4
+    assert stub.calls.count("mmae_block_forward") == 2 + 4 * 1 and stub.calls.count(head_b) == 4
+    assert stub.calls.count("mmae_ctxproj_forward") == stub.calls.count("mmae_ctxproj_backward") == (1 if shared_ctx else 0)
+    if shared_ctx:      # the shared projection's backward runs after the last head's, before the encoder's
+        order = [c for c in stub.calls if c in (head_b, "mmae_ctxproj_backward", "mmae_block_backward")]
+        i = order.index("mmae_ctxproj_backward")
+        assert order[:i].count(head_b) == 4 and order[i + 1:].count(head_b) == 0
+        # the proj_context tensors of the four adapters lie back to back in the arena (used in place as one matrix)
+        offs = [arena.offsets["output_adapters.%s.proj_context.weight" % k] for k in preds]
+        assert all(o1[0] + o1[1] == o2[0] for o1, o2 in zip(offs, offs[1:])), offs
     assert arena.numel >= sum(p.numel() for p in model.parameters() if p.requires_grad)
 
 

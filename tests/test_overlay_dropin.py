@@ -110,10 +110,17 @@ stats = R.train_one_epoch(model, [batch(), batch()], tasks_loss_fn, loss_balance
                           lr_schedule_values=[1e-4, 1e-4], wd_schedule_values=[0.05, 0.05], num_encoded_tokens=98,
                           in_domains=args.in_domains, loss_on_unmasked=False, alphas=1.0, sample_tasks_uniformly=False,
                           standardize_depth=True, extra_norm_pix_loss=True, fp32_output_adapters=["semseg"])
-for name in ("mmae_sample_masks", "mmae_embed_forward", "mmae_block_forward", "mmae_dechead_forward", "mmae_dectail_forward",
-             "mmae_masked_loss_forward", "mmae_masked_loss_backward", "mmae_dectail_backward", "mmae_dechead_backward",
-             "mmae_block_backward", "mmae_embed_backward"):
+# the three half-precision adapters (rgb, depth, norm_rgb) share ONE context projection GEMM and run the *_ctx heads
+for name in ("mmae_sample_masks", "mmae_embed_forward", "mmae_block_forward", "mmae_ctxproj_forward", "mmae_dechead_forward_ctx",
+             "mmae_dectail_forward", "mmae_masked_loss_forward", "mmae_masked_loss_backward", "mmae_dectail_backward",
+             "mmae_dechead_backward_ctx", "mmae_ctxproj_backward", "mmae_block_backward", "mmae_embed_backward"):
     assert name in Stub.calls, name
+assert Stub.calls.count("mmae_ctxproj_forward") == 2 and Stub.calls.count("mmae_dechead_forward_ctx") == 2 * 3
+assert Stub.calls.count("mmae_ctxproj_backward") == 2 and Stub.calls.count("mmae_dechead_backward_ctx") == 2 * 3
+# every head's backward precedes the shared projection's backward of its step
+_bw = [c for c in Stub.calls if c in ("mmae_dechead_backward_ctx", "mmae_ctxproj_backward")]
+assert _bw == ["mmae_dechead_backward_ctx"] * 3 + ["mmae_ctxproj_backward"] + ["mmae_dechead_backward_ctx"] * 3 + ["mmae_ctxproj_backward"], _bw
+assert "mmae_dechead_forward" not in Stub.calls and "mmae_dechead_backward" not in Stub.calls
 # fp32_output_adapters=["semseg"]: that adapter's head / block / tail run through the fp32-tier entry points
 assert Stub.calls.count("mmae_block_forward") == 2 * (12 + 3 * 1) and Stub.calls.count("mmae_block_f32_forward") == 2 * 1
 assert Stub.calls.count("mmae_dechead_f32_forward") == 2 and Stub.calls.count("mmae_dectail_f32_backward") == 2
