@@ -250,6 +250,25 @@ int mmae_block_forward(const float* x_in, float* x_out, int B, int N, int D, int
 int mmae_block_backward(const float* x_in, const float* dx_out, float* dx_in, int B, int N, int D, int H, int hidden,
                         const mmae_block_params* prm, const mmae_block_grads* grads, const void* saved, void* ws,
                         void* stream);
+/* Chained blocks (nn.Sequential of Blocks: the encoder, multimae/multimae.py:349, and each decoder_transformer,
+ * multimae/output_adapters.py:271).  The residual add that ends a block, `x = x + mlp(norm2(x))`
+ * (multimae/multimae_utils.py:231), is handed to the next block instead of running as a pass of its own:
+ *   forward  - y_out_bf16 != NULL: the MLP branch output is written there, x_out is not written, and the block's output is
+ *              x_mid + y_out, x_mid = mmae_block_saved_x_mid(saved);  x_add_bf16 != NULL: the block input is
+ *              x_in + x_add_bf16, formed inside the first LayerNorm kernel and written to x_sum (fp32) - the x_in to give
+ *              the backward call;
+ *   backward - dx_in_bf16 != NULL: the first LayerNorm's backward also writes bf16(dx_in) there and adds colsum(dx_in) to
+ *              dx_in_colsum (the PREVIOUS block's fc2 bias gradient);  dx_out_bf16 != NULL: that copy, made by the next
+ *              block's backward - this block's cast + bias-gradient pass over dx_out is skipped.
+ * With all optional pointers NULL the calls equal mmae_block_forward / mmae_block_backward. */
+int mmae_block_forward_chain(const float* x_in, const void* x_add_bf16, float* x_sum, float* x_out, void* y_out_bf16,
+                             int B, int N, int D, int H, int hidden, float eps, const mmae_block_params* prm, void* saved,
+                             void* ws, void* stream);
+float* mmae_block_saved_x_mid(void* saved, int B, int N, int D, int H, int hidden);
+int mmae_block_backward_chain(const float* x_in, const float* dx_out, const void* dx_out_bf16, float* dx_in,
+                              void* dx_in_bf16, float* dx_in_colsum, int B, int N, int D, int H, int hidden,
+                              const mmae_block_params* prm, const mmae_block_grads* grads, const void* saved, void* ws,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SpatialOutputAdapter, split at its decoder_transformer (multimae/output_adapters.py:236-282):

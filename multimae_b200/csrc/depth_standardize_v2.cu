@@ -14,6 +14,8 @@
 //     read from HBM once and written once.
 // Same arithmetic as variant 1: exact order statistics, fp32 per-thread partial sums, fp64 across threads and CTAs (in
 // rank order, so every CTA of a cluster holds bit-identical mean / variance).
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace mmae {
@@ -302,7 +304,13 @@ int launch_depth_standardize_v2(const float* depth, float* out, int B, int n, in
                                 cudaStream_t st) {
   // static shared memory of the kernel: 16 KB histogram copies + 2 KB merged + ~0.4 KB; keep 1 KB of slack
   const size_t budget = size_t(227) * 1024 - (DS2_COPIES * 256 * 4 + 2 * 256 * 4 + 2048);
-  for (int cs = 1; cs <= 8; cs *= 2) {
+  // smallest cluster tried first; MMAE_DEPTH_STD_MIN_CLUSTER (1 | 2 | 4 | 8) raises it: more, smaller CTAs per map
+  static const int min_cs = []() {
+    const char* e = getenv("MMAE_DEPTH_STD_MIN_CLUSTER");
+    const int v = e ? atoi(e) : 1;
+    return (v == 2 || v == 4 || v == 8) ? v : 1;
+  }();
+  for (int cs = min_cs; cs <= 8; cs *= 2) {
     const int chunk = (ceil_div(n, cs) + 3) / 4 * 4;
     if (size_t(chunk) * 4 > budget) continue;
     switch (cs) {

@@ -563,19 +563,9 @@ __global__ void __launch_bounds__(Gemm2Cfg<BN>::THREADS, 1)
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-// MMAE_GEMM_BALANCED_GRID=1 (experiment for round 2, default off, not yet measured): launch ceil(items / rounds) persistent
-// CTAs instead of min(items, SMs), rounds = ceil(items / SMs).  The makespan in rounds is unchanged (196 decoder tiles: 2
-// rounds on 148 or on 98 CTAs), but the SMs left free can host the persistent GEMM of another task decoder's stream, which
-// otherwise waits for a whole kernel: the four decoder streams only overlap their small-K GEMMs if those leave SMs free.
-static int g_gemm_balanced_grid = []() {
-  const char* e = getenv("MMAE_GEMM_BALANCED_GRID");
-  return e ? atoi(e) : 0;
-}();
-static int persistent_grid(int items, int slots) {
-  const int full = std::min(items, slots);
-  if (!g_gemm_balanced_grid || items <= 0) return full;
-  return ceil_div(items, ceil_div(items, slots));
-}
+// Persistent grid: min(items, slots) CTAs.  (Launching ceil(items / rounds) CTAs instead - 98 for a 196-tile decoder GEMM -
+// to leave SMs to the other task decoders' streams was measured on B200 and removed: 16.69 vs 16.67-16.77 ms/step.)
+static int persistent_grid(int items, int slots) { return std::min(items, slots); }
 
 template <int BN, bool A_MN, bool B_MN>
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int split_k,

@@ -8,6 +8,7 @@ the model (zeroed once per forward), and the per-parameter views are what backwa
 (data-parallel trainer), what `p.grad` permanently aliases so the arena can be all-reduced in place.
 """
 import ctypes
+import os
 import weakref
 
 import torch
@@ -35,6 +36,9 @@ class Workspace:
             cls._bufs[key] = buf
         return buf
 
+
+# consecutive Blocks hand their residual add / gradient cast over to each other (BlockStackFunction); 0: block by block
+BLOCK_CHAIN = os.environ.get("MMAE_BLOCK_CHAIN", "1") != "0"
 
 _ARENAS = weakref.WeakSet()
 
@@ -180,6 +184,101 @@ class BlockFunction(torch.autograd.Function):
         if meta.get("on_grads_ready") is not None:
             meta["on_grads_ready"](names)
         return (dx, None) + tuple(_ret_grads(arena, names, params))
+
+
+class BlockStackFunction(torch.autograd.Function):
+    """nn.Sequential of n >= 2 Blocks (the encoder, multimae/multimae.py:349; a decoder_transformer,
+    multimae/output_adapters.py:271) with the hand-offs between consecutive blocks fused (mmae_block_*_chain): the residual
+    add that ends block i runs inside block i+1's first LayerNorm kernel, and block i+1's first LayerNorm backward emits the
+    bf16 copy of the gradient and the fc2 bias gradient that block i's backward starts from.  n - 1 add passes and n - 1
+    cast + column-sum passes less than n BlockFunctions; same arithmetic.
+
+    args: x, metas (one dict per block, as for BlockFunction), then the 12 BLOCK_PARAM_NAMES tensors of every block."""
+
+    @staticmethod
+    def forward(ctx, x, metas, *params):
+        _require_cuda(x, "Block")
+        lib = L.lib()
+        n, P = len(metas), len(BLOCK_PARAM_NAMES)
+        B, N, D = x.shape
+        H, hidden, eps = metas[0]["heads"], metas[0]["hidden"], metas[0]["eps"]
+        x = x.contiguous().float()
+        dev = x.device
+        ws = Workspace.get(lib.mmae_block_workspace_bytes(B, N, D, H, hidden), dev)
+        nbytes = lib.mmae_block_saved_bytes(B, N, D, H, hidden)
+        y = torch.empty((B, N, D), dtype=torch.bfloat16, device=dev)      # MLP branch output on its way to the next block
+        out = torch.empty_like(x)
+        xs, saveds = [], []
+        x_ptr, add_ptr = x.data_ptr(), None
+        for i in range(n):
+            last = i == n - 1
+            saved = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            x_sum = torch.empty_like(x) if add_ptr is not None else None
+            prm = L.BlockParams(*[p.data_ptr() for p in params[i * P:(i + 1) * P]])
+            L.check(lib.mmae_block_forward_chain(x_ptr, add_ptr, L.ptr(x_sum), out.data_ptr() if last else None,
+                                                 None if last else y.data_ptr(), B, N, D, H, hidden, eps, ctypes.byref(prm),
+                                                 saved.data_ptr(), ws.data_ptr(), L.current_stream()),
+                    "mmae_block_forward_chain")
+            xs.append(x if x_sum is None else x_sum)
+            saveds.append(saved)
+            if not last:       # the next block's input: this block's x_mid (inside `saved`) + y
+                x_ptr, add_ptr = lib.mmae_block_saved_x_mid(saved.data_ptr(), B, N, D, H, hidden), y.data_ptr()
+        ctx.metas, ctx.params, ctx.dims = metas, params, (B, N, D, H, hidden)
+        ctx.save_for_backward(*xs, *saveds)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.lib()
+        metas, params = ctx.metas, ctx.params
+        B, N, D, H, hidden = ctx.dims
+        n, P = len(metas), len(BLOCK_PARAM_NAMES)
+        xs, saveds = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        dev = dout.device
+        ws = Workspace.get(lib.mmae_block_workspace_bytes(B, N, D, H, hidden), dev)
+        d = dout.contiguous().float()
+        g_in = None                                                        # bf16(d) handed down by the block above
+        g_bufs = [torch.empty((B, N, D), dtype=torch.bfloat16, device=dev) for _ in range(min(2, n - 1))]
+        grads = [None] * (n * P)
+        for i in reversed(range(n)):
+            arena, prefix = metas[i]["arena"], metas[i]["prefix"]
+            names = [prefix + k for k in BLOCK_PARAM_NAMES]
+            blk = params[i * P:(i + 1) * P]
+            prm = L.BlockParams(*[p.data_ptr() for p in blk])
+            grd = L.BlockGrads(*[_grad_ptr(arena, k) for k in names])
+            dx = torch.empty((B, N, D), dtype=torch.float32, device=dev)
+            g_out, below_bias = None, None
+            if i > 0:      # bf16(dx) + the fc2 bias gradient of the block below, from this block's first-LayerNorm backward
+                g_out = g_bufs[i % len(g_bufs)]
+                below_bias = _grad_ptr(metas[i - 1]["arena"], metas[i - 1]["prefix"] + "mlp.fc2.bias")
+            L.check(lib.mmae_block_backward_chain(xs[i].data_ptr(), d.data_ptr(), L.ptr(g_in), dx.data_ptr(), L.ptr(g_out),
+                                                  below_bias, B, N, D, H, hidden, ctypes.byref(prm), ctypes.byref(grd),
+                                                  saveds[i].data_ptr(), ws.data_ptr(), L.current_stream()),
+                    "mmae_block_backward_chain")
+            if metas[i].get("on_grads_ready") is not None:
+                metas[i]["on_grads_ready"](names)       # fc2.bias of block i is complete: its column sums came from block i+1
+            grads[i * P:(i + 1) * P] = _ret_grads(arena, names, blk)
+            d, g_in = dx, g_out
+        return (d, None) + tuple(grads)
+
+
+def block_stack(blocks, x):
+    """Run an nn.Sequential of multimae_utils.Block through BlockStackFunction when it applies (CUDA path, >= 2 blocks of
+    one shape bound to an arena, BLOCK_CHAIN on), else block by block."""
+    blocks = list(blocks)
+    metas = [getattr(b, "_meta", None) for b in blocks]
+    ok = (BLOCK_CHAIN and len(blocks) >= 2 and all(m is not None and m["arena"].flat.device == x.device for m in metas)
+          and not any(getattr(b, "_own_arena", False) for b in blocks)
+          and len({(b.dim, b.num_heads, b.hidden, b.norm1.eps) for b in blocks}) == 1
+          and all(b.chainable() for b in blocks))
+    if not ok:
+        for b in blocks:
+            x = b(x)
+        return x
+    flat = []
+    for b in blocks:
+        flat += list(b._params())
+    return BlockStackFunction.apply(x, metas, *flat)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -337,7 +337,7 @@ class MultiMAE(nn.Module):
             arena.begin_step()
         seq = _embed(adapters, x, ids_keep, self.global_tokens, arena, lambda d: "input_adapters.%s." % d,
                      self._grad_callback)
-        encoder_tokens = self.encoder(seq)
+        encoder_tokens = Fn.block_stack(self.encoder, seq)
         if self.output_adapters is None:
             return encoder_tokens, task_masks
 
@@ -448,7 +448,7 @@ class MultiViT(MultiMAE):
         Fn.fresh_mirrors()
         tokens, input_info = self.process_input(x)
         if not return_all_layers:
-            encoder_tokens = self.encoder(tokens)
+            encoder_tokens = Fn.block_stack(self.encoder, tokens)
         else:
             encoder_tokens = []
             for block in self.encoder:

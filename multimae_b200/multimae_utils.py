@@ -121,6 +121,10 @@ class Block(nn.Module):
                 self.attn.proj.bias, self.norm2.weight, self.norm2.bias, self.mlp.fc1.weight, self.mlp.fc1.bias,
                 self.mlp.fc2.weight, self.mlp.fc2.bias)
 
+    def chainable(self):
+        """May this block run inside functional.BlockStackFunction (no stochastic depth to apply between the blocks)?"""
+        return not isinstance(self.drop_path, DropPath)
+
     def forward(self, x, fp32=False):
         """`fp32`: run this block in the fp32 tier (a decoder block of an adapter listed in fp32_output_adapters)."""
         if isinstance(self.drop_path, DropPath):

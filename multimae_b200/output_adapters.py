@@ -161,6 +161,8 @@ class SpatialOutputAdapter(nn.Module, _PosEmbCache):
         if fp32 and isinstance(self.decoder_transformer, nn.Sequential):
             for blk in self.decoder_transformer:
                 x = blk(x, fp32=True)
+        elif isinstance(self.decoder_transformer, nn.Sequential):
+            x = Fn.block_stack(self.decoder_transformer, x)
         else:
             x = self.decoder_transformer(x)
         tail_meta = dict(self._bound, nh=nh, nw=nw, channels=self.num_channels, patch=self.P_H, fp32=bool(fp32))

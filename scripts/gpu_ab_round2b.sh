@@ -14,6 +14,5 @@ PY
 )"; }
 run default MMAE_X=0
 run ctx_per_adapter MMAE_SHARED_CTX=0
-run balanced_grid MMAE_GEMM_BALANCED_GRID=1
 run decoders_serial MMAE_DECODER_STREAMS=0
 run default_again MMAE_X=0

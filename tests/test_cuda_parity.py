@@ -228,6 +228,42 @@ def test_shared_context_projection_matches_per_adapter(golden_dir, dev, monkeypa
             assert rel_l2(g_shared[n], g_each[n]) < 1e-4, (n, rel_l2(g_shared[n], g_each[n]))
 
 
+def test_block_chain_matches_single_blocks(golden_dir, dev, monkeypatch):
+    """Consecutive Blocks with the hand-offs fused (BlockStackFunction / mmae_block_*_chain, the default) against one
+    BlockFunction per block (MMAE_BLOCK_CHAIN=0): the residual add moves into the next block's first LayerNorm kernel and the
+    gradient cast + fc2 bias gradient into its backward - the same fp32 operations on the same values, so predictions and
+    gradients must agree bit for bit except the fc2 bias gradients (column sums taken in another order).  4 encoder blocks and
+    2-block decoder transformers: both alternating hand-off buffers are in use."""
+    from multimae_b200 import functional as Fn
+    fx = _load(golden_dir, "cuda_small.pt")
+    c = dict(fx["config"], depth=4, dec_depth=2)
+    triple = ({k: v.to(dev) for k, v in fx["task_masks"].items()}, fx["ids_keep"].to(dev), fx["ids_restore"].to(dev))
+
+    def run(chain):
+        monkeypatch.setattr(Fn, "BLOCK_CHAIN", chain)
+        model = _build_model(c)
+        formula_fill_(list(model.named_parameters()))
+        model = model.to(dev).train()
+        before = L.lib().mmae_launch_count()
+        preds, _, losses = _run_cuda_step(model, fx["inputs"], triple, dev)
+        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.requires_grad}
+        return {k: v.detach().clone() for k, v in preds.items()}, grads, L.lib().mmae_launch_count() - before
+
+    p_chain, g_chain, n_chain = run(True)
+    p_single, g_single, n_single = run(False)
+    assert n_chain < n_single
+    for k in p_single:
+        assert torch.equal(p_chain[k], p_single[k]), k
+    for n in g_single:
+        if n.endswith("mlp.fc2.bias"):
+            assert rel_l2(g_chain[n], g_single[n]) < 1e-5, (n, rel_l2(g_chain[n], g_single[n]))
+        elif "norm" in n or n.endswith(".bias") or "token" in n or "emb" in n:
+            # column / row reductions that follow the hand-off read identical inputs; their own summation is deterministic
+            assert rel_l2(g_chain[n], g_single[n]) < 1e-5, (n, rel_l2(g_chain[n], g_single[n]))
+        else:
+            assert rel_l2(g_chain[n], g_single[n]) < 1e-4, (n, rel_l2(g_chain[n], g_single[n]))   # split-K reduce-add order
+
+
 FP32_TOL = 1e-3          # north_star "1e-3 rel fp32": the fp32 tier of fp32_output_adapters against the fp32 oracle
 
 

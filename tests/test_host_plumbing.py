@@ -58,6 +58,7 @@ def test_forward_backward_plumbing(stub, monkeypatch, shared_ctx):
     from multimae_b200 import multimae as MM
     from multimae_b200.criterion import MaskedCrossEntropyLoss, MaskedL1Loss, MaskedMSELoss
     monkeypatch.setattr(MM, "SHARED_CONTEXT_PROJECTION", shared_ctx)
+    monkeypatch.setattr(Fn, "BLOCK_CHAIN", shared_ctx)          # the same switch position also covers chained / single blocks
     model = _build().train()
     x = _inputs()
     preds, masks = model(x, num_encoded_tokens=12, alphas=1.0)
@@ -82,7 +83,11 @@ def test_forward_backward_plumbing(stub, monkeypatch, shared_ctx):
                  "mmae_block_backward", head_f, head_b, "mmae_dectail_forward",
                  "mmae_dectail_backward", "mmae_masked_loss_forward", "mmae_masked_loss_backward"):
         assert name in stub.calls, name
-    assert stub.calls.count("mmae_block_forward") == 2 + 4 * 1 and stub.calls.count(head_b) == 4
+    # the 2 encoder blocks run chained (one hand-off); the 4 one-block decoder transformers stay single blocks
+    chained = 2 if shared_ctx else 0
+    assert stub.calls.count("mmae_block_forward") == 2 + 4 * 1 - chained and stub.calls.count(head_b) == 4
+    assert stub.calls.count("mmae_block_forward_chain") == stub.calls.count("mmae_block_backward_chain") == chained
+    assert stub.calls.count("mmae_block_saved_x_mid") == chained // 2
     assert stub.calls.count("mmae_ctxproj_forward") == stub.calls.count("mmae_ctxproj_backward") == (1 if shared_ctx else 0)
     if shared_ctx:      # the shared projection's backward runs after the last head's, before the encoder's
         order = [c for c in stub.calls if c in (head_b, "mmae_ctxproj_backward", "mmae_block_backward")]

@@ -122,7 +122,9 @@ _bw = [c for c in Stub.calls if c in ("mmae_dechead_backward_ctx", "mmae_ctxproj
 assert _bw == ["mmae_dechead_backward_ctx"] * 3 + ["mmae_ctxproj_backward"] + ["mmae_dechead_backward_ctx"] * 3 + ["mmae_ctxproj_backward"], _bw
 assert "mmae_dechead_forward" not in Stub.calls and "mmae_dechead_backward" not in Stub.calls
 # fp32_output_adapters=["semseg"]: that adapter's head / block / tail run through the fp32-tier entry points
-assert Stub.calls.count("mmae_block_forward") == 2 * (12 + 3 * 1) and Stub.calls.count("mmae_block_f32_forward") == 2 * 1
+# the 12 encoder blocks run chained (hand-offs fused), the one-block decoder transformers as single blocks
+assert Stub.calls.count("mmae_block_forward_chain") == 2 * 12 == Stub.calls.count("mmae_block_backward_chain")
+assert Stub.calls.count("mmae_block_forward") == 2 * (3 * 1) and Stub.calls.count("mmae_block_f32_forward") == 2 * 1
 assert Stub.calls.count("mmae_dechead_f32_forward") == 2 and Stub.calls.count("mmae_dectail_f32_backward") == 2
 assert Stub.calls.count("mmae_masked_loss_forward") == 2 * 4
 assert Stub.calls.count("mmae_grad_unscale_norm") == 2                 # fused unscale + norm over the flat arena, per step
