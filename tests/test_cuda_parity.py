@@ -232,7 +232,7 @@ def test_block_chain_matches_single_blocks(golden_dir, dev, monkeypatch):
     """Consecutive Blocks with the hand-offs fused (BlockStackFunction / mmae_block_*_chain, the default) against one
     BlockFunction per block (MMAE_BLOCK_CHAIN=0): the residual add moves into the next block's first LayerNorm kernel and the
     gradient cast + fc2 bias gradient into its backward - the same fp32 operations on the same values, so predictions and
-    gradients must agree bit for bit except the fc2 bias gradients (column sums taken in another order).  4 encoder blocks and
+    gradients must agree to fp32 summation order (split-K reduce-adds, the fc2 bias column sums).  4 encoder blocks and
     2-block decoder transformers: both alternating hand-off buffers are in use."""
     from multimae_b200 import functional as Fn
     fx = _load(golden_dir, "cuda_small.pt")
@@ -253,7 +253,7 @@ def test_block_chain_matches_single_blocks(golden_dir, dev, monkeypatch):
     p_single, g_single, n_single = run(False)
     assert n_chain < n_single
     for k in p_single:
-        assert torch.equal(p_chain[k], p_single[k]), k
+        assert rel_l2(p_chain[k], p_single[k]) < 1e-6, (k, rel_l2(p_chain[k], p_single[k]))
     for n in g_single:
         if n.endswith("mlp.fc2.bias"):
             assert rel_l2(g_chain[n], g_single[n]) < 1e-5, (n, rel_l2(g_chain[n], g_single[n]))
