@@ -120,6 +120,26 @@ def build_model_and_losses(device, size="base", image=224):
 _T0 = time.perf_counter()
 
 
+_JSON_FD = None
+
+
+def _quiet_stdout():
+    """Point fd 1 at stderr for the duration of the run: native libraries write banners to it (NCCL prints its version
+    line there when the first communicator is built) and the contract is ONE JSON line on stdout.  _emit() restores it."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    sys.stdout.flush()
+    if _JSON_FD is not None:
+        os.dup2(_JSON_FD, 1)
+    print(json.dumps(obj), flush=True)
+
+
 def _note(msg):
     """progress on stderr (the JSON line on stdout stays the only stdout output)"""
     print("[bench %6.1fs] %s" % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
@@ -451,7 +471,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and args.cpu_baseline:
         _note("timing the CPU baseline sample")
         out["cpu_baseline"] = cpu_baseline_bounded(workload=args.workload)
-    print(json.dumps(out), flush=True)
+    _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -605,7 +625,7 @@ def run_reference(args, rank, world):
     base = {"value": round(value, 2), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d steps (after 1 warm-up) of fwd+4 losses+bwd+grad-norm at bs=%d on the host cores, fp32, no optimizer "
                       "update (the oracle port of the reference path; bounded step count)" % (steps, batch)}
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": wl["metric"], "value": round(value, 2), "unit": "samples/s", "n_gpus": world,
         "steps": steps, "warmup": 1, "ms_per_step": round(ms_step, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -615,7 +635,7 @@ def run_reference(args, rank, world):
                            "still ONE host process - compare it with the N = 1 line only"},
         "cpu_baseline": base,
         "e2e": {"value": round(value, 2), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def main():
@@ -640,15 +660,15 @@ def main():
     args = ap.parse_args()
     if args.batch is None:
         args.batch = WORKLOADS[args.workload]["batch"]
+    _quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "cpu-baseline":
-        print(json.dumps(cpu_baseline(sample_steps=2, batch=4 if args.workload == "cfg2" else 2, workload=args.workload)),
-              flush=True)
+        _emit(cpu_baseline(sample_steps=2, batch=4 if args.workload == "cfg2" else 2, workload=args.workload))
         return
     if args.impl == "gpu-eager":
-        print(json.dumps(gpu_eager_baseline(args.workload)), flush=True)
+        _emit(gpu_eager_baseline(args.workload))
         return
     if args.impl == "reference":
         run_reference(args, rank, world)

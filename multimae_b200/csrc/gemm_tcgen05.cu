@@ -963,7 +963,11 @@ extern "C" int mmae_gemm_bf16(const void* A, int64_t lda, int a_mn_major, const 
     }
     // CTA-pair kernels (256-row tiles, rounds counted in pairs): measured +3..6 % on the big encoder GEMMs (N*K >= 2 M
     // elements: fc1 / fc2 forward, fc2 dgrad), slower on short-K or narrow problems - only those shapes are candidates.
-    if (split_k == 1 && g_gemm_pair && M >= 2048 && long(N) * K >= 2000000L && sms >= 2) {
+    static const long pair_min_nk = []() {
+      const char* e = getenv("MMAE_GEMM_PAIR_NK");
+      return e ? atol(e) : 2000000L;
+    }();
+    if (split_k == 1 && g_gemm_pair && M >= 2048 && long(N) * K >= pair_min_nk && sms >= 2) {
       const int tm2 = ceil_div(M, 2 * BM);
       const int pair_bn[2] = {192, 256};
       const int pair_var[2] = {5, 4};
