@@ -95,8 +95,9 @@ if __name__ == "__main__":
     a = ap.parse_args()
     summ = main(a.csv)
     if a.json:
-        gk = a.gemm or next((k for k in summ if k.startswith("gemm")), None)
-        out = {"commit": a.commit, "when": datetime.datetime.utcnow().strftime("%Y-%m-%dT%H:%MZ"),
+        summ = {k: v for k, v in summ.items() if not k.startswith("at::")}      # L2-flush fills between the profiled launches
+        gk = a.gemm or next((k for k in summ if "gemm" in k), None)
+        out = {"commit": a.commit, "when": datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%dT%H:%MZ"),
                "how": "ncu --set full --clock-control none, L2 flushed before each profiled launch (scripts/gpu_ncu_targets.py)",
                "kernels": summ}
         if gk:
