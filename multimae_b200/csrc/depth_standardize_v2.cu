@@ -1,7 +1,9 @@
-// Truncated depth standardisation, second version — EXPERIMENTAL, NOT YET RUN ON HARDWARE (written after round 1's GPU
-// budget was spent; selected only by mmae_standardize_depth_set_variant(2) / MMAE_DEPTH_STD_VARIANT=2, the default stays
-// the validated kernel of depth_standardize.cu).  scripts/gpu_check_depth_standardize_v2.py checks it against the oracle
-// and against variant 1 and times both.
+// Truncated depth standardisation, second version - the default since round 2 (mmae_standardize_depth_set_variant(1) /
+// MMAE_DEPTH_STD_VARIANT=1 select the kernel of depth_standardize.cu).  Validated on B200 against the oracle fixtures
+// (tests/test_cuda_kernels.py) and timed (profiles/r02_depth_standardize_timing.log): 193 us at 128 x 224^2, 205 us at
+// 32 x 448^2 (variant 1: 195 / 860 us; the reference's torch.sort expression: 747 / 557 us).  Both variants are latency-bound
+// shared-memory selects at 0.04 of the 8 B/pixel HBM figure; clusters larger than the map needs are slower
+// (MMAE_DEPTH_STD_MIN_CLUSTER: 214 / 270 / 545 us for 2 / 4 / 8 CTAs at 224^2).
 //
 // What the round-1 measurement showed (profiles/r01_depth_standardize_timing.log): variant 1 runs at 0.04 of the 8 B/pixel
 // HBM bound.  Its first radix-select pass funnels 32 warps into a handful of shared-memory histogram bins (depth maps use
