@@ -399,7 +399,8 @@ class MultiMAE(nn.Module):
             self._dec_streams = [torch.cuda.Stream(device=dev) for _ in domains]
         main = torch.cuda.current_stream(dev)
         ready = main.record_event()
-        for sh in list(shared.values())[:1]:          # allocated on this stream, read / written on the decoders' streams
+        if shared:                                    # allocated on this stream, read / written on the decoders' streams
+            sh = next(iter(shared.values()))          # every entry carries the same projection tensor and state
             for st in self._dec_streams:
                 sh["ctx"].record_stream(st)
                 if sh["state"].get("dctx") is not None:

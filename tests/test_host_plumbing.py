@@ -209,3 +209,121 @@ def test_train_step_eager_and_sampling_options(stub):
     assert "mmae_sample_masks" in stub.calls and "mmae_standardize_depth" not in stub.calls
     a = model.sample_alphas(64, 3, alphas=[1.0, 1.0, 1.0])
     assert a.shape == (64, 3) and bool(((a > 0.5).sum(1) >= 1).all())      # never the all-zero task subset (:150)
+
+
+def test_block_stack_hand_off_pointers(monkeypatch):
+    """BlockStackFunction wires consecutive blocks through raw pointers: block i+1 must receive block i's x_mid (inside
+    block i's `saved` buffer) as x_in and the shared MLP-output buffer as x_add; only the last block writes x_out; in backward
+    block i+1 writes bf16(dx) into the buffer block i then reads, and its column sums into block i's fc2 bias gradient."""
+    from multimae_b200.multimae_utils import Block
+    calls = []
+
+    class Rec:
+        def __getattr__(self, name):
+            res, argtypes = L.SIGNATURES[name]
+
+            def fn(*args):
+                assert len(args) == len(argtypes), name
+                calls.append((name, args))
+                if name.endswith("_bytes"):
+                    return 4096
+                if name == "mmae_block_saved_x_mid":
+                    return args[0] + 64                     # "x_mid lives 64 bytes into the saved buffer"
+                return 0
+            return fn
+
+    rec = Rec()
+    monkeypatch.setattr(L, "lib", lambda: rec)
+    monkeypatch.setattr(L, "current_stream", lambda: 0)
+    monkeypatch.setattr(Fn, "_require_cuda", lambda t, what: None)
+    monkeypatch.setattr(Fn, "BLOCK_CHAIN", True)
+    blocks = torch.nn.Sequential(*[Block(128, 2, qkv_bias=True) for _ in range(4)])
+    named = [(n, p) for n, p in blocks.named_parameters()]
+    arena = Fn.GradArena(named, torch.device("cpu"))
+    ready = []
+    for i, b in enumerate(blocks):
+        b.bind(arena, "%d." % i, lambda names: ready.append(list(names)))
+    x = torch.randn(2, 5, 128, requires_grad=True)
+    out = Fn.block_stack(blocks, x)
+    fwd = [a for n, a in calls if n == "mmae_block_forward_chain"]
+    mids = [a for n, a in calls if n == "mmae_block_saved_x_mid"]
+    assert len(fwd) == 4 and len(mids) == 3 and not [n for n, _ in calls if n == "mmae_block_forward"]
+    # args: x_in, x_add, x_sum, x_out, y_out, ..., saved (index 12)
+    assert fwd[0][0] == x.data_ptr() and fwd[0][1] is None and fwd[0][2] is None        # first block: plain input
+    y_buf = fwd[0][4]
+    assert y_buf is not None and fwd[0][3] is None                                       # not the last: y_out, no x_out
+    for i in (1, 2, 3):
+        assert fwd[i][0] == fwd[i - 1][12] + 64                  # x_in = x_mid of the block before (inside ITS saved buffer)
+        assert fwd[i][1] == y_buf and fwd[i][2] is not None      # x_add = the MLP branch output; the sum is materialised
+    assert fwd[3][3] == out.data_ptr() and fwd[3][4] is None    # the last block adds by itself
+    assert len({a[12] for a in fwd}) == 4 and len({a[2] for a in fwd[1:]}) == 3          # own saved / x_sum buffers
+    out.sum().backward()
+    bwd = [a for n, a in calls if n == "mmae_block_backward_chain"]
+    assert len(bwd) == 4
+    # args: x_in, dx_out, dx_out_bf16, dx_in, dx_in_bf16, dx_in_colsum, ...; issued for blocks 3, 2, 1, 0
+    assert bwd[0][2] is None and bwd[3][4] is None and bwd[3][5] is None
+    for k in (1, 2, 3):
+        assert bwd[k][1] == bwd[k - 1][3]                        # dx_out = the dx_in the block above produced
+        assert bwd[k][2] == bwd[k - 1][4] is not None            # ... and its bf16 copy
+        blk = 3 - k                                              # this call's block; the one above added into ITS fc2 bias slot
+        assert bwd[k - 1][5] == arena.views["%d.mlp.fc2.bias" % blk].data_ptr()
+        assert bwd[k][4] != bwd[k][2] or bwd[k][4] is None       # never reads and writes the same hand-off buffer
+    # the saved x_in of backward is what forward used: x for block 0, the materialised sums above
+    assert bwd[3][0] == x.data_ptr() and [b[0] for b in bwd[:3]] == [fwd[3][2], fwd[2][2], fwd[1][2]]
+    assert [r[0].split(".")[0] for r in ready] == ["3", "2", "1", "0"] and all(len(r) == 12 for r in ready)
+    assert x.grad is not None and x.grad.shape == x.shape
+
+
+def test_shared_context_projection_pointers(monkeypatch):
+    """SharedContextFunction / DecoderHeadFunction wiring: every head reads its column segment of the ONE projection output and
+    writes its bf16 context gradient into the matching segment of the ONE gradient matrix that mmae_ctxproj_backward consumes;
+    the four proj_context weights (and their gradient slots) are handed over in adapter order and lie back to back."""
+    from multimae_b200 import multimae as MM
+    from multimae_b200.criterion import MaskedMSELoss
+    calls = []
+
+    class Rec:
+        def __getattr__(self, name):
+            res, argtypes = L.SIGNATURES[name]
+
+            def fn(*args):
+                assert len(args) == len(argtypes), name
+                calls.append((name, args))
+                return 4096 if name.endswith("_bytes") else 0
+            return fn
+
+    rec = Rec()
+    monkeypatch.setattr(L, "lib", lambda: rec)
+    monkeypatch.setattr(L, "current_stream", lambda: 0)
+    monkeypatch.setattr(Fn, "_require_cuda", lambda t, what: None)
+    monkeypatch.setattr(MM, "SHARED_CONTEXT_PROJECTION", True)
+    model = _build().train()
+    x = _inputs()
+    preds, masks = model(x, num_encoded_tokens=12, alphas=1.0)
+    order = list(preds)                                              # adapter order = column-segment order
+    dims = [model.output_adapters[k].dim_tokens for k in order]
+    offs = [sum(dims[:i]) for i in range(len(dims))]
+    (pf,) = [a for n, a in calls if n == "mmae_ctxproj_forward"]
+    prm = pf[3]._obj
+    arena = model.grad_arena()
+    assert prm.num == len(order) and list(prm.dim)[:len(order)] == dims
+    for i, k in enumerate(order):
+        ad = model.output_adapters[k]
+        assert prm.weight[i] == ad.proj_context.weight.data_ptr() and prm.bias[i] == ad.proj_context.bias.data_ptr()
+    ctx_ptr = pf[4]
+    heads = [a for n, a in calls if n == "mmae_dechead_forward_ctx"]
+    assert [h[0] for h in heads] == [ctx_ptr + 4 * o for o in offs] and all(h[1] == sum(dims) for h in heads)
+    assert all(h[6]._obj.proj_context_w is None for h in heads)       # the weight belongs to the shared GEMM
+    loss = sum(MaskedMSELoss(16, 1)(preds[k].float(), torch.zeros_like(preds[k]), mask=None) for k in preds)
+    loss.backward()
+    (pb,) = [a for n, a in calls if n == "mmae_ctxproj_backward"]
+    dctx_ptr = pb[4]
+    hb = {a[6]: a for n, a in calls if n == "mmae_dechead_backward_ctx"}
+    assert sorted(hb) == [dctx_ptr + 2 * o for o in offs] and all(a[7] == sum(dims) for a in hb.values())
+    grd = pb[3]._obj
+    for i, k in enumerate(order):
+        assert grd.weight[i] == arena.views["output_adapters.%s.proj_context.weight" % k].data_ptr()
+        seg = hb[dctx_ptr + 2 * offs[i]]
+        assert seg[4]._obj.proj_context_b == arena.views["output_adapters.%s.proj_context.bias" % k].data_ptr()
+        assert seg[4]._obj.proj_context_w is None
+    assert all(grd.weight[i + 1] == grd.weight[i] + 4 * dims[i] * pf[2] for i in range(len(order) - 1))   # back to back
