@@ -175,6 +175,28 @@ def test_c_abi_rejects_bad_arguments_before_any_launch():
         (lib.mmae_attention_forward(16, 64, 16, 64, 16, 64, 16, 64, None, 1, 1, 8, 8, 48, 0.1, None), UNSUPPORTED, b"head_dim 48"),
         (lib.mmae_masked_loss_forward(5, 0, 0.0, 16, 16, None, 1, 3, 32, 32, 16, 16, 16, None), UNSUPPORTED, b"kind"),
     ]
+    # round-2 entry points: shared context projection, *_ctx heads, chained blocks
+    cp = L.CtxProjParams()
+    cp.num = 2
+    cp.dim[0], cp.dim[1] = 256, 100                                      # 100 is not a multiple of 8
+    cp.weight[0] = cp.weight[1] = cp.bias[0] = cp.bias[1] = 16
+    bp, bg = L.BlockParams(), L.BlockGrads()
+    cases += [
+        (lib.mmae_ctxproj_forward(16, 128, 768, ctypes.byref(cp), 16, 16, None), ARG, b"mmae_ctxproj_forward"),
+        (lib.mmae_ctxproj_forward(None, 128, 768, ctypes.byref(cp), 16, 16, None), ARG, b"mmae_ctxproj_forward"),
+        (lib.mmae_ctxproj_backward(128, 768, ctypes.byref(cp), ctypes.byref(L.CtxProjGrads()), None, 16, 16, None), ARG,
+         b"mmae_ctxproj_backward"),
+        (lib.mmae_dechead_forward_ctx(None, 1024, None, 8, 1024, 1e-6, None, None, None, None, None), ARG, b"bad args"),
+        (lib.mmae_dechead_backward_ctx(None, 8, 1024, None, None, None, None, 1024, None, None, None), ARG, b"bad args"),
+        # x_add without a buffer for the sum; neither x_out nor y_out; a bf16 gradient copy without its column-sum target
+        (lib.mmae_block_forward_chain(16, 16, None, 16, None, 2, 8, 128, 2, 512, 1e-6, ctypes.byref(bp), 16, 16, None), ARG,
+         b"mmae_block_forward"),
+        (lib.mmae_block_forward_chain(16, None, None, None, None, 2, 8, 128, 2, 512, 1e-6, ctypes.byref(bp), 16, 16, None), ARG,
+         b"mmae_block_forward"),
+        (lib.mmae_block_backward_chain(16, 16, None, 16, 16, None, 2, 8, 128, 2, 512, ctypes.byref(bp), ctypes.byref(bg), 16,
+                                       16, None), ARG, b"mmae_block_backward"),
+    ]
+    assert lib.mmae_block_saved_x_mid(None, 2, 8, 128, 2, 512) is None
     # mmae_last_error() holds the message of the most recent failure: re-issue each call to read its own message
     assert [rc for rc, _, _ in cases] == [want for _, want, _ in cases]
     assert lib.mmae_gemm_bf16(16, 64, 0, 16, 64, 0, 128, 100, 64, 1, ctypes.byref(ep), None) == ARG
